@@ -1,0 +1,139 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/model) on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container:  ``python oracle/make_goldens.py``.
+Inputs are windows of the reference's own real-token fixture ``test/prefix_test.npy``; parameters are
+regenerated from a seed by ``txl_oracle.init_params`` (so the 13.7 M-parameter real-size case needs no
+55 MB file).  The reference runs in float64 (``model.double()``), dropout 0, so the goldens pin the
+arithmetic far below any tolerance used later (fp32 mode 1e-4, bf16 1e-2).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness  # noqa: E402
+import txl_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+PREFIX = "/root/reference/test/prefix_test.npy"
+
+
+def token_stream(B, total_len, offset=0):
+    """[total_len+1, B] int64 windows of prefix_test.npy, one contiguous stretch per batch column."""
+    a = np.load(PREFIX).astype(np.int64)
+    per = (len(a) - offset) // B
+    assert per > total_len
+    cols = [a[offset + b * per: offset + b * per + total_len + 1] for b in range(B)]
+    return torch.from_numpy(np.stack(cols, 1))
+
+
+def run_mle_case(name, shape: O.TxlShape, seed, Q, B, nseg, reset_at=None, full_mems=True):
+    params = O.init_params(shape, seed, dtype=torch.float64)
+    model = ref_harness.build_reference_lm(shape, params, Q, dtype=torch.float64)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    stream = token_stream(B, Q * nseg)
+    mems = None
+    out = {"seed": seed, "Q": Q, "B": B, "nseg": nseg,
+           "shape": np.array([shape.n_layer, shape.n_head, shape.d_model, shape.d_inner, shape.n_token,
+                              shape.mem_len, int(shape.same_length), shape.clamp_len, int(shape.pre_lnorm)])}
+    model.zero_grad()
+    for s in range(nseg):
+        data = stream[s * Q:(s + 1) * Q].contiguous()
+        target = stream[s * Q + 1:(s + 1) * Q + 1].contiguous()
+        reset = torch.zeros(B, dtype=torch.bool)
+        if reset_at is not None and s == reset_at[0]:
+            reset[reset_at[1]] = True
+        loss, mems = model(data, target, reset, mems)
+        (loss.mean()).backward()
+        out[f"data{s}"] = data.numpy()
+        out[f"target{s}"] = target.numpy()
+        out[f"reset{s}"] = reset.numpy()
+        out[f"loss{s}"] = loss.detach().numpy()
+    m = mems.detach().numpy()
+    out["mems_shape"] = np.array(m.shape)
+    if full_mems:
+        out["mems"] = m
+    else:
+        out["mems_slice"] = m[:, :, :, ::7].astype(np.float64)
+    sd_grads = {}
+    for k, p in model.named_parameters():
+        if k == "crit.out_layers.0.weight":
+            continue
+        sd_grads[k] = p.grad.detach()
+    for k, g in sd_grads.items():
+        key = k.replace(".", "/")
+        out["gnorm:" + key] = np.array(g.norm().item())
+        flat = g.reshape(-1)
+        if flat.numel() <= 4096:
+            out["grad:" + key] = g.numpy()
+        else:
+            idx = torch.linspace(0, flat.numel() - 1, 2048).long()
+            out["gidx:" + key] = idx.numpy()
+            out["gval:" + key] = flat[idx].numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, "loss0 mean", float(out["loss0"].mean()))
+
+
+def run_generate_case(name, shape: O.TxlShape, seed, B, T, temperature):
+    """forward_generate: incremental-with-memory vs one-shot (generate.py:309-327 invariance) and
+    forward_generate_gumbel with injected uniform noise."""
+    params = O.init_params(shape, seed, dtype=torch.float64)
+    model = ref_harness.build_reference_lm(shape, params, 1, dtype=torch.float64)
+    stream = token_stream(B, T, offset=1234)
+    data = stream[:T].contiguous()
+    out = {"seed": seed, "B": B, "T": T, "temperature": temperature, "data": data.numpy(),
+           "shape": np.array([shape.n_layer, shape.n_head, shape.d_model, shape.d_inner, shape.n_token,
+                              shape.mem_len, int(shape.same_length), shape.clamp_len, int(shape.pre_lnorm)])}
+    with torch.no_grad():
+        full_logits, full_mems = model.forward_generate(data, None)
+        mems = None
+        inc = []
+        for t in range(T):
+            lg, mems = model.forward_generate(data[t:t + 1], mems)
+            inc.append(lg)
+        inc = torch.cat(inc, 0)
+        out["full_logits"] = full_logits.numpy()
+        out["inc_logits"] = inc.numpy()
+        out["full_mems"] = full_mems.numpy()
+        out["inc_mems"] = mems.numpy()
+        # gumbel: context of 3 tokens, then 4 sampled steps fed back as hard ids
+        g = torch.Generator().manual_seed(seed + 1)
+        U = [torch.rand(1, B, shape.n_token, generator=g, dtype=torch.float64) for _ in range(4)]
+        _, mems = model.forward_generate(data[:3], None)
+        inp = data[3:4]
+        sts, ids = [], []
+        with ref_harness.injected_uniform(U):
+            for t in range(4):
+                st, mems = model.forward_generate_gumbel(inp, temperature, mems)
+                sts.append(st)
+                inp = st.argmax(-1)
+                ids.append(inp)
+        out["gumbel_U"] = torch.cat(U, 0).numpy()
+        out["gumbel_st"] = torch.cat(sts, 0).numpy()
+        out["gumbel_ids"] = torch.cat(ids, 0).numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    tiny = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=16)
+    run_mle_case("mle_tiny", tiny, seed=11, Q=8, B=3, nseg=4, reset_at=(2, 1))
+    tiny_sl = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=12, same_length=True,
+                         clamp_len=15)
+    run_mle_case("mle_tiny_samelen", tiny_sl, seed=12, Q=8, B=2, nseg=4, reset_at=(1, 0))
+    real = O.TxlShape(n_layer=6, n_head=10, d_model=500, d_inner=1000, n_token=310, mem_len=24)
+    run_mle_case("mle_real", real, seed=13, Q=16, B=2, nseg=3, reset_at=(2, 1), full_mems=False)
+    gen = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=64, same_length=True)
+    run_generate_case("generate_tiny", gen, seed=14, B=2, T=12, temperature=0.7)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,313 @@
+"""CPU oracle for the Transformer-XL generator / GAN-step hot path.
+
+TEST INFRASTRUCTURE ONLY.  This file is a CPU restatement (torch on the host, fp32 or fp64) of the
+algorithm in the reference's ``model/mem_transformer.py``, ``model/utils/proj_adaptive_softmax.py``
+and the sampling part of ``model/transformer_gan.py``.  It may be imported only by ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` -- as
+the checker or the timed CPU baseline, never as the product path.  The product path
+(``transformer-gan_b200/``) never imports it and fails loudly when the CUDA library is missing.
+
+Parity status: **pinned**.  The reference's own tests hold no numerical fixture for this path
+(SURVEY.md section 4), so the pins are golden vectors produced by running the unmodified reference
+modules in the build container (``oracle/make_goldens.py`` -> ``tests/golden/*.npz``);
+``tests/test_oracle_golden.py`` checks this restatement against every one of them.
+
+The restatement is deliberately *not* a transcription: the reference builds the relative shift with a
+pad/reshape trick and the mask as a materialised bool tensor; here both are closed-form index
+arithmetic, which is also what the CUDA kernels implement.  Gradients come from
+autograd over this restatement (fp64 capable).
+
+All ``file:line`` citations are relative to ``/root/reference/model``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass
+class TxlShape:
+    """Hyper-parameters of MemTransformerLM (mem_transformer.py:351-367)."""
+    n_layer: int
+    n_head: int
+    d_model: int
+    d_inner: int
+    n_token: int
+    mem_len: int
+    same_length: bool = False
+    clamp_len: int = -1
+    pre_lnorm: bool = False
+
+    @property
+    def d_head(self) -> int:
+        return self.d_model // self.n_head  # mem_transformer.py:354
+
+
+# ----------------------------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------------------------
+def param_names(shape: TxlShape) -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict names / shapes of the generator (SURVEY.md section 5 'Checkpoint / resume')."""
+    D, N, dh, DI, V = shape.d_model, shape.n_head, shape.d_head, shape.d_inner, shape.n_token
+    out = [("r_w_bias", (N, dh)), ("r_r_bias", (N, dh)), ("word_emb.emb_layers.0.weight", (V, D))]
+    for i in range(shape.n_layer):
+        p = f"layers.{i}."
+        out += [
+            (p + "dec_attn.qkv_net.weight", (3 * N * dh, D)),
+            (p + "dec_attn.o_net.weight", (D, N * dh)),
+            (p + "dec_attn.layer_norm.weight", (D,)),
+            (p + "dec_attn.layer_norm.bias", (D,)),
+            (p + "dec_attn.r_net.weight", (N * dh, D)),
+            (p + "pos_ff.CoreNet.0.weight", (DI, D)),
+            (p + "pos_ff.CoreNet.0.bias", (DI,)),
+            (p + "pos_ff.CoreNet.3.weight", (D, DI)),
+            (p + "pos_ff.CoreNet.3.bias", (D,)),
+            (p + "pos_ff.layer_norm.weight", (D,)),
+            (p + "pos_ff.layer_norm.bias", (D,)),
+        ]
+    out += [("crit.out_layers.0.bias", (V,))]  # crit.out_layers.0.weight is tied to the embedding (:411-413)
+    return out
+
+
+def init_params(shape: TxlShape, seed: int, std: float = 0.02, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Deterministic synthetic parameters (CPU generator).  Not the reference's init distribution on
+    purpose: std 0.02 and non-zero biases / LN offsets make every term observable in parity tests."""
+    g = torch.Generator().manual_seed(seed)
+    params = {}
+    for name, shp in param_names(shape):
+        if name.endswith("layer_norm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith("bias") and "r_" not in name:
+            t = 0.05 * torch.randn(shp, generator=g)
+        elif name in ("r_w_bias", "r_r_bias"):
+            t = 0.2 * torch.randn(shp, generator=g)
+        elif "emb_layers" in name:
+            t = 0.05 * torch.randn(shp, generator=g)
+        else:
+            t = std * 2.5 * torch.randn(shp, generator=g)
+        params[name] = t.to(dtype)
+    return params
+
+
+# ----------------------------------------------------------------------------------------------
+# A1  positional embedding                                     mem_transformer.py:13-23, 550-555
+# ----------------------------------------------------------------------------------------------
+def positional_embedding(klen: int, d_model: int, clamp_len: int = -1, dtype=torch.float32) -> torch.Tensor:
+    """pos_emb[p] = [sin(d_p f), cos(d_p f)], d_p = klen-1-p, f_t = 10000^(-2t/D).  Returns [klen, D]."""
+    # the reference builds inv_freq once, in float32, as a registered buffer (mem_transformer.py:13-14); later
+    # .to(dtype)/.double() only widens those rounded values -- reproduce that rounding exactly.
+    inv_freq = (1 / (10000 ** (torch.arange(0.0, d_model, 2.0) / d_model))).to(dtype)
+    pos_seq = torch.arange(klen - 1, -1, -1.0, dtype=dtype)
+    if clamp_len > 0:
+        pos_seq = pos_seq.clamp(max=clamp_len)
+    ang = pos_seq[:, None] * inv_freq[None, :]
+    return torch.cat([ang.sin(), ang.cos()], dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# A3  attention mask (True = masked), closed form             mem_transformer.py:495-547
+# ----------------------------------------------------------------------------------------------
+def attn_mask(qlen: int, mlen: int, mem_len: int, same_length: bool,
+              reset_mems: Optional[torch.Tensor], bsz: int) -> torch.Tensor:
+    """[B, Q, K] bool.  masked iff j > i+M  or  (same_length and j <= i - msl)  or  (reset[b] and j < M)."""
+    klen = qlen + mlen
+    i = torch.arange(qlen)[:, None]
+    j = torch.arange(klen)[None, :]
+    m = j > i + mlen                                           # triu(ones, 1+mlen)           :525-527
+    if same_length:
+        mask_len = klen - mem_len                              #                               :499-503
+        msl = qlen - mask_len if mask_len > 0 else qlen
+        m = m | (j <= i - msl)                                 # tril(ones, -mask_shift_len)   :520
+    m = m[None].repeat(bsz, 1, 1)
+    if reset_mems is not None and mlen > 0:
+        m[reset_mems.bool(), :, :mlen] = True                  #                               :529
+    return m
+
+
+# ----------------------------------------------------------------------------------------------
+# A4  relative-position attention (post-LN / pre-LN)           mem_transformer.py:162-257
+# ----------------------------------------------------------------------------------------------
+def rel_shift_gather(bd_raw: torch.Tensor, qlen: int) -> torch.Tensor:
+    """_rel_shift (mem_transformer.py:133-147) as index arithmetic: out[..., i, j] = x[..., i, j+Q-1-i].
+    Entries with j+Q-1-i >= K (always masked: j > i+M) are set to 0 instead of the reference's wrap-around
+    garbage."""
+    klen = bd_raw.shape[-1]
+    i = torch.arange(qlen)[:, None]
+    j = torch.arange(klen)[None, :]
+    src = j + qlen - 1 - i
+    valid = src < klen
+    src = src.clamp(max=klen - 1)
+    out = torch.gather(bd_raw, -1, src.expand(bd_raw.shape[:-2] + src.shape))
+    return out * valid.to(out.dtype)
+
+
+def rel_attn(w: torch.Tensor, mem: Optional[torch.Tensor], pos_emb: torch.Tensor, p: Dict[str, torch.Tensor],
+             prefix: str, r_w_bias: torch.Tensor, r_r_bias: torch.Tensor, mask: torch.Tensor,
+             shape: TxlShape) -> torch.Tensor:
+    """w [Q,B,D], mem [M,B,D] or None, pos_emb [K,D] -> [Q,B,D]."""
+    Q, B, D = w.shape
+    N, dh = shape.n_head, shape.d_head
+    Wqkv = p[prefix + "dec_attn.qkv_net.weight"]
+    Wq, Wk, Wv = Wqkv[: N * dh], Wqkv[N * dh: 2 * N * dh], Wqkv[2 * N * dh:]      # chunk(3)   :173
+    ln_w, ln_b = p[prefix + "dec_attn.layer_norm.weight"], p[prefix + "dec_attn.layer_norm.bias"]
+    x = w if mem is None or mem.numel() == 0 else torch.cat([mem, w], 0)            #            :166
+    xin, win = x, w
+    if shape.pre_lnorm:                                                               #            :167-168
+        xin = F.layer_norm(x, (D,), ln_w, ln_b)
+        win = xin[-Q:]
+    K = x.shape[0]
+    q = (win @ Wq.t()).view(Q, B, N, dh)               # Q-projection of memory rows is discarded   :174
+    k = (xin @ Wk.t()).view(K, B, N, dh)
+    v = (xin @ Wv.t()).view(K, B, N, dh)
+    r = (pos_emb @ p[prefix + "dec_attn.r_net.weight"].t()).view(K, N, dh)           #            :171
+    ac = torch.einsum("ibnd,jbnd->bnij", q + r_w_bias, k)                            #            :201-204
+    bd = rel_shift_gather(torch.einsum("ibnd,jnd->bnij", q + r_r_bias, r), Q)        #            :206-210
+    s = (ac + bd) * (1.0 / math.sqrt(dh))                                            #            :213-214
+    s = s.masked_fill(mask[:, None], float("-inf"))                                  #            :225
+    prob = torch.softmax(s, dim=-1)                                                  #            :228
+    a = torch.einsum("bnij,jbnd->ibnd", prob, v).reshape(Q, B, N * dh)               #            :239-244
+    out = a @ p[prefix + "dec_attn.o_net.weight"].t()                                #            :247
+    if shape.pre_lnorm:
+        return w + out                                                               #            :252
+    return F.layer_norm(w + out, (D,), ln_w, ln_b)                                   #            :255
+
+
+# ----------------------------------------------------------------------------------------------
+# A5  position-wise FFN                                        mem_transformer.py:46-60
+# ----------------------------------------------------------------------------------------------
+def pos_ff(x: torch.Tensor, p: Dict[str, torch.Tensor], prefix: str, shape: TxlShape) -> torch.Tensor:
+    D = x.shape[-1]
+    ln_w, ln_b = p[prefix + "pos_ff.layer_norm.weight"], p[prefix + "pos_ff.layer_norm.bias"]
+    inp = F.layer_norm(x, (D,), ln_w, ln_b) if shape.pre_lnorm else x
+    h = torch.relu(inp @ p[prefix + "pos_ff.CoreNet.0.weight"].t() + p[prefix + "pos_ff.CoreNet.0.bias"])
+    y = h @ p[prefix + "pos_ff.CoreNet.3.weight"].t() + p[prefix + "pos_ff.CoreNet.3.bias"]
+    if shape.pre_lnorm:
+        return y + x
+    return F.layer_norm(x + y, (D,), ln_w, ln_b)
+
+
+# ----------------------------------------------------------------------------------------------
+# A2 + A8 + A7  embedding, layer stack, memory update          mem_transformer.py:319-341, 484-576, 445-482
+# ----------------------------------------------------------------------------------------------
+def embed(inp: torch.Tensor, E: torch.Tensor, d_model: int) -> torch.Tensor:
+    """index path (2-D int64 [Q,B]) or soft path (3-D float [Q,B,V]); both scaled by sqrt(D)."""
+    e = E[inp] if inp.dim() == 2 else inp.to(E.dtype) @ E
+    return e * math.sqrt(d_model)
+
+
+def update_mems(hids: List[torch.Tensor], mems: Optional[torch.Tensor], mem_len: int) -> torch.Tensor:
+    """new_mems = last mem_len rows of [mems; hids] per slab, detached (mem_transformer.py:461-475)."""
+    stacked = torch.stack(hids).detach()
+    cat = stacked if mems is None or mems.numel() == 0 else torch.cat([mems.detach(), stacked], 1)
+    end = cat.shape[1]
+    return cat[:, max(0, end - mem_len): end]
+
+
+def core_forward(inp: torch.Tensor, reset_mems: Optional[torch.Tensor], mems: Optional[torch.Tensor],
+                 p: Dict[str, torch.Tensor], shape: TxlShape) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """MemTransformerLM._forward with dropout 0.  Returns (core_out [Q,B,D], new_mems [L+1,M',B,D])."""
+    E = p["word_emb.emb_layers.0.weight"]
+    x = embed(inp, E, shape.d_model)
+    Q, B = x.shape[0], x.shape[1]
+    M = 0 if mems is None or mems.numel() == 0 else mems.shape[1]
+    K = Q + M
+    mask = attn_mask(Q, M, shape.mem_len, shape.same_length, reset_mems, B)
+    pe = positional_embedding(K, shape.d_model, shape.clamp_len, dtype=x.dtype)
+    hids = [x]
+    for l in range(shape.n_layer):
+        pre = f"layers.{l}."
+        mem_l = None if M == 0 else mems[l]
+        x = rel_attn(x, mem_l, pe, p, pre, p["r_w_bias"], p["r_r_bias"], mask, shape)
+        x = pos_ff(x, p, pre, shape)
+        hids.append(x)
+    new_mems = update_mems(hids, mems, shape.mem_len) if shape.mem_len > 0 else None
+    return x, new_mems
+
+
+# ----------------------------------------------------------------------------------------------
+# A9  logits + NLL                                             proj_adaptive_softmax.py:50-84
+# ----------------------------------------------------------------------------------------------
+def logits_of(hidden: torch.Tensor, p: Dict[str, torch.Tensor]) -> torch.Tensor:
+    return hidden @ p["word_emb.emb_layers.0.weight"].t() + p["crit.out_layers.0.bias"]
+
+
+def mle_forward(data: torch.Tensor, target: torch.Tensor, reset_mems: Optional[torch.Tensor],
+                mems: Optional[torch.Tensor], p: Dict[str, torch.Tensor], shape: TxlShape):
+    """MemTransformerLM.forward (mem_transformer.py:653-670): returns (nll [Q,B], new_mems)."""
+    hid, new_mems = core_forward(data, reset_mems, mems, p, shape)
+    T = target.shape[0]
+    lg = logits_of(hid[-T:].reshape(-1, shape.d_model), p)
+    nll = torch.logsumexp(lg, -1) - lg.gather(1, target.reshape(-1, 1)).squeeze(1)
+    return nll.view(T, -1), new_mems
+
+
+def generate_logits(data: torch.Tensor, mems, p, shape: TxlShape):
+    """forward_generate (mem_transformer.py:578-600): returns (logits [T,B,V], new_mems)."""
+    hid, new_mems = core_forward(data, None, mems, p, shape)
+    return logits_of(hid, p), new_mems
+
+
+# ----------------------------------------------------------------------------------------------
+# A10  Gumbel-softmax straight-through                         mem_transformer.py:609-628
+# ----------------------------------------------------------------------------------------------
+def gumbel_noise(U: torch.Tensor, eps: float = 1e-20) -> torch.Tensor:
+    return -torch.log(-torch.log(U + eps) + eps)
+
+
+def gumbel_st(logits: torch.Tensor, U: torch.Tensor, temperature: float):
+    """Returns (st_out, y_soft, ids).  st_out = (onehot(argmax y) - y).detach() + y."""
+    y = torch.softmax((logits + gumbel_noise(U)) / temperature, dim=-1)
+    ids = y.argmax(dim=-1)
+    hard = F.one_hot(ids, y.shape[-1]).to(y.dtype)
+    return (hard - y).detach() + y, y, ids
+
+
+def generate_gumbel(data, temperature, mems, p, shape: TxlShape, U: torch.Tensor):
+    """forward_generate_gumbel with injected uniform noise U [T,B,V]."""
+    lg, new_mems = generate_logits(data, mems, p, shape)
+    st, y, ids = gumbel_st(lg, U, temperature)
+    return st, new_mems, lg, ids
+
+
+# ----------------------------------------------------------------------------------------------
+# A11 (generator side)  the sampling loop of TransformerGAN.forward      transformer_gan.py:273-349
+# ----------------------------------------------------------------------------------------------
+def sample_fake_chunks(data: torch.Tensor, p, shape_gen: TxlShape, temperature: float, noise: List[torch.Tensor],
+                       tgt_len: int, context_len: int, sample_chunks_mem: int, truncate_backprop: bool = False):
+    """Replays the generator side of one 'gen_loss'/'dis_loss' call.  ``shape_gen.mem_len`` must be
+    DISCRIMINATOR.mem_len (the call runs under reset_length(1, mem_len), transformer_gan.py:251).
+    ``noise[k]`` is the uniform tensor [1,B,V] consumed by the k-th forward_generate_gumbel call.
+    Yields (chunk_start, fake_chunk [len,B,V]) with the autograd graph of each chunk intact (memory is
+    detached between steps by update_mems, and the chunk's first generated token restarts from a hard id)."""
+    V = shape_gen.n_token
+    seq: List[torch.Tensor] = []
+    mems = None
+    with torch.no_grad():
+        if context_len > 1:                                                        # :281-290
+            _, mems = generate_logits(data[: context_len - 1], None, p, shape_gen)
+    sample_len = tgt_len // sample_chunks_mem
+    k = 0
+    out = []
+    for cs in range(0, tgt_len, sample_len):
+        ce = min(cs + sample_len, tgt_len)
+        for ind in range(cs, ce):
+            if ind < context_len:
+                seq.append(F.one_hot(data[ind], V).to(p["r_w_bias"].dtype))             # :304-306
+                continue
+            if truncate_backprop or ind == cs:
+                inp = seq[-1].argmax(-1)[None, :].detach()                            # :315
+            else:
+                inp = seq[-1][None]                                                   # :319
+            st, mems, _, _ = generate_gumbel(inp, temperature, mems, p, shape_gen, noise[k])
+            k += 1
+            seq.append(st[0])
+        if len(seq) == sample_len + 1:                                                # :339-340
+            seq = seq[1:]
+        out.append((cs, torch.stack(seq, 0)))
+        mems = mems.detach()                                                          # :507
+        seq = [seq[-1]]
+    return out
