@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- train tokens/sec of the Transformer-XL MLE training step (experiment_baseline.yml shapes) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU implementation of the same path
+
+A "step" is one optimizer step of the reference's train loop (train.py:859-921) on synthetic MAESTRO-vocab tokens:
+forward + backward of MemTransformerLM over the global batch (512 sequences x 128 tokens, memory 1024), gradient
+clip + Adam.  One process per GPU; N > 1 shards the batch columns (data parallel, global batch fixed = strong
+scaling as in train.py:226-227) and all-reduces the flat gradient buffer once per step over NCCL.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "transformer-gan_b200"))
+
+import torch  # noqa: E402
+
+# experiment_baseline.yml (model/training_config/experiment_baseline.yml:8-38)
+WORK = dict(n_layer=6, n_head=10, d_model=500, d_inner=1000, n_token=310, tgt_len=128, mem_len=1024,
+            global_batch=512, dropout=0.1, dropatt=0.1, clip=1.0, lr=0.004)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-chunk", type=int, default=1, help="micro-batches per step (reference yml: 4; native: 1)")
+    ap.add_argument("--global-batch", type=int, default=WORK["global_batch"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    return ap.parse_args()
+
+
+def make_cfg():
+    ns = types.SimpleNamespace
+    return ns(MODEL=ns(num_layers=WORK["n_layer"], num_heads=WORK["n_head"], units=WORK["d_model"],
+                       inner_size=WORK["d_inner"], dropout=WORK["dropout"], attention_dropout=WORK["dropatt"],
+                       tie_embedding=True, tie_proj=False, pre_lnorm=False, same_length=False, clamp_len=-1),
+              TRAIN=ns(tgt_length=WORK["tgt_len"], mem_length=WORK["mem_len"], pad_type="model",
+                       replace_start_with_pad=False, append_note_status=False))
+
+
+def init_like_train_py(model, seed):
+    """train.py:291-371 with INITIALIZER base/embed 'normal' 0.01: weights N(0, .01), LN weight N(1, .01), biases 0."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in model.named_parameters():
+        if name.endswith("layer_norm.weight"):
+            p.data.copy_(1.0 + 0.01 * torch.randn(p.shape, generator=g))
+        elif name.endswith("bias") and "r_" not in name:
+            p.data.zero_()
+        else:
+            p.data.copy_(0.01 * torch.randn(p.shape, generator=g))
+
+
+def flatten_params(model):
+    """Move every parameter into one flat fp32 buffer (views), with a matching flat gradient buffer, so the
+    gradient all-reduce, the norm clip and Adam are one kernel each."""
+    params = []
+    seen = set()
+    for p in model.parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            params.append(p)
+    n = sum(p.numel() for p in params)
+    flat = torch.empty(n, dtype=torch.float32, device=params[0].device)
+    grad = torch.zeros_like(flat)
+    off = 0
+    for p in params:
+        k = p.numel()
+        flat[off:off + k].copy_(p.data.view(-1))
+        p.data = flat[off:off + k].view_as(p)
+        p.grad = grad[off:off + k].view_as(p)
+        off += k
+    return flat, grad
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path (oracle/txl_oracle.py), all host threads
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_setup(batch):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import txl_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    shape = O.TxlShape(n_layer=WORK["n_layer"], n_head=WORK["n_head"], d_model=WORK["d_model"],
+                       d_inner=WORK["d_inner"], n_token=WORK["n_token"], mem_len=WORK["mem_len"])
+    p = O.init_params(shape, 1111)
+    for t in p.values():
+        t.requires_grad_(True)
+    g = torch.Generator().manual_seed(1111)
+    Q = WORK["tgt_len"]
+    # warm the memory to M = mem_len without running 8 segments: steady-state shapes only need a full-size memory
+    mems = 0.1 * torch.randn(shape.n_layer + 1, WORK["mem_len"], batch, shape.d_model, generator=g)
+
+    def step():
+        data = torch.randint(2, WORK["n_token"], (Q, batch), generator=g)
+        target = torch.randint(2, WORK["n_token"], (Q, batch), generator=g)
+        loss, new_mems = O.mle_forward(data, target, torch.zeros(batch, dtype=torch.bool), mems, p, shape)
+        loss.mean().backward()
+        for t in p.values():
+            t.grad = None
+        return Q * batch
+
+    return step
+
+
+def cpu_baseline(batch, budget_s=20.0):
+    step = cpu_reference_setup(batch)
+    step()  # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    toks, n = 0, 0
+    while n < 1 or (time.perf_counter() - t0 < budget_s and n < 8):
+        toks += step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": toks / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle/txl_oracle.py fp32 fwd+bwd, {n} micro-batches of B={batch} x Q=128 tokens at M=1024 "
+                      f"(same model / shapes as the GPU workload, reduced batch)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step = cpu_reference_setup(args.cpu_batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    toks = 0
+    for _ in range(args.steps):
+        toks += step()
+    dt = time.perf_counter() - t0
+    v = toks / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = oracle port of MemTransformerLM fwd+bwd (fp32) on B={args.cpu_batch} x Q=128 tokens at "
+              f"M=1024: a bounded sample of the 512 x 128-token step")
+    print(json.dumps({
+        "impl": "reference", "metric": "train tokens/sec", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, world):
+    return {"workload": "experiment_baseline.yml Transformer-XL MLE training step (6 layers, 10 heads, d_model 500, "
+                        "d_inner 1000, vocab 310, tgt_len 128, mem_len 1024, dropout 0.1), synthetic MAESTRO-vocab tokens",
+            "global_batch": args.global_batch, "seq_len": WORK["tgt_len"], "mem_len": WORK["mem_len"],
+            "batch_chunk": args.batch_chunk, "parallelism": f"dp{world}",
+            "l2": "per-step working set (activations + recurrence memory, several GB) is far larger than the 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import mem_transformer as MT
+    from tgan_b200 import lib as L
+
+    if args.global_batch % (world * args.batch_chunk):
+        raise SystemExit("global batch must divide by gpus * batch_chunk")
+    Bc = args.global_batch // world // args.batch_chunk  # sequences per micro-batch on this rank
+    Q, V = WORK["tgt_len"], WORK["n_token"]
+    model = MT.MemTransformerLM(make_cfg(), V, 0)
+    init_like_train_py(model, 1111)
+    model = model.to(dev).train()
+    model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model.kernel_impl = args.kernel_impl
+    flat, fgrad = flatten_params(model)
+    m_buf, v_buf = torch.zeros_like(flat), torch.zeros_like(flat)
+    gnorm = torch.zeros(1, device=dev)
+    lr = WORK["lr"] / world  # train.py:392 divides lr by the GPU count
+    gen = torch.Generator().manual_seed(1111 + 1000 * rank)  # train.py:224
+    n_chunks = args.batch_chunk
+    pin = lambda t: t.pin_memory()
+    host_data = [pin(torch.randint(2, V, (Q, Bc), generator=gen)) for _ in range(4 * n_chunks)]
+    host_tgt = [pin(torch.randint(2, V, (Q, Bc), generator=gen)) for _ in range(4 * n_chunks)]
+    dev_data = [t.to(dev) for t in host_data]
+    dev_tgt = [t.to(dev) for t in host_tgt]
+    reset = torch.zeros(Bc, dtype=torch.bool, device=dev)
+    mems = [None] * n_chunks
+    loss_host = torch.zeros(1).pin_memory()
+    step_no = [0]
+
+    def train_step(e2e):
+        step_no[0] += 1
+        total = None
+        for c in range(n_chunks):
+            i = (step_no[0] * n_chunks + c) % len(host_data)
+            if e2e:
+                data = host_data[i].to(dev, non_blocking=True)
+                tgt = host_tgt[i].to(dev, non_blocking=True)
+            else:
+                data, tgt = dev_data[i], dev_tgt[i]
+            loss, mems[c] = model(data, tgt, reset, mems[c])
+            l = loss.mean() / n_chunks  # train.py:891-892
+            l.backward()
+            total = l.detach() if total is None else total + l.detach()
+        if world > 1:
+            dist.all_reduce(fgrad)  # one all-reduce per optimizer step over NVLink; 1/world folded into grad_scale
+        gnorm.zero_()
+        L.sumsq(fgrad, fgrad.numel(), gnorm)
+        L.adam_step(flat, fgrad, m_buf, v_buf, flat.numel(), lr, 0.9, 0.999, 1e-8, 0.0, step_no[0], gnorm,
+                    WORK["clip"], 1.0 / world)
+        fgrad.zero_()
+        # the flat buffer changed in place: tell the engine to re-pack (parameter views share its version counter)
+        model._engine._packed_version = None
+        if e2e:
+            loss_host.copy_(total.view(1), non_blocking=True)
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.launch_count()
+        e0.record()
+        for _ in range(k):
+            train_step(e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), L.launch_count() - l0
+
+    # warm the recurrence memory to its steady-state length (M = mem_len) before timing: 8 segments
+    warm_segments = max(args.warmup, WORK["mem_len"] // Q)
+    for _ in range(warm_segments):
+        train_step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches = timed(args.steps, False)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(args.steps, True)
+    final_loss = float(loss_host.item())
+    tokens = Q * args.global_batch * args.steps
+    value = tokens / (ms_dev / 1e3)
+    e2e_value = tokens / (ms_e2e / 1e3)
+
+    # roofline of the dominant dense contraction: K/V projection over [memory; segment] rows (58% of the FLOPs)
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        Mrows = (WORK["mem_len"] + Q) * Bc
+        DP, NH = 512, 640
+        A = torch.randn(Mrows, DP, device=dev).to(torch.bfloat16)
+        W = torch.randn(2 * NH, DP, device=dev).to(torch.bfloat16)
+        C = torch.empty(Mrows, 2 * NH, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            L.gemm(A, W, C, M=Mrows, N=2 * NH, K=DP, impl=args.kernel_impl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            L.gemm(A, W, C, M=Mrows, N=2 * NH, K=DP, impl=args.kernel_impl)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps / 1e3
+        alg_flops = 2.0 * Mrows * WORK["d_model"] * 2 * WORK["d_model"]  # 2*B*K*D*2D
+        peak = (pk or {}).get("bf16_tflops", 1590.0)
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (K/V projection, M=%d N=1280 K=512)" % Mrows,
+                "achieved": alg_flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": alg_flops / t / 1e12 / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if pk else "fallback 1.59 PFLOP/s",
+                "us_per_launch": t * 1e6}
+        del A, W, C
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_batch)
+    if rank == 0:
+        step_flops = 231.8e6 * Q * args.global_batch  # fwd+bwd algorithmic FLOPs per token
+        pk = peaks() or {}
+        print(json.dumps({
+            "metric": "train tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm_segments, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * 8 * Q * (args.global_batch // world),
+                    "d2h_bytes_per_step": 4, "final_loss": final_loss},
+            "gpu_launches": launches,
+            "step_tensor_frac_of_sustained_peak": step_flops / (ms_dev / args.steps / 1e3) / world /
+                                                  (pk.get("bf16_tflops_sustained", 1400.0) * 1e12),
+            "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+/*
+ * tgan_b200.h -- C ABI of libtgan_b200.so: the sm_100a kernels of the Transformer-XL generator / GAN-step hot path.
+ *
+ * The reference (amazon-science/transformer-gan) has no FFI layer: its hot path is eager PyTorch in
+ * model/mem_transformer.py, model/utils/proj_adaptive_softmax.py and model/transformer_gan.py.  Each entry
+ * point below replaces the ATen/cuBLAS call sequence of the cited reference lines; the Python host
+ * (transformer-gan_b200/tgan_b200/) binds them with ctypes and re-exposes the reference's module API
+ * (MemTransformerLM / TransformerGAN).  See INTEGRATION.md for the binding stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *   - `stream` is a CUstream / cudaStream_t handle passed as void* (0 = legacy default stream).
+ *   - no allocation, no hidden streams, no synchronisation: every call only enqueues work on `stream`.
+ *   - return 0 on success, non-zero on error; tgan_last_error() returns a thread-local message.
+ *   - dtype codes: TGAN_F32 = 0 (fp32 mode, SIMT FFMA kernels, 1e-4 parity), TGAN_BF16 = 1 (bf16 operands,
+ *     fp32 accumulation, tcgen05 tensor cores where eligible).
+ *   - activations are row-major [rows, ld] with rows = position * bsz + batch (the reference's sequence-major
+ *     [len, bsz, feature] layout flattened); feature widths are padded (D->DP multiple of 64, d_head->64, ...)
+ *     and the pad lanes are kept exactly zero.  Heads use a fixed stride of TGAN_HS = 64 lanes.
+ */
+#ifndef TGAN_B200_H
+#define TGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGAN_F32 0
+#define TGAN_BF16 1
+#define TGAN_HS 64 /* head stride (padded d_head) */
+
+/* epilogue flags of tgan_gemm; applied in this order: v = acc*alpha, BIAS, RELU, MASK_POS, DROPOUT, ADD_AUX, ACCUM */
+#define TGAN_EPI_BIAS 1       /* v += bias[n]                      (fp32 bias vector)            */
+#define TGAN_EPI_RELU 2       /* v = max(v, 0)                                                   */
+#define TGAN_EPI_MASK_POS 4   /* v = aux[m,n] > 0 ? v : 0          (ReLU / dropout backward)      */
+#define TGAN_EPI_ADD_AUX 8    /* v += aux[m,n]                     (residual add)                 */
+#define TGAN_EPI_ACCUM 16     /* v += C_old[m,n]                   (gradient accumulation)        */
+#define TGAN_EPI_DROPOUT 32   /* v = keep(seed,site,m*ldc+n) ? v/(1-p) : 0                        */
+#define TGAN_EPI_AUX_F32 64   /* aux is fp32 even when the operands are bf16                      */
+
+/* impl selector of tgan_gemm / tgan_relattn_* : 0 = auto, 1 = force SIMT, 2 = force tcgen05 (error if ineligible) */
+#define TGAN_IMPL_AUTO 0
+#define TGAN_IMPL_SIMT 1
+#define TGAN_IMPL_TC 2
+
+const char* tgan_last_error(void);
+int tgan_version(void);
+/* 1 if the tcgen05/TMA code paths were compiled in (sm_100a build) */
+int tgan_has_tcgen05(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+unsigned long long tgan_launch_count(void);
+
+/* ---- dense contractions ------------------------------------------------------------------------------
+ * C[M,N] = epi( sum_k opA(A)[m,k] * opB(B)[k,n] ),  row-major.
+ *   transA = 0: A is [M,K] (lda >= K);  transA = 1: A is [K,M] (lda >= M)
+ *   transB = 0: B is [K,N] (ldb >= N);  transB = 1: B is [N,K] (ldb >= K)   <- nn.Linear weight layout
+ * Replaces nn.Linear / F.linear / torch.matmul at mem_transformer.py:35,38,85,92,160,168-171,247,331 and
+ * proj_adaptive_softmax.py:52, plus their autograd dgrad / wgrad.
+ * dtype_ab: element type of A, B and aux; dtype_c: element type of C (TGAN_F32 allowed with bf16 operands). */
+int tgan_gemm(int dtype_ab, int dtype_c, int transA, int transB, int M, int N, int K,
+              const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+              const float* bias, const void* aux, int64_t ldaux, int epi_flags, float alpha,
+              float drop_p, uint64_t seed, uint64_t site, int impl, void* stream);
+
+/* ---- embedding: AdaptiveEmbedding.forward, mem_transformer.py:319-341 (index path) --------------------
+ * out[row, :D] = drop(E[ids[row], :D] * scale), pad lanes zeroed.  ids int64 [rows].                        */
+int tgan_embed_fwd(int dtype, const int64_t* ids, const void* E, int64_t lde, void* out, int64_t ldo,
+                   int rows, int D, int DP, float scale, float drop_p, uint64_t seed, uint64_t site,
+                   void* stream);
+/* dE[v, :D] += scale * sum_{rows: ids[row]==v} dropmask(dout[row, :])   (fp32, no atomics: one CTA per v) */
+int tgan_embed_bwd(int dtype, const int64_t* ids, const void* dout, int64_t ldo, float* dE, int64_t ldde,
+                   int rows, int V, int D, float scale, float drop_p, uint64_t seed, uint64_t site, void* stream);
+
+/* ---- positional embedding: PositionalEmbedding.forward, mem_transformer.py:16-23 + :550-558 ------------
+ * pe[p, :] = drop([sin(d_p f), cos(d_p f)]), d_p = min(klen-1-p, clamp_len if > 0); inv_freq fp32 [D/2].   */
+int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t ld, int klen, int D, int DP, int clamp_len,
+                 float drop_p, uint64_t seed, uint64_t site, void* stream);
+
+/* ---- LayerNorm (eps 1e-5) over the first D of DP lanes: mem_transformer.py:58, 255 ---------------------
+ * y = LN(z) * gamma + beta; z is fp32 (the GEMM epilogue wrote x + residual in fp32), y has `dtype`;
+ * mean / rstd (fp32 [rows]) are saved for the backward.                                                     */
+int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
+                const float* beta, float* mean, float* rstd, int rows, int D, int DP, void* stream);
+/* dz = LN'(dy) ; dz_drop (optional) = dropmask(seed, site)(dz) / (1-p) -- the gradient entering the dropout
+ * that precedes the residual add; dgamma / dbeta (fp32 [D]) are accumulated (+=).                         */
+int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float* z, int64_t ldz, const float* gamma,
+                const float* mean, const float* rstd, void* dz, int64_t lddz, void* dz_drop, int64_t lddd,
+                float* dgamma, float* dbeta, int rows, int D, int DP, float drop_p, uint64_t seed,
+                uint64_t site, void* stream);
+
+/* ---- stateless dropout (Philox4x32-10 keyed by seed/site/element): nn.Dropout sites of :37,39,248,557,573 -
+ * dst = keep ? src / (1-p) : 0 (src may equal dst); the same (seed, site) regenerates the mask in backward.
+ * element index = row * ldd + col (the DESTINATION leading dimension).                                      */
+int tgan_dropout(int dtype, const void* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, float p,
+                 uint64_t seed, uint64_t site, void* stream);
+
+/* ---- relative-position attention core: mem_transformer.py:201-244 (+ _rel_shift :133-147, mask :495-547) --
+ * q   [Q*B, ldq]   head n at columns n*64 .. n*64+63        (current rows only; row = i*B + b)
+ * k,v [K*B, ldkv]  head n at columns n*64 ..                (memory rows then current rows; K = M + Q)
+ * r   [K, ldr]     r_net(pos_emb), head n at columns n*64
+ * u = r_w_bias, vb = r_r_bias: fp32 [N, 64] (zero padded)
+ * S[b,n,i,j] = ((q_i+u)k_j + (q_i+vb) r_{j+Q-1-i}) * scale ;  masked iff j > i+M  or (same_length and
+ * j <= i-msl) or (reset[b] and j < M) ;  P = softmax_j S ; out_i = sum_j drop(P_ij) v_j -> out [Q*B, ldo];
+ * lse fp32 [B, N, Q].  reset: uint8 [B] or NULL.  The rel-shift and the mask are index arithmetic: no
+ * [B,Q,K] tensor exists.                                                                                    */
+int tgan_relattn_fwd(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                     const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                     void* out, int64_t ldo, float* lse, int B, int N, int Q, int M, int msl, int same_length,
+                     float scale, float drop_p, uint64_t seed, uint64_t site, int impl, void* stream);
+/* Backward.  dq [Q*B, ldq], dk, dv [K*B, lddkv] (dtype) and dr (fp32 [K, lddr]) are WRITTEN;
+ * du, dvb (fp32 [N,64]) are ACCUMULATED (+=); delta is an fp32 [B,N,Q] scratch buffer (row-wise dout.out). */
+int tgan_relattn_bwd(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                     const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                     const void* out, const void* dout, int64_t ldo, const float* lse, float* delta,
+                     void* dq, void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb,
+                     int B, int N, int Q, int M, int msl, int same_length, float scale,
+                     float drop_p, uint64_t seed, uint64_t site, int impl, void* stream);
+
+/* ---- logits -> NLL: proj_adaptive_softmax.py:75-84 ------------------------------------------------------
+ * logits fp32 [rows, ldl] (first V columns valid); nll = lse - logits[target]; lse saved for the backward. */
+int tgan_ce_fwd(const float* logits, int64_t ldl, const int64_t* target, float* nll, float* lse, int rows, int V,
+                void* stream);
+/* dlogits[row, :] = (softmax - onehot(target)) * dnll[row]  -> dtype [rows, ldd], pad lanes zero */
+int tgan_ce_bwd(int dtype, const float* logits, int64_t ldl, const int64_t* target, const float* lse,
+                const float* dnll, void* dlogits, int64_t ldd, int rows, int V, int VP, void* stream);
+
+/* ---- Gumbel-softmax straight-through: mem_transformer.py:609-628 ----------------------------------------
+ * g = -log(-log(U+1e-20)+1e-20); y = softmax((logits+g)/tau); ids = argmax y;
+ * st = (onehot(ids) - y) + y evaluated in fp32 exactly as the reference does.  U fp32 [rows, ldu] (injected
+ * noise) or NULL -> Philox(seed, site).  y (fp32 [rows, ldy]) is saved for the backward.                   */
+int tgan_gumbel_st_fwd(const float* logits, int64_t ldl, const float* U, int64_t ldu, float tau, float* y,
+                       int64_t ldy, float* st, int64_t lds, int64_t* ids, int rows, int V, uint64_t seed,
+                       uint64_t site, void* stream);
+/* dlogits = (1/tau) * y * (dst - <y, dst>)  -> fp32 [rows, ldd] */
+int tgan_gumbel_st_bwd(const float* y, int64_t ldy, const float* dst, int64_t lds, float tau, float* dlogits,
+                       int64_t ldd, int rows, int V, void* stream);
+
+/* ---- small reductions / converts -------------------------------------------------------------------------*/
+/* out[n] += sum_m x[m,n]   (bias gradients) */
+int tgan_colsum(int dtype, const void* x, int64_t ld, float* out, int rows, int cols, void* stream);
+/* dst[rows, cols] (dtype_dst, ldd) = src (dtype_src, lds); pad columns [cols, cols_pad) of dst zeroed.
+ * Also the recurrence-memory import/export (mem_transformer.py:461-475): ring slab <-> reference fp32 mems. */
+int tgan_convert(int dtype_src, const void* src, int64_t lds, int dtype_dst, void* dst, int64_t ldd,
+                 int64_t rows, int cols, int cols_pad, void* stream);
+
+/* ---- parameter packing -----------------------------------------------------------------------------------
+ * One launch converts the reference-layout fp32 parameters into the kernel-private padded layout, driven by a
+ * DEVICE descriptor table of int64[12] rows:
+ *   { src_ptr, dst_off, rows, cols, ld_dst, row_group, row_group_pad, col_group, col_group_pad, transpose,
+ *     dst_kind (0 = matrix buffer of `dtype`, 1 = fp32 vector buffer), unused }
+ * element (r, c) of the source goes to padded (r', c') with r' = (r / row_group) * row_group_pad + r % row_group
+ * (head padding d_head -> 64), same for columns; with transpose the destination index is c' * ld_dst + r'.
+ * Destinations must be pre-zeroed once (pad lanes stay zero).
+ * tgan_unpack_grads does the inverse for fp32 gradients: *src_ptr[r, c] = padded[r', c'] (never transposed).  */
+int tgan_pack_params(int dtype, void* packed_mat, float* packed_vec, const int64_t* desc, int n_desc,
+                     int64_t max_elems, void* stream);
+int tgan_unpack_grads(const float* padded_mat, const float* padded_vec, const int64_t* desc, int n_desc,
+                      int64_t max_elems, void* stream);
+
+/* ---- optimizer side (next-row): fused grad-norm clip + Adam over flat buffers ----------------*/
+int tgan_sumsq(const float* x, int64_t n, float* out /* 1 float, accumulated */, void* stream);
+int tgan_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* gnorm_sq, float clip,
+                   float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGAN_B200_H */

@@ -1,0 +1,301 @@
+// tcgen05 GEMM for sm_100a: C[M,N] = epi(opA(A) * opB(B)), bf16 operands, fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised kernel (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128-byte swizzle) into a STAGES-deep shared-memory ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) per 16-wide k slice, commits the
+//               stage back to the producer (tcgen05.commit -> mbarrier) and the finished tile to the epilogue
+//   warps 2..5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM, 2 x BN columns),
+//               transpose 32x32 blocks through shared memory so global accesses are row-contiguous, apply
+//               alpha / bias / ReLU / ReLU-mask / dropout / residual / accumulate, store bf16 or fp32.
+// Operand layouts: K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); both are read by TMA with
+// the same 64 x 64-element swizzled boxes and described to the tensor core through the UMMA descriptors.
+// Used for every dense contraction of the path: QKV / R / O projections, FFN, logits, and all dgrad / wgrad.
+#include "tc_common.cuh"
+
+namespace tc {
+
+static EncodeTiledFn g_encode = nullptr;
+EncodeTiledFn get_encode_fn() {
+    if (g_encode) return g_encode;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    g_encode = (EncodeTiledFn)fn;
+    return g_encode;
+}
+
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_cols) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { tgan_set_error("cuTensorMapEncodeTiled entry point not available"); return 2; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        tgan_set_error("cuTensorMapEncodeTiled(2d) failed: %d (rows %llu cols %llu ld %llu)", (int)r,
+                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+        return 2;
+    }
+    return 0;
+}
+
+int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                 uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { tgan_set_error("cuTensorMapEncodeTiled entry point not available"); return 2; }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        tgan_set_error("cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+        return 2;
+    }
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+}  // namespace tc
+
+namespace {
+using namespace tc;
+
+constexpr int BM = 128, BK = 64;
+constexpr int NUM_THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int STG_BYTES = 4 * 32 * 33 * 4;
+
+template <int BN> struct Cfg {
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 8 * (2 * STAGES + 4) + 16 + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TC* __restrict__ C,
+               int64_t ldc, int M, int N, int K, EpiParams ep) {
+    constexpr int STAGES = Cfg<BN>::STAGES;
+    constexpr int B_BYTES = Cfg<BN>::B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + STAGES * A_BYTES;
+    const uint32_t sStg = sB + STAGES * B_BYTES;
+    const uint32_t sBar = sStg + STG_BYTES;
+    const uint32_t full0 = sBar, empty0 = sBar + 8 * STAGES, tfull0 = sBar + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t sTmemPtr = tempty0 + 16;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* stg_all = reinterpret_cast<float*>(gen_base + STAGES * (A_BYTES + B_BYTES));
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+    const int num_tiles = tiles_m * tiles_n;
+    const int nk = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 1) tmem_alloc(sTmemPtr, 2 * BN);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_expect_tx(fb, A_BYTES + B_BYTES);
+                    const uint32_t a_dst = sA + s * A_BYTES, b_dst = sB + s * B_BYTES;
+                    if (!A_MN) tma_load_2d(a_dst, &tmA, fb, kb * BK, m0);
+                    else {
+#pragma unroll
+                        for (int bx = 0; bx < BM / 64; ++bx) tma_load_2d(a_dst + bx * 8192, &tmA, fb, m0 + 64 * bx, kb * BK);
+                    }
+                    if (!B_MN) tma_load_2d(b_dst, &tmB, fb, kb * BK, n0);
+                    else {
+#pragma unroll
+                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(b_dst + bx * 8192, &tmB, fb, n0 + 64 * bx, kb * BK);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * as, aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_src = sA + s * A_BYTES, b_src = sB + s * B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = A_MN ? umma_smem_desc(a_src + k * 2048, 8192, 1024)
+                                                 : umma_smem_desc(a_src + k * 32, 16, 1024);
+                        const uint64_t db = B_MN ? umma_smem_desc(b_src + k * 2048, 8192, 1024)
+                                                 : umma_smem_desc(b_src + k * 32, 16, 1024);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int ew = warp & 3;  // TMEM lane quarter this warp may access
+        float* stg = stg_all + (warp - 2) * (32 * 33);
+        const int flags = ep.flags;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tfull0 + 8 * as, aph);
+            tcgen05_fence_after();
+            const int row_base = m0 + 32 * ew;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= N || row_base >= M) break;  // warp-uniform
+                uint32_t regs[32];
+                tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * ew) << 16), regs);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(regs[c]);
+                __syncwarp();
+                const int col = n0 + c0 + lane;
+                if (col < N) {
+                    const float bias_v = (flags & TGAN_EPI_BIAS) ? ep.bias[col] : 0.f;
+                    const int rmax = min(32, M - row_base);
+                    for (int rr = 0; rr < rmax; ++rr) {
+                        const int64_t row = row_base + rr;
+                        float v = stg[rr * 33 + lane] * ep.alpha + bias_v;
+                        if (flags & TGAN_EPI_RELU) v = fmaxf(v, 0.f);
+                        float a = 0.f;
+                        if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX))
+                            a = ep.aux_is_f32 ? ((const float*)ep.aux)[row * ep.ldaux + col]
+                                              : to_f(((const bf16*)ep.aux)[row * ep.ldaux + col]);
+                        if (flags & TGAN_EPI_MASK_POS) v = a > 0.f ? v : 0.f;
+                        if (flags & TGAN_EPI_DROPOUT)
+                            v = dropout_keep_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
+                        if (flags & TGAN_EPI_ADD_AUX) v += a;
+                        TC* cp = C + row * ldc + col;
+                        if (flags & TGAN_EPI_ACCUM) v += to_f(*cp);
+                        *cp = from_f<TC>(v);
+                    }
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, typename TC>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M, int N, int K,
+              const EpiParams& ep, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+        attr_set = true;
+    }
+    const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, (TC*)C, ldc, M, N, K, ep);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+template <int BN, typename TC>
+int launch_layout(int transA, int transB, const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M,
+                  int N, int K, const EpiParams& ep, cudaStream_t st) {
+    // transA = 1 -> A stored [K, M] -> MN-major A;  transB = 0 -> B stored [K, N] -> MN-major B
+    if (!transA && transB) return launch_tc<BN, false, false, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
+    if (!transA && !transB) return launch_tc<BN, false, true, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
+    if (transA && transB) return launch_tc<BN, true, false, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
+    return launch_tc<BN, true, true, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
+}
+}  // namespace
+
+extern "C" int tgan_has_tcgen05(void) { return 1; }
+
+int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
+                 int64_t ldb, void* C, int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int flags,
+                 float alpha, float drop_p, uint64_t seed, uint64_t site, int force, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    const bool aligned = (lda % 8 == 0) && (ldb % 8 == 0) && (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && K >= 1;
+    if (!aligned) {
+        tgan_set_error("tgan_gemm: tcgen05 path needs 16-byte aligned operands and leading dimensions that are multiples of 8");
+        return -1;
+    }
+    if (!force && (M < 64 || 2.0 * M * N * K < 3.0e7)) {
+        tgan_set_error("tgan_gemm: problem too small for the tcgen05 path");
+        return -1;
+    }
+    const int waste256 = ceil_div(N, 256) * 256 - N, waste128 = ceil_div(N, 128) * 128 - N;
+    const int BN = (waste256 <= waste128) ? 256 : 128;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!transA) rc = tc::make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    else rc = tc::make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 64);
+    if (rc) return rc;
+    if (transB) rc = tc::make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK);
+    else rc = tc::make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 64);
+    if (rc) return rc;
+    EpiParams ep;
+    ep.bias = bias; ep.aux = aux; ep.ldaux = ldaux; ep.flags = flags; ep.alpha = alpha;
+    ep.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    ep.drop_thresh = dropout_thresh(drop_p);
+    ep.drop_key = dropout_key(seed, site);
+    ep.aux_is_f32 = (flags & TGAN_EPI_AUX_F32) ? 1 : 0;
+    if (drop_p <= 0.f) ep.flags &= ~TGAN_EPI_DROPOUT;
+    if (dtype_c == TGAN_F32) {
+        if (BN == 256) return launch_layout<256, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
+        return launch_layout<128, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
+    }
+    if (BN == 256) return launch_layout<256, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
+    return launch_layout<128, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
+}

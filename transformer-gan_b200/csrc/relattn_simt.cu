@@ -1,0 +1,427 @@
+// Relative-position attention core, SIMT (FFMA) implementation.
+//
+// This is the fp32-mode path (1e-4 parity with the reference's fp32 arithmetic), the path for single-token
+// decode shapes (Q = 1: GAN sampling loop, generation) and the fallback for shapes the tcgen05 kernel does not
+// take.  The relative shift (mem_transformer.py:133-147) and the causal / same_length / reset mask
+// (mem_transformer.py:495-547) are index arithmetic:  p(i, j) = j + Q - 1 - i,  no [B,Q,K] tensor exists.
+//
+// Forward: one warp per (b, n, i) query row, lanes stride over the keys with a private online softmax and a
+// private output accumulator, merged across the warp at the end.
+// Backward: three atomic-free passes that each recompute the scores:
+//   rows  : warp per (b, n, i)  -> dq, delta, (du, dvb: one atomic per column per block)
+//   keys  : warp per (b, n, j)  -> dk, dv
+//   rel   : warp per (n, p)     -> dr  (the inverse rel-shift: a gather along the anti-diagonal i - j = const)
+#include "common.cuh"
+
+namespace {
+constexpr int HS = TGAN_HS;  // 64
+constexpr int WARPS = 4;
+
+struct AttnArgs {
+    int B, N, Q, M, K, msl, same_length;
+    float scale, drop_scale;
+    uint32_t thresh;
+    uint64_t seed, site;
+};
+
+template <typename T>
+__device__ __forceinline__ float dot_row(const float* __restrict__ a, const T* __restrict__ row) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < HS / 8; ++c) {
+        float x[8];
+        load8(row + 8 * c, x);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s = fmaf(a[8 * c + t], x[t], s);
+    }
+    return s;
+}
+// s = a . x + b . y
+template <typename T>
+__device__ __forceinline__ float dot_row2(const float* __restrict__ a, const T* __restrict__ x,
+                                          const float* __restrict__ b, const T* __restrict__ y) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < HS / 8; ++c) {
+        float xv[8], yv[8];
+        load8(x + 8 * c, xv);
+        load8(y + 8 * c, yv);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s = fmaf(a[8 * c + t], xv[t], fmaf(b[8 * c + t], yv[t], s));
+    }
+    return s;
+}
+
+__device__ __forceinline__ bool attn_masked(int i, int j, int b_reset, const AttnArgs& a) {
+    if (j > i + a.M) return true;
+    if (a.same_length && j <= i - a.msl) return true;
+    if (b_reset && j < a.M) return true;
+    return false;
+}
+
+__device__ __forceinline__ bool drop_keep_ij(const AttnArgs& a, int bn, int i, int j) {
+    if (!a.thresh) return true;
+    uint64_t e = ((uint64_t)bn * a.Q + i) * a.K + j;
+    return dropout_keep(a.seed, a.site, e, a.thresh);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+relattn_fwd_simt(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v,
+                 int64_t ldkv, const T* __restrict__ r, int64_t ldr, const float* __restrict__ u,
+                 const float* __restrict__ vb, const uint8_t* __restrict__ reset, T* __restrict__ out, int64_t ldo,
+                 float* __restrict__ lse, AttnArgs a) {
+    __shared__ float s_qu[WARPS][HS], s_qv[WARPS][HS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WARPS + warp;
+    const int bn = blockIdx.y, b = bn / a.N, n = bn % a.N;
+    if (i >= a.Q) return;  // no block-wide barrier below
+    const int64_t row = (int64_t)i * a.B + b;
+    for (int d = lane; d < HS; d += 32) {
+        float qd = to_f(q[row * ldq + n * HS + d]);
+        s_qu[warp][d] = qd + u[n * HS + d];
+        s_qv[warp][d] = qd + vb[n * HS + d];
+    }
+    __syncwarp();
+    int jlo = 0, jhi = min(a.K - 1, i + a.M);
+    if (a.same_length) jlo = max(0, i - a.msl + 1);
+    if (reset && reset[b]) jlo = max(jlo, a.M);
+    float m = -INFINITY, l = 0.f, acc[HS];
+#pragma unroll
+    for (int d = 0; d < HS; ++d) acc[d] = 0.f;
+    for (int j = jlo + lane; j <= jhi; j += 32) {
+        const int p = j + a.Q - 1 - i;
+        const T* kr = k + ((int64_t)j * a.B + b) * ldkv + n * HS;
+        const T* rr = r + (int64_t)p * ldr + n * HS;
+        float s = dot_row2(s_qu[warp], kr, s_qv[warp], rr) * a.scale;
+        float mn = fmaxf(m, s);
+        float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+        float pe = expf(s - mn);
+        l = l * corr + pe;
+        float pw = drop_keep_ij(a, bn, i, j) ? pe * a.drop_scale : 0.f;
+        const T* vr = v + ((int64_t)j * a.B + b) * ldkv + n * HS;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8];
+            load8(vr + 8 * c, x);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[8 * c + t] = fmaf(pw, x[t], acc[8 * c + t] * corr);
+        }
+        m = mn;
+    }
+    const float m_all = warp_max(m);
+    const float f = (m == -INFINITY) ? 0.f : expf(m - m_all);
+    const float l_all = warp_sum(l * f);
+    const float inv = l_all > 0.f ? 1.f / l_all : 0.f;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HS; ++d) {
+        float t = warp_sum(acc[d] * f);
+        if (d == lane) o0 = t;
+        if (d == lane + 32) o1 = t;
+    }
+    out[row * ldo + n * HS + lane] = from_f<T>(o0 * inv);
+    out[row * ldo + n * HS + lane + 32] = from_f<T>(o1 * inv);
+    if (lane == 0) lse[(int64_t)bn * a.Q + i] = l_all > 0.f ? m_all + logf(l_all) : -INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward pass 1: per query row -> dq, delta, du, dvb
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+relattn_bwd_rows_simt(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v,
+                      int64_t ldkv, const T* __restrict__ r, int64_t ldr, const float* __restrict__ u,
+                      const float* __restrict__ vb, const uint8_t* __restrict__ reset, const T* __restrict__ out,
+                      const T* __restrict__ dout, int64_t ldo, const float* __restrict__ lse,
+                      float* __restrict__ delta, T* __restrict__ dq, float* __restrict__ du,
+                      float* __restrict__ dvb, AttnArgs a) {
+    __shared__ float s_qu[WARPS][HS], s_qv[WARPS][HS], s_do[WARPS][HS];
+    __shared__ float s_du[HS], s_dvb[HS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * WARPS + warp;
+    const int bn = blockIdx.y, b = bn / a.N, n = bn % a.N;
+    for (int d = threadIdx.x; d < HS; d += blockDim.x) { s_du[d] = 0.f; s_dvb[d] = 0.f; }
+    __syncthreads();
+    if (i < a.Q) {
+        const int64_t row = (int64_t)i * a.B + b;
+        float dl = 0.f;
+        for (int d = lane; d < HS; d += 32) {
+            float qd = to_f(q[row * ldq + n * HS + d]);
+            s_qu[warp][d] = qd + u[n * HS + d];
+            s_qv[warp][d] = qd + vb[n * HS + d];
+            float g = to_f(dout[row * ldo + n * HS + d]);
+            s_do[warp][d] = g;
+            dl += g * to_f(out[row * ldo + n * HS + d]);
+        }
+        dl = warp_sum(dl);
+        __syncwarp();
+        const float L = lse[(int64_t)bn * a.Q + i];
+        if (lane == 0) delta[(int64_t)bn * a.Q + i] = dl;
+        int jlo = 0, jhi = min(a.K - 1, i + a.M);
+        if (a.same_length) jlo = max(0, i - a.msl + 1);
+        if (reset && reset[b]) jlo = max(jlo, a.M);
+        float acck[HS], accr[HS];
+#pragma unroll
+        for (int d = 0; d < HS; ++d) { acck[d] = 0.f; accr[d] = 0.f; }
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+            const int p = j + a.Q - 1 - i;
+            const T* kr = k + ((int64_t)j * a.B + b) * ldkv + n * HS;
+            const T* rr = r + (int64_t)p * ldr + n * HS;
+            const T* vr = v + ((int64_t)j * a.B + b) * ldkv + n * HS;
+            float s = dot_row2(s_qu[warp], kr, s_qv[warp], rr) * a.scale;
+            float pr = expf(s - L);
+            float dp = dot_row(s_do[warp], vr);
+            dp = drop_keep_ij(a, bn, i, j) ? dp * a.drop_scale : 0.f;
+            float ds = pr * (dp - dl) * a.scale;
+#pragma unroll
+            for (int c = 0; c < HS / 8; ++c) {
+                float x[8], y[8];
+                load8(kr + 8 * c, x);
+                load8(rr + 8 * c, y);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    acck[8 * c + t] = fmaf(ds, x[t], acck[8 * c + t]);
+                    accr[8 * c + t] = fmaf(ds, y[t], accr[8 * c + t]);
+                }
+            }
+        }
+        float k0 = 0.f, k1 = 0.f, r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < HS; ++d) {
+            float tk = warp_sum(acck[d]), tr = warp_sum(accr[d]);
+            if (d == lane) { k0 = tk; r0 = tr; }
+            if (d == lane + 32) { k1 = tk; r1 = tr; }
+        }
+        dq[row * ldq + n * HS + lane] = from_f<T>(k0 + r0);
+        dq[row * ldq + n * HS + lane + 32] = from_f<T>(k1 + r1);
+        atomicAdd(&s_du[lane], k0); atomicAdd(&s_du[lane + 32], k1);
+        atomicAdd(&s_dvb[lane], r0); atomicAdd(&s_dvb[lane + 32], r1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < HS; d += blockDim.x) {
+        atomicAdd(&du[n * HS + d], s_du[d]);
+        atomicAdd(&dvb[n * HS + d], s_dvb[d]);
+    }
+}
+
+// backward pass 2: per key row -> dk, dv
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+relattn_bwd_keys_simt(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v,
+                      int64_t ldkv, const T* __restrict__ r, int64_t ldr, const float* __restrict__ u,
+                      const float* __restrict__ vb, const uint8_t* __restrict__ reset,
+                      const T* __restrict__ dout, int64_t ldo, const float* __restrict__ lse,
+                      const float* __restrict__ delta, T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv,
+                      AttnArgs a) {
+    __shared__ float s_k[WARPS][HS], s_v[WARPS][HS], s_u[HS], s_vb[HS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * WARPS + warp;
+    const int bn = blockIdx.y, b = bn / a.N, n = bn % a.N;
+    for (int d = threadIdx.x; d < HS; d += blockDim.x) { s_u[d] = u[n * HS + d]; s_vb[d] = vb[n * HS + d]; }
+    __syncthreads();
+    if (j >= a.K) return;
+    const int64_t krow = (int64_t)j * a.B + b;
+    for (int d = lane; d < HS; d += 32) {
+        s_k[warp][d] = to_f(k[krow * ldkv + n * HS + d]);
+        s_v[warp][d] = to_f(v[krow * ldkv + n * HS + d]);
+    }
+    __syncwarp();
+    int ilo = max(0, j - a.M), ihi = a.Q - 1;
+    if (a.same_length) ihi = min(ihi, j + a.msl - 1);
+    if (reset && reset[b] && j < a.M) ihi = -1;
+    float acck[HS], accv[HS];
+#pragma unroll
+    for (int d = 0; d < HS; ++d) { acck[d] = 0.f; accv[d] = 0.f; }
+    for (int i = ilo + lane; i <= ihi; i += 32) {
+        const int64_t row = (int64_t)i * a.B + b;
+        const int p = j + a.Q - 1 - i;
+        const T* qr = q + row * ldq + n * HS;
+        const T* rr = r + (int64_t)p * ldr + n * HS;
+        const T* dor = dout + row * ldo + n * HS;
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8], y[8], g[8];
+            load8(qr + 8 * c, x);
+            load8(rr + 8 * c, y);
+            load8(dor + 8 * c, g);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                int d = 8 * c + t;
+                s = fmaf(x[t] + s_u[d], s_k[warp][d], fmaf(x[t] + s_vb[d], y[t], s));
+                dp = fmaf(g[t], s_v[warp][d], dp);
+            }
+        }
+        const float L = lse[(int64_t)bn * a.Q + i], dl = delta[(int64_t)bn * a.Q + i];
+        float pr = expf(s * a.scale - L);
+        bool keep = drop_keep_ij(a, bn, i, j);
+        float pw = keep ? pr * a.drop_scale : 0.f;
+        dp = keep ? dp * a.drop_scale : 0.f;
+        float ds = pr * (dp - dl) * a.scale;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8], g[8];
+            load8(qr + 8 * c, x);
+            load8(dor + 8 * c, g);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                int d = 8 * c + t;
+                acck[d] = fmaf(ds, x[t] + s_u[d], acck[d]);
+                accv[d] = fmaf(pw, g[t], accv[d]);
+            }
+        }
+    }
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HS; ++d) {
+        float tk = warp_sum(acck[d]), tv = warp_sum(accv[d]);
+        if (d == lane) { k0 = tk; v0 = tv; }
+        if (d == lane + 32) { k1 = tk; v1 = tv; }
+    }
+    dk[krow * lddkv + n * HS + lane] = from_f<T>(k0);
+    dk[krow * lddkv + n * HS + lane + 32] = from_f<T>(k1);
+    dv[krow * lddkv + n * HS + lane] = from_f<T>(v0);
+    dv[krow * lddkv + n * HS + lane + 32] = from_f<T>(v1);
+}
+
+// backward pass 3: per relative position -> dr[p] = scale * sum_{b,i} dS[b,i,j=p-Q+1+i] (q_i + vb)
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+relattn_bwd_rel_simt(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v,
+                     int64_t ldkv, const T* __restrict__ r, int64_t ldr, const float* __restrict__ u,
+                     const float* __restrict__ vb, const uint8_t* __restrict__ reset, const T* __restrict__ dout,
+                     int64_t ldo, const float* __restrict__ lse, const float* __restrict__ delta,
+                     float* __restrict__ dr, int64_t lddr, AttnArgs a) {
+    __shared__ float s_r[WARPS][HS], s_u[HS], s_vb[HS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * WARPS + warp;
+    const int n = blockIdx.y;
+    for (int d = threadIdx.x; d < HS; d += blockDim.x) { s_u[d] = u[n * HS + d]; s_vb[d] = vb[n * HS + d]; }
+    __syncthreads();
+    if (p >= a.K) return;
+    for (int d = lane; d < HS; d += 32) s_r[warp][d] = to_f(r[(int64_t)p * ldr + n * HS + d]);
+    __syncwarp();
+    float acc[HS];
+#pragma unroll
+    for (int d = 0; d < HS; ++d) acc[d] = 0.f;
+    const int total = a.B * a.Q;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int b = idx / a.Q, i = idx % a.Q;
+        const int j = p - a.Q + 1 + i;
+        if (j < 0 || j >= a.K) continue;
+        if (attn_masked(i, j, reset ? reset[b] : 0, a)) continue;
+        const int bn = b * a.N + n;
+        const int64_t row = (int64_t)i * a.B + b, krow = (int64_t)j * a.B + b;
+        const T* qr = q + row * ldq + n * HS;
+        const T* kr = k + krow * ldkv + n * HS;
+        const T* vr = v + krow * ldkv + n * HS;
+        const T* dor = dout + row * ldo + n * HS;
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8], y[8], g[8], w[8];
+            load8(qr + 8 * c, x);
+            load8(kr + 8 * c, y);
+            load8(dor + 8 * c, g);
+            load8(vr + 8 * c, w);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                int d = 8 * c + t;
+                s = fmaf(x[t] + s_u[d], y[t], fmaf(x[t] + s_vb[d], s_r[warp][d], s));
+                dp = fmaf(g[t], w[t], dp);
+            }
+        }
+        const float L = lse[(int64_t)bn * a.Q + i], dl = delta[(int64_t)bn * a.Q + i];
+        float pr = expf(s * a.scale - L);
+        dp = drop_keep_ij(a, bn, i, j) ? dp * a.drop_scale : 0.f;
+        float ds = pr * (dp - dl) * a.scale;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8];
+            load8(qr + 8 * c, x);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[8 * c + t] = fmaf(ds, x[t] + s_vb[8 * c + t], acc[8 * c + t]);
+        }
+    }
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HS; ++d) {
+        float t = warp_sum(acc[d]);
+        if (d == lane) r0 = t;
+        if (d == lane + 32) r1 = t;
+    }
+    dr[(int64_t)p * lddr + n * HS + lane] = r0;
+    dr[(int64_t)p * lddr + n * HS + lane + 32] = r1;
+}
+
+AttnArgs make_args(int B, int N, int Q, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
+                   uint64_t site) {
+    AttnArgs a;
+    a.B = B; a.N = N; a.Q = Q; a.M = M; a.K = M + Q; a.msl = msl; a.same_length = same_length; a.scale = scale;
+    a.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    a.thresh = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    a.seed = seed; a.site = site;
+    return a;
+}
+}  // namespace
+
+int tgan_relattn_fwd_simt(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                          const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out,
+                          int64_t ldo, float* lse, int B, int N, int Q, int M, int msl, int same_length, float scale,
+                          float drop_p, uint64_t seed, uint64_t site, cudaStream_t st) {
+    AttnArgs a = make_args(B, N, Q, M, msl, same_length, scale, drop_p, seed, site);
+    dim3 grid(ceil_div(Q, WARPS), B * N);
+    if (dtype == TGAN_F32)
+        relattn_fwd_simt<float><<<grid, WARPS * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v,
+                                                              ldkv, (const float*)r, ldr, u, vb, reset, (float*)out,
+                                                              ldo, lse, a);
+    else
+        relattn_fwd_simt<bf16><<<grid, WARPS * 32, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
+                                                             (const bf16*)r, ldr, u, vb, reset, (bf16*)out, ldo, lse,
+                                                             a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+template <typename T>
+static int bwd_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
+                      int64_t ldr, const float* u, const float* vb, const uint8_t* reset, const void* out,
+                      const void* dout, int64_t ldo, const float* lse, float* delta, void* dq, void* dk, void* dv,
+                      int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, const AttnArgs& a,
+                      cudaStream_t st) {
+    dim3 g1(ceil_div(a.Q, WARPS), a.B * a.N);
+    relattn_bwd_rows_simt<T><<<g1, WARPS * 32, 0, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)r,
+                                                         ldr, u, vb, reset, (const T*)out, (const T*)dout, ldo, lse,
+                                                         delta, (T*)dq, du, dvb, a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    dim3 g2(ceil_div(a.K, WARPS), a.B * a.N);
+    relattn_bwd_keys_simt<T><<<g2, WARPS * 32, 0, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)r,
+                                                         ldr, u, vb, reset, (const T*)dout, ldo, lse, delta, (T*)dk,
+                                                         (T*)dv, lddkv, a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    dim3 g3(ceil_div(a.K, WARPS), a.N);
+    relattn_bwd_rel_simt<T><<<g3, WARPS * 32, 0, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)r,
+                                                        ldr, u, vb, reset, (const T*)dout, ldo, lse, delta, dr, lddr,
+                                                        a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+int tgan_relattn_bwd_simt(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                          const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                          const void* out, const void* dout, int64_t ldo, const float* lse, float* delta, void* dq,
+                          void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
+                          int N, int Q, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
+                          uint64_t site, cudaStream_t st) {
+    AttnArgs a = make_args(B, N, Q, M, msl, same_length, scale, drop_p, seed, site);
+    if (dtype == TGAN_F32)
+        return bwd_launch<float>(q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq, dk, dv,
+                                 lddkv, dr, lddr, du, dvb, a, st);
+    return bwd_launch<bf16>(q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq, dk, dv, lddkv,
+                            dr, lddr, du, dvb, a, st);
+}

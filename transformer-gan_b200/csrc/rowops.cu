@@ -1,0 +1,694 @@
+// Bandwidth-bound row-wise kernels of the Transformer-XL hot path: embedding, positional embedding, LayerNorm,
+// dropout, cross-entropy, Gumbel-softmax straight-through, bias-gradient column sums, dtype/pad converts,
+// parameter packing and the fused clip+Adam update.  All are HBM-bound: one warp per row, 16-byte vector
+// accesses, no shared-memory staging needed (no reuse).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// error plumbing / bookkeeping
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+unsigned long long g_tgan_launches = 0;
+
+void tgan_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* tgan_last_error(void) { return g_err; }
+extern "C" int tgan_version(void) { return 100; }
+extern "C" unsigned long long tgan_launch_count(void) { return g_tgan_launches; }
+
+#define DISPATCH_T(dtype, ...)                                  \
+    do {                                                        \
+        if ((dtype) == TGAN_F32) { typedef float T; __VA_ARGS__; } \
+        else if ((dtype) == TGAN_BF16) { typedef bf16 T; __VA_ARGS__; } \
+        else { tgan_set_error("bad dtype %d", (int)(dtype)); return 1; } \
+    } while (0)
+
+namespace {
+constexpr int WPB = 8;  // warps per block for the warp-per-row kernels
+
+// ------------------------------------------------------------------------------------------------------------
+// embedding forward: out[row, c] = drop(E[ids[row], c] * scale)         mem_transformer.py:329-339, 557
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ E, int64_t lde,
+                                 T* __restrict__ out, int64_t ldo, int rows, int D, int DP, float scale,
+                                 float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
+    int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const T* e = E + ids[row] * lde;
+    T* o = out + (int64_t)row * ldo;
+    for (int c0 = lane * 8; c0 < DP; c0 += 256) {
+        float v[8];
+        load8(e + c0, v);
+        uint32_t keep = thresh ? dropout_keep8(seed, site, (uint64_t)row * ldo + c0, thresh) : 0xffu;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = (c0 + t < D && ((keep >> t) & 1)) ? v[t] * scale * drop_scale : 0.f;
+        store8(o + c0, v);
+    }
+}
+
+// embedding backward: one CTA per vocabulary id (no atomics, deterministic).  dE[v, c] += scale * sum dout[row, c]
+template <typename T>
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout, int64_t ldo,
+                                 float* __restrict__ dE, int64_t ldde, int rows, int D, float scale,
+                                 float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
+    __shared__ int s_ids[1024];
+    const int v = blockIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // columns threadIdx.x + 256*t, D <= 1024
+    for (int r0 = 0; r0 < rows; r0 += 1024) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 1024 && r0 + t < rows; t += blockDim.x) s_ids[t] = (int)ids[r0 + t];
+        __syncthreads();
+        int n = min(1024, rows - r0);
+        for (int t = 0; t < n; ++t) {
+            if (s_ids[t] != v) continue;  // block-uniform branch
+            int64_t row = r0 + t;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int c = threadIdx.x + 256 * u;
+                if (c < D) {
+                    float g = to_f(dout[row * ldo + c]);
+                    if (thresh) g = dropout_keep(seed, site, (uint64_t)row * ldo + c, thresh) ? g * drop_scale : 0.f;
+                    acc[u] += g;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int c = threadIdx.x + 256 * u;
+        if (c < D && acc[u] != 0.f) dE[(int64_t)v * ldde + c] += scale * acc[u];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// positional embedding                                             mem_transformer.py:13-23, 550-558
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pos_emb_kernel(const float* __restrict__ inv_freq, T* __restrict__ pe, int64_t ld, int klen, int D,
+                               int DP, int clamp_len, float drop_scale, uint32_t thresh, uint64_t seed,
+                               uint64_t site) {
+    int p = blockIdx.x;
+    float d = (float)(klen - 1 - p);
+    if (clamp_len > 0) d = fminf(d, (float)clamp_len);
+    int half = D / 2;
+    for (int c = threadIdx.x; c < DP; c += blockDim.x) {
+        float v = 0.f;
+        if (c < D) {
+            float ang = d * inv_freq[c < half ? c : c - half];
+            v = c < half ? sinf(ang) : cosf(ang);
+            if (thresh) v = dropout_keep(seed, site, (uint64_t)p * ld + c, thresh) ? v * drop_scale : 0.f;
+        }
+        pe[(int64_t)p * ld + c] = from_f<T>(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm forward (warp per row; z fp32 -> y T)                   mem_transformer.py:58, 255
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void ln_fwd_kernel(const float* __restrict__ z, int64_t ldz, T* __restrict__ y, int64_t ldy,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, int DP) {
+    int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* zr = z + (int64_t)row * ldz;
+    float s = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(zr + c);
+        s += v.x + (c + 1 < D ? v.y : 0.f) + (c + 2 < D ? v.z : 0.f) + (c + 3 < D ? v.w : 0.f);
+    }
+    float mu = warp_sum(s) / D;
+    float q = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(zr + c);
+        float a = v.x - mu, b = v.y - mu, cc = v.z - mu, d = v.w - mu;
+        q += a * a + (c + 1 < D ? b * b : 0.f) + (c + 2 < D ? cc * cc : 0.f) + (c + 3 < D ? d * d : 0.f);
+    }
+    float rs = rsqrtf(warp_sum(q) / D + 1e-5f);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    T* yr = y + (int64_t)row * ldy;
+    for (int c0 = lane * 8; c0 < DP; c0 += 256) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            int c = c0 + t;
+            o[t] = c < D ? (zr[c] - mu) * rs * gamma[c] + beta[c] : 0.f;
+        }
+        store8(yr + c0, o);
+    }
+}
+
+// LayerNorm backward.  One warp per row; dgamma/dbeta partials are reduced per block in shared memory and
+// added to global memory with one atomic per column per block.
+template <typename T, int MAXC>
+__global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz,
+                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, T* __restrict__ dz, int64_t lddz,
+                              T* __restrict__ dzd, int64_t lddd, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, int rows, int D, int DP, int rows_per_block,
+                              float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
+    extern __shared__ float sm[];  // [2][DP]
+    float* s_dg = sm;
+    float* s_db = sm + DP;
+    for (int c = threadIdx.x; c < 2 * DP; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float pg[MAXC], pb[MAXC];  // per-lane partials for columns lane*8 + 256*u + t
+#pragma unroll
+    for (int t = 0; t < MAXC; ++t) pg[t] = pb[t] = 0.f;
+    const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+    for (int row = r_begin + warp; row < r_end; row += WPB) {
+        const T* dyr = dy + (int64_t)row * lddy;
+        const float* zr = z + (int64_t)row * ldz;
+        const float mu = mean[row], rs = rstd[row];
+        float g[MAXC], xh[MAXC];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < MAXC / 8; ++u) {
+            int c0 = lane * 8 + 256 * u;
+            if (c0 < DP) {
+                float d8[8];
+                load8(dyr + c0, d8);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    int c = c0 + t;
+                    float x = c < D ? (zr[c] - mu) * rs : 0.f;
+                    float dv = c < D ? d8[t] : 0.f;
+                    pg[u * 8 + t] += dv * x;
+                    pb[u * 8 + t] += dv;
+                    float gg = c < D ? dv * gamma[c] : 0.f;
+                    g[u * 8 + t] = gg; xh[u * 8 + t] = x;
+                    s1 += gg; s2 += gg * x;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { g[u * 8 + t] = 0.f; xh[u * 8 + t] = 0.f; }
+            }
+        }
+        s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
+#pragma unroll
+        for (int u = 0; u < MAXC / 8; ++u) {
+            int c0 = lane * 8 + 256 * u;
+            if (c0 < DP) {
+                float o[8], od[8];
+                uint32_t keep = (thresh && dzd) ? dropout_keep8(seed, site, (uint64_t)row * lddd + c0, thresh) : 0xffu;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    int c = c0 + t;
+                    float v = c < D ? rs * (g[u * 8 + t] - s1 - xh[u * 8 + t] * s2) : 0.f;
+                    o[t] = v;
+                    od[t] = ((keep >> t) & 1) ? v * drop_scale : 0.f;
+                }
+                store8(dz + (int64_t)row * lddz + c0, o);
+                if (dzd) store8(dzd + (int64_t)row * lddd + c0, od);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXC / 8; ++u) {
+        int c0 = lane * 8 + 256 * u;
+        if (c0 < DP) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                atomicAdd(&s_dg[c0 + t], pg[u * 8 + t]);
+                atomicAdd(&s_db[c0 + t], pb[u * 8 + t]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        atomicAdd(&dgamma[c], s_dg[c]);
+        atomicAdd(&dbeta[c], s_db[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dropout (out of place or in place)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd, int rows,
+                               int cols8, float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
+    int64_t total = (int64_t)rows * cols8;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = e / cols8;
+        int c0 = (int)(e % cols8) * 8;
+        float v[8];
+        load8(src + row * lds + c0, v);
+        uint32_t keep = thresh ? dropout_keep8(seed, site, (uint64_t)row * ldd + c0, thresh) : 0xffu;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * drop_scale : 0.f;
+        store8(dst + row * ldd + c0, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cross-entropy over the small vocabulary (warp per row)            proj_adaptive_softmax.py:75-84
+// ------------------------------------------------------------------------------------------------------------
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ target,
+                              float* __restrict__ nll, float* __restrict__ lse, int rows, int V) {
+    int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* l = logits + (int64_t)row * ldl;
+    float m = -INFINITY;
+    for (int c = lane; c < V; c += 32) m = fmaxf(m, l[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += expf(l[c] - m);
+    s = warp_sum(s);
+    if (lane == 0) {
+        float ls = m + logf(s);
+        lse[row] = ls;
+        nll[row] = ls - l[target[row]];
+    }
+}
+
+template <typename T>
+__global__ void ce_bwd_kernel(const float* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ target,
+                              const float* __restrict__ lse, const float* __restrict__ dnll, T* __restrict__ dl,
+                              int64_t ldd, int rows, int V, int VP) {
+    int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* l = logits + (int64_t)row * ldl;
+    const float ls = lse[row], g = dnll[row];
+    const int tg = (int)target[row];
+    for (int c0 = lane * 8; c0 < VP; c0 += 256) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            int c = c0 + t;
+            o[t] = c < V ? (expf(l[c] - ls) - (c == tg ? 1.f : 0.f)) * g : 0.f;
+        }
+        store8(dl + (int64_t)row * ldd + c0, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gumbel-softmax straight-through (warp per row)                    mem_transformer.py:609-628
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gumbel_fwd_kernel(const float* __restrict__ logits, int64_t ldl, const float* __restrict__ U,
+                                  int64_t ldu, float tau, float* __restrict__ y, int64_t ldy,
+                                  float* __restrict__ st, int64_t lds, int64_t* __restrict__ ids, int rows, int V,
+                                  uint64_t seed, uint64_t site) {
+    int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* l = logits + (int64_t)row * ldl;
+    float* yr = y + (int64_t)row * ldy;
+    // pass 1: perturbed, tempered logits (kept in y), running max / first argmax
+    float m = -INFINITY;
+    int am = 0x7fffffff;
+    for (int c = lane; c < V; c += 32) {
+        float u;
+        if (U) u = U[(int64_t)row * ldu + c];
+        else {
+            uint64_t e = (uint64_t)row * V + c;
+            Philox4 r = philox4x32_10(seed, site, e >> 2);
+            uint32_t bits = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+            u = (bits >> 8) * (1.0f / 16777216.0f);  // [0, 1) like torch.rand
+        }
+        float g = -logf(-logf(u + 1e-20f) + 1e-20f);
+        float t = (l[c] + g) / tau;
+        yr[c] = t;
+        if (t > m) { m = t; am = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, m, o);
+        int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+    }
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += expf(yr[c] - m);
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    // the reference takes argmax of the softmax output; exp() is monotone so the first maximal tempered logit
+    // is also the first maximal probability unless two probabilities round to the same float -- then torch's
+    // max returns the first index of the rounded maximum: replicate by comparing the rounded values.
+    float pm = -1.f;
+    int pa = 0x7fffffff;
+    for (int c = lane; c < V; c += 32) {
+        float p = expf(yr[c] - m) * inv;
+        yr[c] = p;
+        if (p > pm) { pm = p; pa = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, pm, o);
+        int oa = __shfl_xor_sync(0xffffffffu, pa, o);
+        if (om > pm || (om == pm && oa < pa)) { pm = om; pa = oa; }
+    }
+    if (lane == 0 && ids) ids[row] = pa;
+    if (st) {
+        float* sr = st + (int64_t)row * lds;
+        for (int c = lane; c < V; c += 32) {
+            float p = yr[c];
+            sr[c] = ((c == pa ? 1.f : 0.f) - p) + p;  // (y_hard - y).detach() + y, same fp32 rounding
+        }
+    }
+}
+
+__global__ void gumbel_bwd_kernel(const float* __restrict__ y, int64_t ldy, const float* __restrict__ dst,
+                                  int64_t lds, float tau, float* __restrict__ dl, int64_t ldd, int rows, int V) {
+    int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* yr = y + (int64_t)row * ldy;
+    const float* dr = dst + (int64_t)row * lds;
+    float dot = 0.f;
+    for (int c = lane; c < V; c += 32) dot += yr[c] * dr[c];
+    dot = warp_sum(dot);
+    const float it = 1.f / tau;
+    for (int c = lane; c < V; c += 32) dl[(int64_t)row * ldd + c] = it * yr[c] * (dr[c] - dot);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] += sum_m x[m, n]
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out, int rows, int cols,
+                              int rows_per_block) {
+    // block = 32 x 8 threads: threadIdx.x -> column, threadIdx.y -> row phase
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < cols)
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) s += to_f(x[(int64_t)r * ld + c]);
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(&out[c], t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// convert / pad
+// ------------------------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void convert_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst, int64_t ldd,
+                               int64_t rows, int cols, int cols_pad) {
+    int64_t total = rows * cols_pad;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e / cols_pad;
+        int c = (int)(e % cols_pad);
+        dst[r * ldd + c] = from_f<TD>(c < cols ? to_f(src[r * lds + c]) : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// parameter packing / gradient unpacking (descriptor table, one launch)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_kernel(T* __restrict__ mat, float* __restrict__ vec, const int64_t* __restrict__ desc) {
+    const int64_t* d = desc + 12 * blockIdx.y;
+    const float* src = reinterpret_cast<const float*>(d[0]);
+    const int64_t dst_off = d[1], rows = d[2], cols = d[3], ld = d[4], rg = d[5], rgp = d[6], cg = d[7], cgp = d[8];
+    const bool tr = d[9] != 0, is_vec = d[10] != 0;
+    const int64_t total = rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e / cols, c = e % cols;
+        int64_t rp = (r / rg) * rgp + r % rg, cp = (c / cg) * cgp + c % cg;
+        int64_t o = dst_off + (tr ? cp * ld + rp : rp * ld + cp);
+        float v = src[e];
+        if (is_vec) vec[o] = v;
+        else mat[o] = from_f<T>(v);
+    }
+}
+
+__global__ void unpack_kernel(const float* __restrict__ mat, const float* __restrict__ vec,
+                              const int64_t* __restrict__ desc) {
+    const int64_t* d = desc + 12 * blockIdx.y;
+    float* dst = reinterpret_cast<float*>(d[0]);
+    const int64_t off = d[1], rows = d[2], cols = d[3], ld = d[4], rg = d[5], rgp = d[6], cg = d[7], cgp = d[8];
+    const bool is_vec = d[10] != 0;
+    const int64_t total = rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e / cols, c = e % cols;
+        int64_t rp = (r / rg) * rgp + r % rg, cp = (c / cg) * cgp + c % cg;
+        int64_t o = off + rp * ld + cp;
+        dst[e] = is_vec ? vec[o] : mat[o];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// optimizer side: sum of squares, fused clip + Adam
+// ------------------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    float s = 0.f;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float v = x[e];
+        s += v * v;
+    }
+    s = warp_sum(s);
+    __shared__ float part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) atomicAdd(out, t);
+    }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2, const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+    float cs = grad_scale;
+    if (gnorm_sq && clip > 0.f) {
+        float nrm = sqrtf(*gnorm_sq) * grad_scale;
+        float coef = clip / (nrm + 1e-6f);  // torch.nn.utils.clip_grad_norm_
+        if (coef < 1.f) cs *= coef;
+    }
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        float gr = g[e] * cs;
+        float pv = p[e];
+        if (wd != 0.f) gr += wd * pv;
+        float mm = b1 * m[e] + (1.f - b1) * gr;
+        float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+        m[e] = mm; v[e] = vv;
+        float denom = sqrtf(vv) / sqrtf(bc2) + eps;  // torch.optim.Adam
+        p[e] = pv - (lr / bc1) * mm / denom;
+    }
+}
+
+inline int grid_for(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads;
+    int64_t cap = 148LL * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+#define ST ((cudaStream_t)stream)
+
+extern "C" int tgan_embed_fwd(int dtype, const int64_t* ids, const void* E, int64_t lde, void* out, int64_t ldo,
+                              int rows, int D, int DP, float scale, float drop_p, uint64_t seed, uint64_t site,
+                              void* stream) {
+    if (rows <= 0) return 0;
+    TGAN_CHECK_ARG(DP % 8 == 0 && lde % 8 == 0 && ldo % 8 == 0 && D <= DP, "tgan_embed_fwd: DP/ld must be multiples of 8");
+    uint32_t th = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    DISPATCH_T(dtype, (embed_fwd_kernel<T><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(
+                          ids, (const T*)E, lde, (T*)out, ldo, rows, D, DP, scale, ds, th, seed, site)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_embed_bwd(int dtype, const int64_t* ids, const void* dout, int64_t ldo, float* dE, int64_t ldde,
+                              int rows, int V, int D, float scale, float drop_p, uint64_t seed, uint64_t site,
+                              void* stream) {
+    if (rows <= 0) return 0;
+    TGAN_CHECK_ARG(D <= 1024, "tgan_embed_bwd: D <= 1024 supported");
+    uint32_t th = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    DISPATCH_T(dtype, (embed_bwd_kernel<T><<<V, 256, 0, ST>>>(ids, (const T*)dout, ldo, dE, ldde, rows, D, scale, ds,
+                                                               th, seed, site)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t ld, int klen, int D, int DP,
+                            int clamp_len, float drop_p, uint64_t seed, uint64_t site, void* stream) {
+    if (klen <= 0) return 0;
+    uint32_t th = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    DISPATCH_T(dtype, (pos_emb_kernel<T><<<klen, 128, 0, ST>>>(inv_freq, (T*)pe, ld, klen, D, DP, clamp_len, ds, th,
+                                                                seed, site)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
+                           const float* beta, float* mean, float* rstd, int rows, int D, int DP, void* stream) {
+    if (rows <= 0) return 0;
+    TGAN_CHECK_ARG(DP % 8 == 0 && ldz % 4 == 0 && ldy % 8 == 0 && D <= DP, "tgan_ln_fwd: alignment");
+    DISPATCH_T(dtype, (ln_fwd_kernel<T><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
+                                                                                   mean, rstd, rows, D, DP)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float* z, int64_t ldz, const float* gamma,
+                           const float* mean, const float* rstd, void* dz, int64_t lddz, void* dz_drop, int64_t lddd,
+                           float* dgamma, float* dbeta, int rows, int D, int DP, float drop_p, uint64_t seed,
+                           uint64_t site, void* stream) {
+    if (rows <= 0) return 0;
+    TGAN_CHECK_ARG(DP % 8 == 0 && DP <= 1024 && lddy % 8 == 0 && lddz % 8 == 0 && (!dz_drop || lddd % 8 == 0),
+                   "tgan_ln_bwd: DP <= 1024, multiples of 8");
+    uint32_t th = (drop_p > 0.f && dz_drop) ? dropout_thresh(drop_p) : 0u;
+    float ds = (drop_p > 0.f && dz_drop) ? 1.f / (1.f - drop_p) : 1.f;
+    int blocks = min(ceil_div(rows, WPB), 148 * 4);
+    int rpb = ceil_div(rows, blocks);
+    blocks = ceil_div(rows, rpb);
+    size_t smem = 2 * DP * sizeof(float);
+    if (DP <= 512) {
+        DISPATCH_T(dtype, (ln_bwd_kernel<T, 16><<<blocks, WPB * 32, smem, ST>>>(
+                              (const T*)dy, lddy, z, ldz, gamma, mean, rstd, (T*)dz, lddz, (T*)dz_drop, lddd, dgamma,
+                              dbeta, rows, D, DP, rpb, ds, th, seed, site)));
+    } else {
+        DISPATCH_T(dtype, (ln_bwd_kernel<T, 32><<<blocks, WPB * 32, smem, ST>>>(
+                              (const T*)dy, lddy, z, ldz, gamma, mean, rstd, (T*)dz, lddz, (T*)dz_drop, lddd, dgamma,
+                              dbeta, rows, D, DP, rpb, ds, th, seed, site)));
+    }
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_dropout(int dtype, const void* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols,
+                            float p, uint64_t seed, uint64_t site, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    TGAN_CHECK_ARG(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "tgan_dropout: cols/ld must be multiples of 8");
+    uint32_t th = p > 0.f ? dropout_thresh(p) : 0u;
+    float ds = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    int64_t n = (int64_t)rows * (cols / 8);
+    DISPATCH_T(dtype, (dropout_kernel<T><<<grid_for(n, 256), 256, 0, ST>>>((const T*)src, lds, (T*)dst, ldd, rows,
+                                                                            cols / 8, ds, th, seed, site)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_ce_fwd(const float* logits, int64_t ldl, const int64_t* target, float* nll, float* lse, int rows,
+                           int V, void* stream) {
+    if (rows <= 0) return 0;
+    ce_fwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(logits, ldl, target, nll, lse, rows, V);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_ce_bwd(int dtype, const float* logits, int64_t ldl, const int64_t* target, const float* lse,
+                           const float* dnll, void* dlogits, int64_t ldd, int rows, int V, int VP, void* stream) {
+    if (rows <= 0) return 0;
+    TGAN_CHECK_ARG(VP % 8 == 0 && ldd % 8 == 0, "tgan_ce_bwd: VP/ldd must be multiples of 8");
+    DISPATCH_T(dtype, (ce_bwd_kernel<T><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(logits, ldl, target, lse, dnll,
+                                                                                   (T*)dlogits, ldd, rows, V, VP)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_gumbel_st_fwd(const float* logits, int64_t ldl, const float* U, int64_t ldu, float tau, float* y,
+                                  int64_t ldy, float* st, int64_t lds, int64_t* ids, int rows, int V, uint64_t seed,
+                                  uint64_t site, void* stream) {
+    if (rows <= 0) return 0;
+    TGAN_CHECK_ARG(y != nullptr && tau > 0.f, "tgan_gumbel_st_fwd: y buffer and tau > 0 required");
+    gumbel_fwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(logits, ldl, U, ldu, tau, y, ldy, st, lds, ids, rows,
+                                                                 V, seed, site);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_gumbel_st_bwd(const float* y, int64_t ldy, const float* dst, int64_t lds, float tau,
+                                  float* dlogits, int64_t ldd, int rows, int V, void* stream) {
+    if (rows <= 0) return 0;
+    gumbel_bwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(y, ldy, dst, lds, tau, dlogits, ldd, rows, V);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_colsum(int dtype, const void* x, int64_t ld, float* out, int rows, int cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    int by = min(ceil_div(rows, 64), 64);
+    int rpb = ceil_div(rows, by);
+    by = ceil_div(rows, rpb);
+    dim3 grid(ceil_div(cols, 32), by), block(32, 8);
+    DISPATCH_T(dtype, (colsum_kernel<T><<<grid, block, 0, ST>>>((const T*)x, ld, out, rows, cols, rpb)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_convert(int dtype_src, const void* src, int64_t lds, int dtype_dst, void* dst, int64_t ldd,
+                            int64_t rows, int cols, int cols_pad, void* stream) {
+    if (rows <= 0 || cols_pad <= 0) return 0;
+    int g = grid_for(rows * cols_pad, 256);
+#define CONV(TS, TD) convert_kernel<TS, TD><<<g, 256, 0, ST>>>((const TS*)src, lds, (TD*)dst, ldd, rows, cols, cols_pad)
+    if (dtype_src == TGAN_F32 && dtype_dst == TGAN_F32) CONV(float, float);
+    else if (dtype_src == TGAN_F32 && dtype_dst == TGAN_BF16) CONV(float, bf16);
+    else if (dtype_src == TGAN_BF16 && dtype_dst == TGAN_F32) CONV(bf16, float);
+    else if (dtype_src == TGAN_BF16 && dtype_dst == TGAN_BF16) CONV(bf16, bf16);
+    else { tgan_set_error("tgan_convert: bad dtype"); return 1; }
+#undef CONV
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_pack_params(int dtype, void* packed_mat, float* packed_vec, const int64_t* desc, int n_desc,
+                                int64_t max_elems, void* stream) {
+    if (n_desc <= 0) return 0;
+    dim3 grid(grid_for(max_elems, 256) > 64 ? 64 : grid_for(max_elems, 256), n_desc);
+    DISPATCH_T(dtype, (pack_kernel<T><<<grid, 256, 0, ST>>>((T*)packed_mat, packed_vec, desc)));
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_unpack_grads(const float* padded_mat, const float* padded_vec, const int64_t* desc, int n_desc,
+                                 int64_t max_elems, void* stream) {
+    if (n_desc <= 0) return 0;
+    dim3 grid(grid_for(max_elems, 256) > 64 ? 64 : grid_for(max_elems, 256), n_desc);
+    unpack_kernel<<<grid, 256, 0, ST>>>(padded_mat, padded_vec, desc);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_sumsq(const float* x, int64_t n, float* out, void* stream) {
+    if (n <= 0) return 0;
+    sumsq_kernel<<<grid_for(n, 256) > 296 ? 296 : grid_for(n, 256), 256, 0, ST>>>(x, n, out);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int tgan_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, const float* gnorm_sq, float clip,
+                              float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adam_kernel<<<grid_for(n, 256), 256, 0, ST>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                   gnorm_sq, clip, grad_scale);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,241 @@
+"""Drop-in replacement of the reference's ``model/mem_transformer.py`` on the libtgan_b200 kernels.
+
+Same module tree, parameter names / shapes (the checkpoint contract) and public methods as
+the reference -- ``MemTransformerLM(cfg, n_token, vec_len)`` with ``forward(data, target, reset_mems, mems)``
+(mem_transformer.py:653), ``forward_generate`` (:578), ``forward_generate_gumbel`` (:602), ``reset_length``
+(:432), ``init_mems`` (:436) -- but the sub-modules are parameter containers only: all arithmetic of ``_forward``
+(:484-576) and its backward runs in the CUDA library through ``tgan_b200.engine.TxlEngine``.  There is no eager /
+CPU fallback: calling the model on a CPU tensor raises.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from utils.proj_adaptive_softmax import ProjectedAdaptiveLogSoftmax
+from tgan_b200 import lib as L
+from tgan_b200.engine import RingMems, TxlDims, TxlEngine
+
+
+class PositionalEmbedding(nn.Module):
+    """mem_transformer.py:7-23 (the sinusoid itself is produced by tgan_pos_emb)."""
+
+    def __init__(self, demb):
+        super().__init__()
+        self.demb = demb
+        inv_freq = 1 / (10000 ** (torch.arange(0.0, demb, 2.0) / demb))
+        self.register_buffer("inv_freq", inv_freq)
+
+
+class PositionwiseFF(nn.Module):
+    """mem_transformer.py:26-60: parameters of the position-wise FFN + its LayerNorm."""
+
+    def __init__(self, d_model, d_inner, dropout, pre_lnorm=False):
+        super().__init__()
+        self.d_model, self.d_inner, self.dropout = d_model, d_inner, dropout
+        self.CoreNet = nn.Sequential(nn.Linear(d_model, d_inner), nn.ReLU(inplace=True), nn.Dropout(dropout),
+                                     nn.Linear(d_inner, d_model), nn.Dropout(dropout))
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.pre_lnorm = pre_lnorm
+
+
+class RelMultiHeadAttn(nn.Module):
+    """mem_transformer.py:63-160: parameters of the relative multi-head attention."""
+
+    def __init__(self, n_head, d_model, d_head, dropout, dropatt=0, tgt_len=None, mem_len=None, pre_lnorm=False):
+        super().__init__()
+        self.n_head, self.d_model, self.d_head, self.dropout = n_head, d_model, d_head, dropout
+        self.qkv_net = nn.Linear(d_model, 3 * n_head * d_head, bias=False)
+        self.drop = nn.Dropout(dropout)
+        self.dropatt = nn.Dropout(dropatt)
+        self.o_net = nn.Linear(n_head * d_head, d_model, bias=False)
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.scale = 1 / (d_head ** 0.5)
+        self.pre_lnorm = pre_lnorm
+
+
+class RelPartialLearnableMultiHeadAttn(RelMultiHeadAttn):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.r_net = nn.Linear(self.d_model, self.n_head * self.d_head, bias=False)
+
+
+class RelPartialLearnableDecoderLayer(nn.Module):
+    def __init__(self, n_head, d_model, d_head, d_inner, dropout, **kwargs):
+        super().__init__()
+        self.dec_attn = RelPartialLearnableMultiHeadAttn(n_head, d_model, d_head, dropout, **kwargs)
+        self.pos_ff = PositionwiseFF(d_model, d_inner, dropout, pre_lnorm=kwargs.get("pre_lnorm"))
+
+
+class AdaptiveEmbedding(nn.Module):
+    """mem_transformer.py:284-341 (div_val 1, cutoffs []): owns ``emb_layers.0.weight``."""
+
+    def __init__(self, n_token, d_embed, d_proj, vec_len, append_note_status):
+        super().__init__()
+        if append_note_status:
+            raise NotImplementedError("append_note_status is off in every shipped config and not accelerated")
+        if d_proj != d_embed:
+            raise NotImplementedError("d_proj != d_embed is not part of the accelerated path")
+        self.n_token, self.d_embed, self.d_proj = n_token, d_embed, d_proj
+        self.append_note_status = append_note_status
+        self.cutoffs = [n_token]
+        self.emb_scale = d_proj ** 0.5
+        self.emb_layers = nn.ModuleList([nn.Embedding(n_token, d_embed, sparse=False)])
+        self.emb_projs = nn.ParameterList()
+
+
+def _param_dict(model):
+    sd = dict(model.named_parameters())
+    sd.setdefault("crit.out_layers.0.weight", model.crit.out_layers[0].weight)
+    return sd
+
+
+class _TxlFunction(torch.autograd.Function):
+    """One autograd node for the whole generator stack (embedding .. NLL or Gumbel-ST output)."""
+
+    @staticmethod
+    def forward(ctx, model, mode, inp, target, reset, mems, temperature, noise, names, *params):
+        eng = model._get_engine()
+        need_grad = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
+        ectx = eng.forward(inp.detach(), reset, mems, mem_len=model.mem_len, same_length=model.same_length,
+                           training=model.training, target=target if mode == "mle" else None,
+                           n_pred=target.size(0) if mode == "mle" else None, save_for_backward=need_grad)
+        model._new_mems = ectx.new_mems
+        ctx.ectx, ctx.model, ctx.mode, ctx.names = ectx, model, mode, names
+        ctx.soft_in = inp.is_floating_point()
+        T, B, V = ectx.T, ectx.B, model.n_token
+        if mode == "mle":
+            return ectx.nll.view(T, B)
+        logits = torch.empty(T * B, V, dtype=torch.float32, device=eng.device)
+        if mode == "logits":
+            L.convert(ectx.logits, ectx.logits.stride(0), logits, V, T * B, V, V)
+            return logits.view(T, B, V)
+        # gumbel straight-through (mem_transformer.py:609-628)
+        y = torch.empty(T * B, V, dtype=torch.float32, device=eng.device)
+        U = None if noise is None else noise.reshape(T * B, V).to(device=eng.device, dtype=torch.float32).contiguous()
+        eng.calls += 1
+        L.gumbel_st_fwd(ectx.logits, U, float(temperature), y, logits, None, T * B, V, seed=eng.seed,
+                        site=eng._site(eng.calls, 3))
+        ctx.y, ctx.tau = y, float(temperature)
+        return logits.view(T, B, V)
+
+    @staticmethod
+    def backward(ctx, gout):
+        ectx, model, mode = ctx.ectx, ctx.model, ctx.mode
+        eng = model._get_engine()
+        if ectx.layers is None or len(ectx.layers) == 0:
+            raise RuntimeError("backward through a generator call that did not save activations")
+        T, B, V = ectx.T, ectx.B, model.n_token
+        gout = gout.contiguous().float()
+        if mode == "mle":
+            grads = eng.backward(ectx, dnll=gout, need_dinput=ctx.soft_in)
+        else:
+            g = gout.view(T * B, V)
+            if mode == "gumbel":
+                dl = torch.empty_like(g)
+                L.gumbel_st_bwd(ctx.y, g, ctx.tau, dl, T * B, V)
+                g = dl
+            grads = eng.backward(ectx, dlogits32=g, need_dinput=ctx.soft_in)
+        dinp = None
+        if ctx.soft_in:
+            d = grads["__dinput__"]
+            dinp = torch.empty(ectx.Q * B, V, dtype=torch.float32, device=eng.device)
+            L.convert(d, d.stride(0), dinp, V, ectx.Q * B, V, V)
+            dinp = dinp.view(ectx.Q, B, V)
+        return (None, None, dinp, None, None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+class MemTransformerLM(nn.Module):
+    def __init__(self, cfg, n_token, vec_len):
+        n_layer, n_head, d_model = cfg.MODEL.num_layers, cfg.MODEL.num_heads, cfg.MODEL.units
+        d_head = d_model // n_head
+        d_inner, dropout, dropatt = cfg.MODEL.inner_size, cfg.MODEL.dropout, cfg.MODEL.attention_dropout
+        pre_lnorm = cfg.MODEL.pre_lnorm
+        super().__init__()
+        if pre_lnorm:
+            raise NotImplementedError("pre_lnorm=True is off in every shipped config and not accelerated yet")
+        self.cfg = cfg
+        self.n_token = n_token
+        self.d_embed = self.d_model = d_model
+        self.n_head, self.d_head = n_head, d_head
+        self.pad_type = cfg.TRAIN.pad_type
+        self.replace_start_with_pad = cfg.TRAIN.replace_start_with_pad
+        self.word_emb = AdaptiveEmbedding(n_token, d_model, d_model, vec_len, cfg.TRAIN.append_note_status)
+        self.drop = nn.Dropout(dropout)
+        self.n_layer = n_layer
+        self.tgt_len, self.mem_len = cfg.TRAIN.tgt_length, cfg.TRAIN.mem_length
+        self.max_klen = self.tgt_len + self.mem_len
+        self.layers = nn.ModuleList([
+            RelPartialLearnableDecoderLayer(n_head, d_model, d_head, d_inner, dropout, tgt_len=self.tgt_len,
+                                            mem_len=self.mem_len, dropatt=dropatt, pre_lnorm=pre_lnorm)
+            for _ in range(n_layer)])
+        self.crit = ProjectedAdaptiveLogSoftmax(n_token, d_model, d_model)
+        if cfg.MODEL.tie_embedding:
+            self.crit.out_layers[0].weight = self.word_emb.emb_layers[0].weight
+        else:
+            raise NotImplementedError("tie_embedding=False is not part of the accelerated path")
+        self.same_length = cfg.MODEL.same_length
+        self.clamp_len = cfg.MODEL.clamp_len
+        self.detach_mems_grad = True  # kept for the GAN loop; memory is always detached (mem_transformer.py:461-475)
+        self.pos_emb = PositionalEmbedding(d_model)
+        self.r_w_bias = nn.Parameter(torch.Tensor(n_head, d_head))
+        self.r_r_bias = nn.Parameter(torch.Tensor(n_head, d_head))
+        # fp32 mode (TGAN_B200_DTYPE=fp32) reproduces the reference's fp32 arithmetic to 1e-4; bf16 is the default
+        self.compute_dtype = torch.float32 if os.environ.get("TGAN_B200_DTYPE", "bf16") == "fp32" else torch.bfloat16
+        self.kernel_impl = L.IMPL_AUTO
+        self._engine = None
+        self._new_mems = None
+
+    # ---- reference API ---------------------------------------------------------------------------------
+    def reset_length(self, tgt_len, mem_len):
+        self.tgt_len, self.mem_len = tgt_len, mem_len
+
+    def init_mems(self, n_layers):
+        if self.mem_len > 0:
+            param = next(self.parameters())
+            return torch.empty(n_layers + 1, 0, dtype=param.dtype, device=param.device)
+        return None
+
+    def _get_engine(self) -> TxlEngine:
+        dev = self.r_w_bias.device
+        if dev.type != "cuda":
+            raise RuntimeError("tgan_b200 MemTransformerLM runs on CUDA only (no CPU fallback): move the model to a GPU")
+        drop, dropatt = self.drop.p, self.layers[0].dec_attn.dropatt.p
+        e = self._engine
+        if e is None or e.device != dev or e.dtype != self.compute_dtype or e.impl != self.kernel_impl:
+            dims = TxlDims(self.n_layer, self.n_head, self.d_model, self.layers[0].pos_ff.d_inner, self.n_token,
+                           drop, dropatt, self.clamp_len)
+            e = TxlEngine(dims, dev, self.compute_dtype, seed=torch.initial_seed() & 0x7FFFFFFFFFFFFFFF,
+                          impl=self.kernel_impl)
+            self._engine = e
+        e.d.dropout, e.d.dropatt, e.d.clamp_len = drop, dropatt, self.clamp_len
+        e.bind_params(_param_dict(self))
+        return e
+
+    def _run(self, mode, data, target, reset_mems, mems, temperature=None, noise=None):
+        eng = self._get_engine()
+        names = [r for r, *_ in eng.layout.reference_map()]
+        pd = _param_dict(self)
+        out = _TxlFunction.apply(self, mode, data, target, reset_mems, mems, temperature, noise, names,
+                                 *[pd[n] for n in names])
+        return out, self._new_mems
+
+    def forward(self, data, target, reset_mems, mems, status_vec=None):
+        """-> (nll [tgt_len, bsz], new_mems)   (mem_transformer.py:653-670)"""
+        if status_vec is not None:
+            raise NotImplementedError("status_vec / append_note_status is not accelerated")
+        return self._run("mle", data, target, reset_mems, mems)
+
+    def forward_generate(self, data, mems, status_vec=None):
+        """-> (logits [T, bsz, n_token] fp32, new_mems)   (mem_transformer.py:578-600)"""
+        if status_vec is not None:
+            raise NotImplementedError("status_vec / append_note_status is not accelerated")
+        return self._run("logits", data, None, None, mems)
+
+    def forward_generate_gumbel(self, data, temperature, mems, status_vec=None, noise=None):
+        """-> (straight-through one-hot [T, bsz, n_token], new_mems)   (mem_transformer.py:602-651).
+        ``noise``: optional uniform [T, bsz, n_token] tensor replacing the reference's CPU ``torch.rand`` draw
+        (parity tests); default is device-side Philox."""
+        if status_vec is not None:
+            raise NotImplementedError("status_vec / append_note_status is not accelerated")
+        return self._run("gumbel", data, None, None, mems, temperature=temperature, noise=noise)

@@ -1,0 +1,625 @@
+"""Host-side orchestration of the Transformer-XL generator on the libtgan_b200 kernels.
+
+This file owns *plumbing only*: device buffers (torch tensors used as raw memory), the padded parameter layout,
+the recurrence-memory ring buffer and the order in which the C-ABI kernels are enqueued.  All arithmetic happens
+in libtgan_b200.so; nothing here calls a torch math op on the hot path.
+
+Reference behaviour implemented (file:line relative to /root/reference/model):
+  * MemTransformerLM._forward            mem_transformer.py:484-576
+  * RelPartialLearnableMultiHeadAttn     mem_transformer.py:162-257   (post-LN)
+  * PositionwiseFF                       mem_transformer.py:46-60     (post-LN)
+  * _update_mems                         mem_transformer.py:445-482   (ring buffer: zero-copy)
+  * ProjectedAdaptiveLogSoftmax          utils/proj_adaptive_softmax.py:64-84 (cutoffs == [])
+and the closed-form backward of all of them.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import lib as L
+
+
+def _ceil(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class TxlDims:
+    n_layer: int
+    n_head: int
+    d_model: int
+    d_inner: int
+    n_token: int
+    dropout: float = 0.0
+    dropatt: float = 0.0
+    clamp_len: int = -1
+
+    @property
+    def d_head(self) -> int:
+        return self.d_model // self.n_head
+
+    @property
+    def DP(self) -> int:
+        return _ceil(self.d_model, 64)
+
+    @property
+    def NH(self) -> int:
+        return self.n_head * L.HS
+
+    @property
+    def DIP(self) -> int:
+        return _ceil(self.d_inner, 64)
+
+    @property
+    def VP(self) -> int:
+        return _ceil(self.n_token, 64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# recurrence memory: ring buffer of the layer inputs (mem_transformer.py:445-482 without the copy)
+# ---------------------------------------------------------------------------------------------------------
+class RingMems:
+    """Per-layer-input memory [n_layer+1 slabs] x [capacity positions] x [B] x [DP] in the compute dtype.
+
+    ``start`` is the ring position of logical memory row 0, ``length`` the number of valid memory rows.
+    The reference returns a fresh ``[n_layer+1, M, B, d_model]`` fp32 tensor per call; ``materialize()``
+    produces exactly that tensor (for tests, checkpoints and the generate.py self-check)."""
+
+    def __init__(self, slabs: torch.Tensor, start: int, length: int, d_model: int):
+        self.slabs = slabs
+        self.start = start
+        self.length = length
+        self.d_model = d_model
+
+    @property
+    def capacity(self) -> int:
+        return self.slabs.shape[1]
+
+    @property
+    def bsz(self) -> int:
+        return self.slabs.shape[2]
+
+    def segments(self, first: int, count: int) -> List[Tuple[int, int]]:
+        """physical (position, count) runs covering logical rows [first, first+count)."""
+        out, C = [], self.capacity
+        pos = (self.start + first) % C
+        while count > 0:
+            n = min(count, C - pos)
+            out.append((pos, n))
+            pos = (pos + n) % C
+            count -= n
+        return out
+
+    def materialize(self) -> torch.Tensor:
+        """-> fp32 [n_layer+1, length, B, d_model] (logical order), via tgan_convert."""
+        S, C, B, DP = self.slabs.shape
+        out = torch.empty(S, self.length, B, self.d_model, dtype=torch.float32, device=self.slabs.device)
+        for s in range(S):
+            row = 0
+            for pos, n in self.segments(0, self.length):
+                L.convert(self.slabs, DP, out, self.d_model, n * B, self.d_model, self.d_model,
+                          src_off=(s * C + pos) * B * DP, dst_off=(s * self.length + row) * B * self.d_model)
+                row += n
+        return out
+
+    # tensor-ish conveniences used by callers that treat mems as opaque
+    def size(self, dim=None):
+        shp = (self.slabs.shape[0], self.length, self.bsz, self.d_model)
+        return shp if dim is None else shp[dim]
+
+    @property
+    def shape(self):
+        return self.size()
+
+    def __len__(self):
+        return self.slabs.shape[0]
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def detach(self):
+        return self
+
+    def numel(self):
+        s = self.size()
+        return s[0] * s[1] * s[2] * s[3]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter layout
+# ---------------------------------------------------------------------------------------------------------
+class ParamLayout:
+    """Offsets of the padded (kernel-private) parameter copies and of the padded fp32 gradient buffers."""
+
+    def __init__(self, d: TxlDims):
+        self.d = d
+        DP, NH, DIP, VP = d.DP, d.NH, d.DIP, d.VP
+        self.mat: Dict[str, Tuple[int, int, int]] = {}  # name -> (offset, rows, ld)
+        self.gmat: Dict[str, Tuple[int, int, int]] = {}
+        self.vec: Dict[str, Tuple[int, int]] = {}  # name -> (offset, n)
+        mo = go = vo = 0
+
+        def add_mat(name, rows, ld, grad=True, transposed=True):
+            nonlocal mo, go
+            self.mat[name] = (mo, rows, ld)
+            mo += rows * ld
+            if transposed:
+                self.mat[name + ".T"] = (mo, ld, rows)
+                mo += rows * ld
+            if grad:
+                self.gmat[name] = (go, rows, ld)
+                go += rows * ld
+
+        def add_vec(name, n):
+            nonlocal vo
+            self.vec[name] = (vo, n)
+            vo += n
+
+        add_mat("E", VP, DP)
+        add_vec("u", NH)
+        add_vec("vb", NH)
+        add_vec("bias_out", VP)
+        for l in range(d.n_layer):
+            p = f"l{l}."
+            add_mat(p + "Wqkv", 3 * NH, DP)
+            add_mat(p + "Wr", NH, DP, transposed=False)
+            add_mat(p + "Wo", DP, NH)
+            add_mat(p + "W1", DIP, DP)
+            add_mat(p + "W2", DP, DIP)
+            for v, n in (("b1", DIP), ("b2", DP), ("ln1_g", DP), ("ln1_b", DP), ("ln2_g", DP), ("ln2_b", DP)):
+                add_vec(p + v, n)
+        self.mat_elems, self.gmat_elems, self.vec_elems = mo, go, vo
+
+    def reference_map(self):
+        """(reference state_dict name, packed name, kind, row_group, row_pad, col_group, col_pad)."""
+        d = self.d
+        dh = d.d_head
+        out = [("word_emb.emb_layers.0.weight", "E", "mat", 1, 1, 1, 1),
+               ("r_w_bias", "u", "vec", 1, 1, dh, L.HS),
+               ("r_r_bias", "vb", "vec", 1, 1, dh, L.HS),
+               ("crit.out_layers.0.bias", "bias_out", "vec", 1, 1, 1, 1)]
+        for l in range(d.n_layer):
+            r, p = f"layers.{l}.", f"l{l}."
+            out += [
+                (r + "dec_attn.qkv_net.weight", p + "Wqkv", "mat", dh, L.HS, 1, 1),
+                (r + "dec_attn.r_net.weight", p + "Wr", "mat", dh, L.HS, 1, 1),
+                (r + "dec_attn.o_net.weight", p + "Wo", "mat", 1, 1, dh, L.HS),
+                (r + "pos_ff.CoreNet.0.weight", p + "W1", "mat", 1, 1, 1, 1),
+                (r + "pos_ff.CoreNet.3.weight", p + "W2", "mat", 1, 1, 1, 1),
+                (r + "pos_ff.CoreNet.0.bias", p + "b1", "vec", 1, 1, 1, 1),
+                (r + "pos_ff.CoreNet.3.bias", p + "b2", "vec", 1, 1, 1, 1),
+                (r + "dec_attn.layer_norm.weight", p + "ln1_g", "vec", 1, 1, 1, 1),
+                (r + "dec_attn.layer_norm.bias", p + "ln1_b", "vec", 1, 1, 1, 1),
+                (r + "pos_ff.layer_norm.weight", p + "ln2_g", "vec", 1, 1, 1, 1),
+                (r + "pos_ff.layer_norm.bias", p + "ln2_b", "vec", 1, 1, 1, 1),
+            ]
+        return out
+
+
+class _Ctx:
+    """Everything one forward saved for its backward."""
+    pass
+
+
+class TxlEngine:
+    """Forward / backward of the generator stack on libtgan_b200."""
+
+    def __init__(self, dims: TxlDims, device, dtype=torch.bfloat16, seed: int = 1111, impl: int = L.IMPL_AUTO):
+        if dims.d_head > L.HS:
+            raise NotImplementedError(f"d_head {dims.d_head} > {L.HS} is not supported by the attention kernels")
+        if dims.d_model % 2:
+            raise NotImplementedError("odd d_model")
+        self.d = dims
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.impl = impl
+        self.seed = seed
+        self.calls = 0
+        self.layout = ParamLayout(dims)
+        lay = self.layout
+        self.pmat = torch.zeros(lay.mat_elems, dtype=dtype, device=self.device)
+        self.pvec = torch.zeros(lay.vec_elems, dtype=torch.float32, device=self.device)
+        self.gmat = torch.zeros(lay.gmat_elems, dtype=torch.float32, device=self.device)
+        self.gvec = torch.zeros(lay.vec_elems, dtype=torch.float32, device=self.device)
+        self.inv_freq = (1 / (10000 ** (torch.arange(0.0, dims.d_model, 2.0) / dims.d_model))).to(self.device)
+        self._params: Optional[Dict[str, torch.Tensor]] = None
+        self._param_key = None
+        self._packed_version = None
+        self._pack_desc = None
+        self._es = 2 if dtype == torch.bfloat16 else 4
+
+    # -- parameters ---------------------------------------------------------------------------------------
+    def bind_params(self, params: Dict[str, torch.Tensor]):
+        """params: reference-layout fp32 CUDA tensors keyed by generator state_dict names."""
+        key = tuple((n, params[n].data_ptr()) for n, *_ in self.layout.reference_map())
+        if key == self._param_key:
+            self._params = params
+            return
+        d, lay = self.d, self.layout
+        rows_pack, rows_unpack, max_elems = [], [], 1
+        self._grad_shapes = {}
+        for ref, name, kind, rg, rgp, cg, cgp in lay.reference_map():
+            t = params[ref]
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise L.TganError(f"parameter {ref} must be a contiguous fp32 CUDA tensor")
+            if t.dim() == 2:
+                r, c = t.shape
+            else:
+                r, c = 1, t.numel()
+            if name in ("u", "vb"):
+                r, c = 1, t.numel()  # [N, dh] flattened: column groups of dh -> 64
+            max_elems = max(max_elems, r * c)
+            self._grad_shapes[ref] = tuple(t.shape)
+            if kind == "mat":
+                off, _, ld = lay.mat[name]
+                rows_pack.append([t.data_ptr(), off, r, c, ld, rg, rgp, cg, cgp, 0, 0, 0])
+                if name + ".T" in lay.mat:
+                    offt, _, ldt = lay.mat[name + ".T"]
+                    rows_pack.append([t.data_ptr(), offt, r, c, ldt, rg, rgp, cg, cgp, 1, 0, 0])
+                goff, _, gld = lay.gmat[name]
+                rows_unpack.append([0, goff, r, c, gld, rg, rgp, cg, cgp, 0, 0, 0])
+            else:
+                off, _ = lay.vec[name]
+                rows_pack.append([t.data_ptr(), off, r, c, c, rg, rgp, cg, cgp, 0, 1, 0])
+                rows_unpack.append([0, off, r, c, c, rg, rgp, cg, cgp, 0, 1, 0])
+        self._pack_desc = torch.tensor(rows_pack, dtype=torch.int64, device=self.device)
+        self._unpack_rows = rows_unpack
+        self._max_elems = max_elems
+        self._params = params
+        self._param_key = key
+        self._packed_version = None
+        self.pmat.zero_()
+        self.pvec.zero_()
+
+    def pack(self):
+        ver = tuple(p._version for p in self._params.values())
+        if ver == self._packed_version:
+            return
+        L.pack_params(self.pmat, self.pvec, self._pack_desc, self._pack_desc.shape[0], self._max_elems)
+        self._packed_version = ver
+
+    def _m(self, name):  # (tensor, element offset, ld)
+        off, rows, ld = self.layout.mat[name]
+        return off, ld
+
+    def _v(self, name) -> int:  # pointer (int) into pvec
+        return self.pvec.data_ptr() + 4 * self.layout.vec[name][0]
+
+    def _gv(self, name) -> int:
+        return self.gvec.data_ptr() + 4 * self.layout.vec[name][0]
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _site(self, call_id: int, local: int) -> int:
+        return call_id * 256 + local
+
+    def _buf(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.dtype, device=self.device)
+
+    def new_ring(self, B: int, Q: int, mem_len: int) -> RingMems:
+        cap = mem_len + Q
+        slabs = torch.zeros(self.d.n_layer + 1, cap, B, self.d.DP, dtype=self.dtype, device=self.device)
+        return RingMems(slabs, 0, 0, self.d.d_model)
+
+    def import_mems(self, mems: torch.Tensor, Q: int, mem_len: int) -> RingMems:
+        """reference-layout fp32 mems [n_layer+1, M, B, d_model] -> ring (tgan_convert pads and casts)."""
+        S, M, B, D = mems.shape
+        ring = self.new_ring(B, Q, max(mem_len, M))
+        mems = mems.contiguous().float()
+        C, DP = ring.capacity, self.d.DP
+        for s in range(S):
+            L.convert(mems, D, ring.slabs, DP, M * B, D, DP, src_off=s * M * B * D, dst_off=s * C * B * DP)
+        ring.length = M
+        return ring
+
+    def _prepare_ring(self, mems, B: int, Q: int, mem_len: int) -> RingMems:
+        if mems is None or (isinstance(mems, torch.Tensor) and mems.numel() == 0):
+            return self.new_ring(B, Q, mem_len)
+        if isinstance(mems, torch.Tensor):
+            return self.import_mems(mems, Q, mem_len)
+        ring: RingMems = mems
+        if ring.bsz != B:
+            raise L.TganError(f"memory batch size {ring.bsz} != input batch size {B}")
+        w = (ring.start + ring.length) % ring.capacity
+        if ring.length > mem_len:  # reset_length shrank the memory: keep the most recent rows
+            ring.start = (ring.start + ring.length - mem_len) % ring.capacity
+            ring.length = mem_len
+        if ring.capacity < min(ring.length, mem_len) + Q or w + Q > ring.capacity or ring.capacity < mem_len + Q:
+            # re-layout (rare: tgt_len / mem_len changed between calls): compact into a fresh ring
+            return self.import_mems(ring.materialize(), Q, mem_len)
+        return ring
+
+    # -- forward ------------------------------------------------------------------------------------------
+    def forward(self, inp: torch.Tensor, reset: Optional[torch.Tensor], mems, *, mem_len: int, same_length: bool,
+                training: bool, target: Optional[torch.Tensor] = None, n_pred: Optional[int] = None,
+                save_for_backward: bool = True) -> _Ctx:
+        """inp: int64 [Q,B] token ids or float [Q,B,V] soft one-hot rows.  Returns a ctx with
+        ``nll`` (fp32 [T*B], when target is given), ``logits`` (fp32 [T*B, VP]) and ``new_mems``."""
+        d, lay, dt = self.d, self.layout, self.dtype
+        DP, NH, DIP, VP, D = d.DP, d.NH, d.DIP, d.VP, d.d_model
+        self.pack()
+        Q, B = inp.shape[0], inp.shape[1]
+        ring = self._prepare_ring(mems, B, Q, mem_len) if mem_len > 0 else self.new_ring(B, Q, 0)
+        M = ring.length
+        K = M + Q
+        R, KR = Q * B, K * B
+        C = ring.capacity
+        w = (ring.start + M) % C  # write position of this segment
+        if w + Q > C:
+            raise L.TganError("internal: ring write would wrap")
+        self.calls += 1
+        cid = self.calls
+        p_drop = d.dropout if training else 0.0
+        p_att = d.dropatt if training else 0.0
+        seed = self.seed
+        ctx = _Ctx()
+        ctx.Q, ctx.B, ctx.M, ctx.K, ctx.cid, ctx.p_drop, ctx.p_att = Q, B, M, K, cid, p_drop, p_att
+        ctx.ring, ctx.w, ctx.same_length, ctx.training = ring, w, same_length, training
+        slab_elems = C * B * DP
+        cur_off = [s * slab_elems + w * B * DP for s in range(d.n_layer + 1)]
+        ctx.cur_off = cur_off
+        ctx.mem_segs = ring.segments(0, M)
+        # contiguous runs of [memory rows; current rows] in logical order
+        segs = list(ctx.mem_segs) + [(w, Q)]
+        merged = []
+        for pos, n in segs:
+            if merged and merged[-1][0] + merged[-1][1] == pos:
+                merged[-1] = (merged[-1][0], merged[-1][1] + n)
+            else:
+                merged.append((pos, n))
+        ctx.x_segs = merged
+        # same_length mask shift (mem_transformer.py:496-503)
+        msl = Q
+        if same_length:
+            mask_len = K - mem_len
+            msl = Q - mask_len if mask_len > 0 else Q
+        ctx.msl = msl
+        reset_u8 = None
+        if reset is not None and M > 0:
+            reset_u8 = reset.to(device=self.device, dtype=torch.uint8).contiguous()
+        ctx.reset = reset_u8
+        slabs = ring.slabs
+        es = self._es
+
+        # 1. embedding (-> ring slab 0, current rows)
+        if inp.dim() == 2:
+            ids = inp.to(self.device).contiguous()
+            ctx.ids, ctx.soft = ids, None
+            eoff, eld = self._m("E")
+            L.embed_fwd(ids, self.pmat[eoff:], slabs, R, D, DP, math.sqrt(D), p_drop, seed, self._site(cid, 0),
+                        out_off=cur_off[0])
+        else:
+            V = d.n_token
+            soft = self._buf(R, VP)
+            L.convert(inp.contiguous().float(), V, soft, VP, R, V, VP)
+            ctx.ids, ctx.soft = None, soft
+            etoff, etld = self._m("E.T")
+            L.gemm(soft, self.pmat, slabs, transB=True, M=R, N=D, K=VP, lda=VP, ldb=etld, ldc=DP, b_off=etoff,
+                   c_off=cur_off[0], alpha=math.sqrt(D), flags=L.EPI_DROPOUT if p_drop > 0 else 0, drop_p=p_drop,
+                   seed=seed, site=self._site(cid, 0), impl=self.impl)
+        # 2. positional embedding
+        pe = self._buf(K, DP)
+        L.pos_emb(self.inv_freq, pe, K, D, DP, d.clamp_len, p_drop, seed, self._site(cid, 1))
+        ctx.pe = pe
+        scale = 1.0 / math.sqrt(d.d_head)
+        ctx.layers = []
+        for l in range(d.n_layer):
+            p = f"l{l}."
+            sv = _Ctx()
+            woff, wld = self._m(p + "Wqkv")
+            q = self._buf(R, NH)
+            kv = self._buf(KR, 2 * NH)
+            r = self._buf(K, NH)
+            x_base = l * slab_elems
+            L.gemm(slabs, self.pmat, q, M=R, N=NH, K=DP, lda=DP, ldb=wld, a_off=cur_off[l], b_off=woff, impl=self.impl)
+            row = 0
+            for pos, n in ctx.x_segs:
+                L.gemm(slabs, self.pmat, kv, M=n * B, N=2 * NH, K=DP, lda=DP, ldb=wld, a_off=x_base + pos * B * DP,
+                       b_off=woff + NH * wld, c_off=row * B * 2 * NH, impl=self.impl)
+                row += n
+            roff, rld = self._m(p + "Wr")
+            L.gemm(pe, self.pmat, r, M=K, N=NH, K=DP, ldb=rld, b_off=roff, impl=self.impl)
+            att = self._buf(R, NH)
+            lse = self._buf(B * d.n_head * Q, dtype=torch.float32)
+            L.relattn_fwd(q, kv, kv, 2 * NH, r, self._v("u"), self._v("vb"), reset_u8, att, lse, B, d.n_head, Q, M, msl,
+                          same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=self.impl, v_off=NH)
+            # O projection + dropout + residual (fp32) -> LN
+            ooff, old = self._m(p + "Wo")
+            z1 = self._buf(R, DP, dtype=torch.float32)
+            L.gemm(att, self.pmat, z1, M=R, N=DP, K=NH, ldb=old, b_off=ooff, aux=slabs, aux_off=cur_off[l], ldaux=DP,
+                   flags=L.EPI_ADD_AUX | (L.EPI_DROPOUT if p_drop > 0 else 0), drop_p=p_drop, seed=seed,
+                   site=self._site(cid, 9 + 4 * l), impl=self.impl)
+            a = self._buf(R, DP)
+            mean1, rstd1 = self._buf(R, dtype=torch.float32), self._buf(R, dtype=torch.float32)
+            L.ln_fwd(z1, a, self._v(p + "ln1_g"), self._v(p + "ln1_b"), mean1, rstd1, R, D, DP)
+            # FFN
+            w1off, w1ld = self._m(p + "W1")
+            h = self._buf(R, DIP)
+            L.gemm(a, self.pmat, h, M=R, N=DIP, K=DP, ldb=w1ld, b_off=w1off, bias=self._v(p + "b1"),
+                   flags=L.EPI_BIAS | L.EPI_RELU | (L.EPI_DROPOUT if p_drop > 0 else 0), drop_p=p_drop, seed=seed,
+                   site=self._site(cid, 10 + 4 * l), impl=self.impl)
+            w2off, w2ld = self._m(p + "W2")
+            z2 = self._buf(R, DP, dtype=torch.float32)
+            L.gemm(h, self.pmat, z2, M=R, N=DP, K=DIP, ldb=w2ld, b_off=w2off, bias=self._v(p + "b2"), aux=a, ldaux=DP,
+                   flags=L.EPI_BIAS | L.EPI_ADD_AUX | (L.EPI_DROPOUT if p_drop > 0 else 0), drop_p=p_drop, seed=seed,
+                   site=self._site(cid, 11 + 4 * l), impl=self.impl)
+            mean2, rstd2 = self._buf(R, dtype=torch.float32), self._buf(R, dtype=torch.float32)
+            L.ln_fwd(z2, slabs, self._v(p + "ln2_g"), self._v(p + "ln2_b"), mean2, rstd2, R, D, DP,
+                     y_off=cur_off[l + 1])
+            if save_for_backward:
+                sv.q, sv.kv, sv.r, sv.att, sv.lse = q, kv, r, att, lse
+                sv.z1, sv.a, sv.mean1, sv.rstd1 = z1, a, mean1, rstd1
+                sv.h, sv.z2, sv.mean2, sv.rstd2 = h, z2, mean2, rstd2
+                ctx.layers.append(sv)
+        # 3. final dropout, logits, NLL
+        T = Q if n_pred is None else n_pred
+        ctx.T = T
+        RT = T * B
+        hid_off = cur_off[d.n_layer] + (Q - T) * B * DP
+        if p_drop > 0:
+            hidden = self._buf(RT, DP)
+            L.dropout(slabs, hidden, RT, DP, DP, DP, p_drop, seed, self._site(cid, 2), src_off=hid_off)
+            hid_t, hid_o = hidden, 0
+        else:
+            hid_t, hid_o = slabs, hid_off
+        ctx.hid_t, ctx.hid_o = hid_t, hid_o
+        eoff, eld = self._m("E")
+        logits = self._buf(RT, VP, dtype=torch.float32)
+        L.gemm(hid_t, self.pmat, logits, M=RT, N=d.n_token, K=DP, lda=DP, ldb=eld, a_off=hid_o, b_off=eoff,
+               bias=self._v("bias_out"), flags=L.EPI_BIAS, impl=self.impl)
+        ctx.logits = logits
+        ctx.nll = None
+        if target is not None:
+            tgt = target.to(self.device).contiguous().view(-1)
+            nll = self._buf(RT, dtype=torch.float32)
+            lse_ce = self._buf(RT, dtype=torch.float32)
+            L.ce_fwd(logits, tgt, nll, lse_ce, RT, d.n_token)
+            ctx.target, ctx.nll, ctx.lse_ce = tgt, nll, lse_ce
+        # 4. memory update: the layer inputs already sit in the ring; only the window moves
+        if mem_len > 0:
+            new_len = min(M + Q, mem_len)
+            new_start = (ring.start + M + Q - new_len) % C
+            ctx.new_mems = RingMems(ring.slabs, new_start, new_len, D)
+        else:
+            ctx.new_mems = None
+        return ctx
+
+    # -- backward -----------------------------------------------------------------------------------------
+    def backward(self, ctx: _Ctx, dnll: Optional[torch.Tensor] = None, dlogits32: Optional[torch.Tensor] = None,
+                 need_dinput: bool = False) -> Dict[str, torch.Tensor]:
+        """Gradients (reference layout, fp32) of sum(nll * dnll) [+ sum(logits * dlogits32)] w.r.t. every
+        generator parameter.  With need_dinput the gradient w.r.t. the soft one-hot input rows is returned
+        under the key '__dinput__' (fp32 [Q*B, VP])."""
+        d, lay, dt = self.d, self.layout, self.dtype
+        DP, NH, DIP, VP, D = d.DP, d.NH, d.DIP, d.VP, d.d_model
+        Q, B, M, K, cid = ctx.Q, ctx.B, ctx.M, ctx.K, ctx.cid
+        R, KR, T = Q * B, K * B, ctx.T
+        RT = T * B
+        seed, p_drop, p_att = self.seed, ctx.p_drop, ctx.p_att
+        slabs = ctx.ring.slabs
+        slab_elems = ctx.ring.capacity * B * DP
+        cur_off = ctx.cur_off
+        impl = self.impl
+        gm, gv = self.gmat, self.gvec
+        gv.zero_()
+        written = set()
+
+        def wgrad(name, dY, X, rows, n_out, k_in, *, dy_off=0, x_off=0, ldy=None, ldx=None, row_off=0):
+            """gmat[name][row_off : row_off+n_out, :k_in] (+)= dY^T X"""
+            goff, _, gld = lay.gmat[name]
+            key = (name, row_off)
+            L.gemm(dY, X, gm, transA=True, transB=False, M=n_out, N=k_in, K=rows, lda=ldy, ldb=ldx, ldc=gld,
+                   a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld,
+                   flags=L.EPI_ACCUM if key in written else 0, impl=impl)
+            written.add(key)
+
+        # ---- loss head
+        dl = self._buf(RT, VP)
+        if dnll is not None:
+            L.ce_bwd(ctx.logits, ctx.target, ctx.lse_ce, dnll.contiguous().view(-1).float(), dl, RT, d.n_token, VP)
+            if dlogits32 is not None:
+                raise L.TganError("either dnll or dlogits32")
+        else:
+            L.convert(dlogits32, dlogits32.stride(0), dl, VP, RT, d.n_token, VP)
+        L.colsum(dl, gv, RT, d.n_token, ld=VP, out_off=lay.vec["bias_out"][0])
+        wgrad("E", dl, ctx.hid_t, RT, VP, DP, ldy=VP, ldx=DP, x_off=ctx.hid_o)
+        etoff, etld = self._m("E.T")
+        dx = self._buf(R, DP)
+        if T < Q:
+            dx.zero_()
+        dxo = (Q - T) * B * DP
+        L.gemm(dl, self.pmat, dx, M=RT, N=DP, K=VP, lda=VP, ldb=etld, b_off=etoff, c_off=dxo, impl=impl)
+        if p_drop > 0:
+            L.dropout(dx, dx, RT, DP, DP, DP, p_drop, seed, self._site(cid, 2), src_off=dxo, dst_off=dxo)
+        scale = 1.0 / math.sqrt(d.d_head)
+        for l in reversed(range(d.n_layer)):
+            p = f"l{l}."
+            sv = ctx.layers[l]
+            x_base = l * slab_elems
+            # LN2 backward
+            dz2, dz2d = self._buf(R, DP), (self._buf(R, DP) if p_drop > 0 else None)
+            L.ln_bwd(dx, sv.z2, self._v(p + "ln2_g"), sv.mean2, sv.rstd2, dz2, dz2d, self._gv(p + "ln2_g"),
+                     self._gv(p + "ln2_b"), R, D, DP, p_drop, seed, self._site(cid, 11 + 4 * l))
+            g2 = dz2d if dz2d is not None else dz2
+            L.colsum(g2, gv, R, D, ld=DP, out_off=lay.vec[p + "b2"][0])
+            wgrad(p + "W2", g2, sv.h, R, DP, DIP, ldy=DP, ldx=DIP)
+            w2toff, w2tld = self._m(p + "W2.T")
+            dh = self._buf(R, DIP)
+            L.gemm(g2, self.pmat, dh, M=R, N=DIP, K=DP, ldb=w2tld, b_off=w2toff, aux=sv.h, ldaux=DIP,
+                   flags=L.EPI_MASK_POS, alpha=1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0, impl=impl)
+            L.colsum(dh, gv, R, d.d_inner, ld=DIP, out_off=lay.vec[p + "b1"][0])
+            wgrad(p + "W1", dh, sv.a, R, DIP, DP, ldy=DIP, ldx=DP)
+            w1toff, w1tld = self._m(p + "W1.T")
+            da = self._buf(R, DP)
+            L.gemm(dh, self.pmat, da, M=R, N=DP, K=DIP, ldb=w1tld, b_off=w1toff, aux=dz2, ldaux=DP,
+                   flags=L.EPI_ADD_AUX, impl=impl)
+            # LN1 backward
+            dz1, dz1d = self._buf(R, DP), (self._buf(R, DP) if p_drop > 0 else None)
+            L.ln_bwd(da, sv.z1, self._v(p + "ln1_g"), sv.mean1, sv.rstd1, dz1, dz1d, self._gv(p + "ln1_g"),
+                     self._gv(p + "ln1_b"), R, D, DP, p_drop, seed, self._site(cid, 9 + 4 * l))
+            g1 = dz1d if dz1d is not None else dz1
+            wgrad(p + "Wo", g1, sv.att, R, DP, NH, ldy=DP, ldx=NH)
+            wotoff, wotld = self._m(p + "Wo.T")
+            datt = self._buf(R, NH)
+            L.gemm(g1, self.pmat, datt, M=R, N=NH, K=DP, ldb=wotld, b_off=wotoff, impl=impl)
+            # attention core backward
+            dq = self._buf(R, NH)
+            dkv = self._buf(KR, 2 * NH)
+            dr32 = self._buf(K, NH, dtype=torch.float32)
+            delta = self._buf(B * d.n_head * Q, dtype=torch.float32)
+            L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
+                          sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
+                          ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,
+                          v_off=NH, dv_off=NH)
+            if dt == torch.float32:
+                dr = dr32
+            else:
+                dr = self._buf(K, NH)
+                L.convert(dr32, NH, dr, NH, K, NH, NH)
+            wgrad(p + "Wr", dr, ctx.pe, K, NH, DP, ldy=NH, ldx=DP)
+            wgrad(p + "Wqkv", dq, slabs, R, NH, DP, ldy=NH, ldx=DP, x_off=cur_off[l])
+            row = 0
+            for pos, n in ctx.x_segs:
+                wgrad(p + "Wqkv", dkv, slabs, n * B, 2 * NH, DP, ldy=2 * NH, ldx=DP, dy_off=row * B * 2 * NH,
+                      x_off=x_base + pos * B * DP, row_off=NH)
+                row += n
+            # dx_l = dz1 + dq Wq + dkv[current rows] Wkv
+            wtoff, wtld = self._m(p + "Wqkv.T")
+            t = self._buf(R, DP)
+            L.gemm(dq, self.pmat, t, M=R, N=DP, K=NH, ldb=wtld, b_off=wtoff, aux=dz1, ldaux=DP, flags=L.EPI_ADD_AUX,
+                   impl=impl)
+            dx = self._buf(R, DP)
+            L.gemm(dkv, self.pmat, dx, M=R, N=DP, K=2 * NH, lda=2 * NH, ldb=wtld, a_off=M * B * 2 * NH,
+                   b_off=wtoff + NH, aux=t, ldaux=DP, flags=L.EPI_ADD_AUX, impl=impl)
+        # ---- embedding
+        out: Dict[str, torch.Tensor] = {}
+        goff, _, gld = lay.gmat["E"]
+        if ctx.ids is not None:
+            L.embed_bwd(ctx.ids, dx, gm[goff:], R, d.n_token, D, DP, math.sqrt(D), p_drop, seed, self._site(cid, 0))
+        else:
+            if p_drop > 0:
+                L.dropout(dx, dx, R, DP, DP, DP, p_drop, seed, self._site(cid, 0))
+            # dE[v, :] += sqrt(D) * soft^T dx ;  dsoft = sqrt(D) * dx E^T
+            L.gemm(ctx.soft, dx, gm, transA=True, transB=False, M=VP, N=DP, K=R, lda=VP, ldb=DP, ldc=gld, c_off=goff,
+                   alpha=math.sqrt(D), flags=L.EPI_ACCUM, impl=impl)
+            if need_dinput:
+                eoff, eld = self._m("E")
+                dsoft = self._buf(R, VP, dtype=torch.float32)
+                L.gemm(dx, self.pmat, dsoft, M=R, N=d.n_token, K=DP, ldb=eld, b_off=eoff, alpha=math.sqrt(D), impl=impl)
+                out["__dinput__"] = dsoft
+        # ---- unpack to reference-layout gradients
+        grads = {}
+        rows = []
+        for (ref, name, kind, *_), urow in zip(lay.reference_map(), self._unpack_rows):
+            g = torch.empty(self._grad_shapes[ref], dtype=torch.float32, device=self.device)
+            grads[ref] = g
+            rows.append([g.data_ptr()] + urow[1:])
+        desc = torch.tensor(rows, dtype=torch.int64, device=self.device)
+        L.unpack_grads(gm, gv, desc, len(rows), self._max_elems)
+        ctx.layers = None  # release activations
+        out.update(grads)
+        out["__desc__"] = desc  # keep the descriptor table alive until the kernel ran
+        return out

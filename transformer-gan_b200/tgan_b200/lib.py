@@ -1,0 +1,225 @@
+"""ctypes binding of libtgan_b200.so (C ABI declared in include/tgan_b200.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing this module raises.
+Tensors are passed as raw device pointers (``tensor.data_ptr()``), the stream is torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_ulonglong, c_void_p
+
+import torch
+
+F32, BF16 = 0, 1
+HS = 64
+EPI_BIAS, EPI_RELU, EPI_MASK_POS, EPI_ADD_AUX, EPI_ACCUM, EPI_DROPOUT, EPI_AUX_F32 = 1, 2, 4, 8, 16, 32, 64
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtgan_b200.so")
+
+
+class TganError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with transformer-gan_b200/csrc/build.sh (or __graft_entry__.build()). "
+            "tgan_b200 has no CPU / eager fallback.")
+    return ctypes.CDLL(LIB_PATH)
+
+
+_lib = _load()
+_lib.tgan_last_error.restype = c_char_p
+_lib.tgan_launch_count.restype = c_ulonglong
+
+P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
+_SIGS = {
+    "tgan_gemm": [I, I, I, I, I, I, I, P, L, P, L, P, L, P, P, L, I, F, F, U, U, I, P],
+    "tgan_embed_fwd": [I, P, P, L, P, L, I, I, I, F, F, U, U, P],
+    "tgan_embed_bwd": [I, P, P, L, P, L, I, I, I, F, F, U, U, P],
+    "tgan_pos_emb": [I, P, P, L, I, I, I, I, F, U, U, P],
+    "tgan_ln_fwd": [I, P, L, P, L, P, P, P, P, I, I, I, P],
+    "tgan_ln_bwd": [I, P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, I, F, U, U, P],
+    "tgan_dropout": [I, P, L, P, L, I, I, F, U, U, P],
+    "tgan_relattn_fwd": [I, P, L, P, P, L, P, L, P, P, P, P, L, P, I, I, I, I, I, I, F, F, U, U, I, P],
+    "tgan_relattn_bwd": [I, P, L, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P, P, L, P, L, P, P, I, I, I, I, I, I,
+                         F, F, U, U, I, P],
+    "tgan_ce_fwd": [P, L, P, P, P, I, I, P],
+    "tgan_ce_bwd": [I, P, L, P, P, P, P, L, I, I, I, P],
+    "tgan_gumbel_st_fwd": [P, L, P, L, F, P, L, P, L, P, I, I, U, U, P],
+    "tgan_gumbel_st_bwd": [P, L, P, L, F, P, L, I, I, P],
+    "tgan_colsum": [I, P, L, P, I, I, P],
+    "tgan_convert": [I, P, L, I, P, L, L, I, I, P],
+    "tgan_pack_params": [I, P, P, P, I, L, P],
+    "tgan_unpack_grads": [P, P, P, I, L, P],
+    "tgan_sumsq": [P, L, P, P],
+    "tgan_adam_step": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P],
+}
+EXPORTS = ["tgan_last_error", "tgan_version", "tgan_has_tcgen05", "tgan_launch_count"] + list(_SIGS)
+for _name, _sig in _SIGS.items():
+    _fn = getattr(_lib, _name)
+    _fn.argtypes = _sig
+    _fn.restype = c_int
+
+
+def version() -> int:
+    return _lib.tgan_version()
+
+
+def has_tcgen05() -> bool:
+    return bool(_lib.tgan_has_tcgen05())
+
+
+def launch_count() -> int:
+    return int(_lib.tgan_launch_count())
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TganError(f"unsupported dtype {dt}")
+
+
+def _call(name, *args):
+    rc = getattr(_lib, name)(*args)
+    if rc != 0:
+        raise TganError(f"{name} failed ({rc}): {_lib.tgan_last_error().decode()}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# thin typed wrappers (tensors in, nothing allocated)
+# ---------------------------------------------------------------------------------------------------------
+def gemm(A, B, C, *, transA=False, transB=True, M, N, K, lda=None, ldb=None, ldc=None, bias=None, aux=None,
+         ldaux=0, flags=0, alpha=1.0, drop_p=0.0, seed=0, site=0, impl=IMPL_AUTO, a_off=0, b_off=0, c_off=0,
+         aux_off=0):
+    """C[M,N] = epi(op(A) op(B)).  *_off are element offsets into the tensors (row/column sub-views)."""
+    ea, ec = A.element_size(), C.element_size()
+    lda = lda if lda is not None else A.stride(0)
+    ldb = ldb if ldb is not None else B.stride(0)
+    ldc = ldc if ldc is not None else C.stride(0)
+    if aux is not None and aux.dtype == torch.float32 and A.dtype != torch.float32:
+        flags |= EPI_AUX_F32
+    _call("tgan_gemm", dtype_code(A.dtype), dtype_code(C.dtype), int(transA), int(transB), M, N, K,
+          A.data_ptr() + a_off * ea, lda, B.data_ptr() + b_off * ea, ldb, C.data_ptr() + c_off * ec, ldc,
+          _ptr(bias), None if aux is None else aux.data_ptr() + aux_off * aux.element_size(), ldaux, flags,
+          alpha, drop_p, seed, site, impl, _stream())
+
+
+def embed_fwd(ids, E, out, rows, D, DP, scale, drop_p, seed, site, out_off=0):
+    _call("tgan_embed_fwd", dtype_code(E.dtype), _ptr(ids), E.data_ptr(), DP,
+          out.data_ptr() + out_off * out.element_size(), DP, rows, D, DP, scale, drop_p, seed, site, _stream())
+
+
+def embed_bwd(ids, dout, dE, rows, V, D, DP, scale, drop_p, seed, site):
+    _call("tgan_embed_bwd", dtype_code(dout.dtype), _ptr(ids), dout.data_ptr(), DP, dE.data_ptr(),
+          DP, rows, V, D, scale, drop_p, seed, site, _stream())
+
+
+def pos_emb(inv_freq, pe, klen, D, DP, clamp_len, drop_p, seed, site):
+    _call("tgan_pos_emb", dtype_code(pe.dtype), _ptr(inv_freq), pe.data_ptr(), pe.stride(0), klen, D, DP,
+          clamp_len, drop_p, seed, site, _stream())
+
+
+def ln_fwd(z, y, gamma, beta, mean, rstd, rows, D, DP, y_off=0):
+    _call("tgan_ln_fwd", dtype_code(y.dtype), z.data_ptr(), z.stride(0), y.data_ptr() + y_off * y.element_size(),
+          DP, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), rows, D, DP, _stream())
+
+
+def ln_bwd(dy, z, gamma, mean, rstd, dz, dz_drop, dgamma, dbeta, rows, D, DP, drop_p, seed, site, dy_off=0):
+    _call("tgan_ln_bwd", dtype_code(dz.dtype), dy.data_ptr() + dy_off * dy.element_size(), DP, z.data_ptr(),
+          z.stride(0), _ptr(gamma), _ptr(mean), _ptr(rstd), dz.data_ptr(), dz.stride(0),
+          _ptr(dz_drop), DP, _ptr(dgamma), _ptr(dbeta), rows, D, DP, drop_p, seed, site, _stream())
+
+
+def dropout(src, dst, rows, cols, lds, ldd, p, seed, site, src_off=0, dst_off=0):
+    es = src.element_size()
+    _call("tgan_dropout", dtype_code(src.dtype), src.data_ptr() + src_off * es, lds, dst.data_ptr() + dst_off * es,
+          ldd, rows, cols, p, seed, site, _stream())
+
+
+def relattn_fwd(q, k, v, ldkv, r, u, vb, reset, out, lse, B, N, Q, M, msl, same_length, scale, drop_p, seed, site,
+                impl=IMPL_AUTO, k_off=0, v_off=0):
+    es = q.element_size()
+    _call("tgan_relattn_fwd", dtype_code(q.dtype), q.data_ptr(), q.stride(0), k.data_ptr() + k_off * es,
+          v.data_ptr() + v_off * es, ldkv, r.data_ptr(), r.stride(0), _ptr(u), _ptr(vb), _ptr(reset),
+          out.data_ptr(), out.stride(0), _ptr(lse), B, N, Q, M, msl, int(same_length), scale, drop_p, seed,
+          site, impl, _stream())
+
+
+def relattn_bwd(q, k, v, ldkv, r, u, vb, reset, out, dout, lse, delta, dq, dk, dv, lddkv, dr, du, dvb, B, N, Q, M,
+                msl, same_length, scale, drop_p, seed, site, impl=IMPL_AUTO, k_off=0, v_off=0, dk_off=0, dv_off=0):
+    es = q.element_size()
+    _call("tgan_relattn_bwd", dtype_code(q.dtype), q.data_ptr(), q.stride(0), k.data_ptr() + k_off * es,
+          v.data_ptr() + v_off * es, ldkv, r.data_ptr(), r.stride(0), _ptr(u), _ptr(vb), _ptr(reset),
+          out.data_ptr(), dout.data_ptr(), out.stride(0), _ptr(lse), _ptr(delta), dq.data_ptr(),
+          dk.data_ptr() + dk_off * es, dv.data_ptr() + dv_off * es, lddkv, dr.data_ptr(), dr.stride(0),
+          _ptr(du), _ptr(dvb), B, N, Q, M, msl, int(same_length), scale, drop_p, seed, site, impl,
+          _stream())
+
+
+def ce_fwd(logits, target, nll, lse, rows, V):
+    _call("tgan_ce_fwd", logits.data_ptr(), logits.stride(0), _ptr(target), _ptr(nll), _ptr(lse),
+          rows, V, _stream())
+
+
+def ce_bwd(logits, target, lse, dnll, dlogits, rows, V, VP):
+    _call("tgan_ce_bwd", dtype_code(dlogits.dtype), logits.data_ptr(), logits.stride(0), _ptr(target),
+          _ptr(lse), _ptr(dnll), dlogits.data_ptr(), dlogits.stride(0), rows, V, VP, _stream())
+
+
+def gumbel_st_fwd(logits, U, tau, y, st, ids, rows, V, seed=0, site=0):
+    _call("tgan_gumbel_st_fwd", logits.data_ptr(), logits.stride(0), _ptr(U), 0 if U is None else U.stride(0),
+          tau, y.data_ptr(), y.stride(0), _ptr(st), 0 if st is None else st.stride(0), _ptr(ids), rows, V, seed,
+          site, _stream())
+
+
+def gumbel_st_bwd(y, dst, tau, dlogits, rows, V):
+    _call("tgan_gumbel_st_bwd", y.data_ptr(), y.stride(0), dst.data_ptr(), dst.stride(0), tau, dlogits.data_ptr(),
+          dlogits.stride(0), rows, V, _stream())
+
+
+def colsum(x, out, rows, cols, ld=None, x_off=0, out_off=0):
+    _call("tgan_colsum", dtype_code(x.dtype), x.data_ptr() + x_off * x.element_size(),
+          ld if ld is not None else x.stride(0), out.data_ptr() + out_off * 4, rows, cols, _stream())
+
+
+def convert(src, lds, dst, ldd, rows, cols, cols_pad, src_off=0, dst_off=0):
+    _call("tgan_convert", dtype_code(src.dtype), src.data_ptr() + src_off * src.element_size(), lds,
+          dtype_code(dst.dtype), dst.data_ptr() + dst_off * dst.element_size(), ldd, rows, cols, cols_pad, _stream())
+
+
+def pack_params(packed_mat, packed_vec, desc, n_desc, max_elems):
+    _call("tgan_pack_params", dtype_code(packed_mat.dtype), packed_mat.data_ptr(), packed_vec.data_ptr(),
+          desc.data_ptr(), n_desc, max_elems, _stream())
+
+
+def unpack_grads(padded_mat, padded_vec, desc, n_desc, max_elems):
+    _call("tgan_unpack_grads", padded_mat.data_ptr(), padded_vec.data_ptr(), desc.data_ptr(), n_desc, max_elems,
+          _stream())
+
+
+def sumsq(x, n, out):
+    _call("tgan_sumsq", x.data_ptr(), n, out.data_ptr(), _stream())
+
+
+def adam_step(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq, clip, grad_scale):
+    _call("tgan_adam_step", param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps,
+          weight_decay, step, _ptr(gnorm_sq), clip, grad_scale, _stream())
