@@ -50,3 +50,26 @@ def check_grads(z, got, rtol, atol_frac=1e-3):
         worst = max(worst, err)
         assert err <= rtol, (name, err)
     return worst
+
+
+def grad_errors(z, got):
+    """{name: (frobenius relative error, max elementwise error relative to |want| + rms)} on the golden (sampled)
+    gradient entries.  The Frobenius figure is the robust one for low precision: a single ReLU sign flip of a
+    near-zero pre-activation changes individual dW entries by one whole term."""
+    grads, norms = golden_grads(z)
+    out = {}
+    for name, spec in grads.items():
+        g = got[name].detach().double().cpu()
+        n = norms[name]
+        if spec[0] == "full":
+            want = torch.from_numpy(spec[1]).double()
+            have = g.reshape(want.shape)
+        else:
+            want = torch.from_numpy(spec[2]).double()
+            have = g.reshape(-1)[torch.from_numpy(spec[1])]
+        scale = max(n / max(g.numel(), 1) ** 0.5, 1e-30)
+        frob = ((have - want).norm() / want.norm().clamp_min(1e-30)).item()
+        elem = ((have - want).abs() / (want.abs() + scale)).max().item()
+        nerr = abs(g.norm().item() - n) / max(n, 1e-30)
+        out[name] = (max(frob, nerr), elem)
+    return out

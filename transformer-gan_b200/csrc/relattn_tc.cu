@@ -1,16 +1,839 @@
-// tcgen05 relative-position attention (placeholder until the kernels land: reports "not eligible").
-#include "common.cuh"
+// tcgen05 relative-position attention for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// One CTA per (batch b, head n, 128-row query tile).  Five warps:
+//   warps 0..3  "row" warps: thread = query row = TMEM lane.  Online softmax, rel-shift, mask, dropout.
+//   warp  4     control: one thread issues the TMA loads (K / V tiles, R chunks) and every tcgen05.mma.
+// Per 64-key tile t the tensor core produces, into TMEM,
+//     S_ac = (q + u) K_t^T            [128 x 64]
+//     G_c  = (q + v) R_c^T            [128 x 64]   for ONE new 64-wide chunk c of relative positions
+//     O_t  = P_t V_t                  [128 x 64]
+// The relative shift  BD[i, j] = G[i, j + Q - 1 - i]  is a row-dependent column offset.  TMEM rows are thread
+// private (thread = lane), so the shift is done through a thread-private ring of the last three G chunks kept in
+// shared memory as ring[column][row] (bank = row: conflict-free for any per-row offset).  Every G element is
+// computed exactly once: tile t needs chunks t, t+1, t+2 and only chunk t+2 is new.  No [Q, K] score / mask /
+// shifted copy ever exists (reference: mem_transformer.py:133-147, 201-244, 495-547).
+// The running output stays in registers: acc = (acc + O_{t-1}) * exp2(m_{t-1} - m_t).
+#include <cuda_fp16.h>
 
-int tgan_relattn_fwd_tc(const void*, int64_t, const void*, const void*, int64_t, const void*, int64_t, const float*,
-                        const float*, const uint8_t*, void*, int64_t, float*, int, int, int, int, int, int, float,
-                        float, uint64_t, uint64_t, cudaStream_t) {
-    tgan_set_error("tgan_relattn_fwd: tcgen05 kernel not available for this shape");
-    return -1;
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int HS = TGAN_HS;  // 64
+constexpr int BQ = 128;      // query rows per CTA
+constexpr int BJ = 64;       // keys per tile
+constexpr int KV_STAGES = 3;
+constexpr int RING_COLS = 192;
+
+// shared-memory carve-up (bytes, relative to a 1024-aligned base)
+constexpr int OFF_QU = 0;                               // [128][64] bf16, K-major SW128
+constexpr int OFF_QV = OFF_QU + BQ * HS * 2;            // 16 KB
+constexpr int OFF_KV = OFF_QV + BQ * HS * 2;            // KV_STAGES x (K tile 8 KB + V tile 8 KB)
+constexpr int OFF_R = OFF_KV + KV_STAGES * 2 * BJ * HS * 2;
+constexpr int OFF_P = OFF_R + 2 * BJ * HS * 2;          // [128][64] bf16
+constexpr int OFF_RING = OFF_P + BQ * BJ * 2;           // [192][128] fp16 (thread-private G ring)
+constexpr int OFF_BAR = OFF_RING + RING_COLS * BQ * 2;
+constexpr int NUM_BARS = 2 * KV_STAGES + 4 + 4 + 4 + 2;
+constexpr int FWD_SMEM = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+
+// TMEM columns
+constexpr int TM_S = 0, TM_G = 128, TM_O = 256, TM_COLS = 512;
+
+struct FwdParams {
+    const bf16* q; int64_t ldq;
+    bf16* out; int64_t ldo;
+    float* lse;
+    const float* u; const float* vb;
+    const uint8_t* reset;
+    int B, N, Q, M, K, msl, same_length;
+    float scale_log2;  // scale * log2(e)
+    float drop_scale; uint32_t drop_thresh; uint32_t drop_key;
+};
+
+// byte offset of the 16-byte chunk `c` (8 bf16) of row `r` inside a K-major SWIZZLE_128B tile with 128-byte rows
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
-int tgan_relattn_bwd_tc(const void*, int64_t, const void*, const void*, int64_t, const void*, int64_t, const float*,
-                        const float*, const uint8_t*, const void*, const void*, int64_t, const float*, float*, void*,
-                        void*, void*, int64_t, float*, int64_t, float*, float*, int, int, int, int, int, int, float,
-                        float, uint64_t, uint64_t, cudaStream_t) {
-    tgan_set_error("tgan_relattn_bwd: tcgen05 kernel not available for this shape");
-    return -1;
+
+__global__ void __launch_bounds__(160, 1)
+relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ CUtensorMap tmR, FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQu = base + OFF_QU, sQv = base + OFF_QV, sKV = base + OFF_KV, sR = base + OFF_R, sP = base + OFF_P;
+    __half* ring = reinterpret_cast<__half*>(gbase + OFF_RING);
+    const uint32_t bar0 = base + OFF_BAR;
+    // barrier map
+    const uint32_t kv_full = bar0, kv_empty = kv_full + 8 * KV_STAGES, r_full = kv_empty + 8 * KV_STAGES,
+                   r_empty = r_full + 16, s_full = r_empty + 16, s_empty = s_full + 16, g_full = s_empty + 16,
+                   g_empty = g_full + 16, p_full = g_empty + 16, o_full = p_full + 8;
+    const uint32_t sTmemPtr = o_full + 8;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bn = blockIdx.y, b = bn / p.N, n = bn % p.N;
+    const int i0 = blockIdx.x * BQ;
+    const int rows_here = min(BQ, p.Q - i0);
+    const bool reset_b = p.reset && p.reset[b];
+
+    // key range needed by this query tile (CTA-uniform)
+    int jlo = 0, jhi = min(p.K - 1, i0 + rows_here - 1 + p.M);
+    if (p.same_length) jlo = max(0, i0 - p.msl + 1);
+    if (reset_b) jlo = max(jlo, p.M);
+    const int t_lo = jlo / BJ, t_hi = jhi / BJ;
+    const int nt = t_hi - t_lo + 1;  // >= 1
+    const int nc = nt + 2;           // G chunks
+    const int P0 = p.Q - 1 - i0 - (BQ - 1) + BJ * t_lo;  // relative position of column 0 of chunk 0
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(r_full + 8 * s, 1); mbar_init(r_empty + 8 * s, 1);
+            mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, 4);
+            mbar_init(g_full + 8 * s, 1); mbar_init(g_empty + 8 * s, 4);
+        }
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(sTmemPtr, TM_COLS);
+
+    // ---- stage (q + u), (q + vb) as swizzled K-major A operands (row warps) ----
+    if (warp < 4) {
+        const int ii = threadIdx.x;  // 0..127
+        const bool live = ii < rows_here;
+        const bf16* qrow = p.q + ((int64_t)(i0 + ii) * p.B + b) * p.ldq + n * HS;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8], a[8], bb[8];
+            if (live) load8(qrow + 8 * c, x);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float qv = live ? x[t] : 0.f;
+                a[t] = live ? qv + p.u[n * HS + 8 * c + t] : 0.f;
+                bb[t] = live ? qv + p.vb[n * HS + 8 * c + t] : 0.f;
+            }
+            store8(reinterpret_cast<bf16*>(gbase + OFF_QU + sw128_off(ii, c)), a);
+            store8(reinterpret_cast<bf16*>(gbase + OFF_QV + sw128_off(ii, c)), bb);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 4) {
+        // =========================== control thread: TMA + MMA issue ===========================
+        if (lane == 0) {
+            constexpr uint32_t idesc_kk = umma_idesc_bf16(BQ, BJ, 0, 0);  // A, B K-major
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HS, 0, 1);  // B (= V tile [keys][d]) MN-major
+            auto issue_kv = [&](int tt) {
+                if (tt >= nt) return;
+                const int st = tt % KV_STAGES;
+                mbar_wait(kv_empty + 8 * st, ((tt / KV_STAGES) & 1) ^ 1);
+                mbar_expect_tx(kv_full + 8 * st, 2 * BJ * HS * 2);
+                const uint32_t dst = sKV + st * (2 * BJ * HS * 2);
+                tma_load_3d(dst, &tmK, kv_full + 8 * st, n * HS, b, (t_lo + tt) * BJ);
+                tma_load_3d(dst + BJ * HS * 2, &tmV, kv_full + 8 * st, n * HS, b, (t_lo + tt) * BJ);
+            };
+            auto issue_r = [&](int cc) {
+                if (cc >= nc) return;
+                const int st = cc & 1;
+                mbar_wait(r_empty + 8 * st, ((cc >> 1) & 1) ^ 1);
+                mbar_expect_tx(r_full + 8 * st, BJ * HS * 2);
+                tma_load_2d(sR + st * (BJ * HS * 2), &tmR, r_full + 8 * st, n * HS, P0 + BJ * cc);
+            };
+            auto mma_s = [&](int tt) {
+                if (tt >= nt) return;
+                const int st = tt % KV_STAGES;
+                mbar_wait(kv_full + 8 * st, (tt / KV_STAGES) & 1);
+                mbar_wait(s_empty + 8 * (tt & 1), ((tt >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t kaddr = sKV + st * (2 * BJ * HS * 2);
+#pragma unroll
+                for (int k = 0; k < HS / 16; ++k)
+                    umma_bf16(tmem_base + TM_S + BJ * (tt & 1), umma_smem_desc(sQu + 32 * k, 16, 1024),
+                              umma_smem_desc(kaddr + 32 * k, 16, 1024), idesc_kk, k != 0);
+                umma_commit(s_full + 8 * (tt & 1));
+            };
+            auto mma_g = [&](int cc) {
+                if (cc >= nc) return;
+                const int st = cc & 1;
+                mbar_wait(r_full + 8 * st, (cc >> 1) & 1);
+                mbar_wait(g_empty + 8 * st, ((cc >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t raddr = sR + st * (BJ * HS * 2);
+#pragma unroll
+                for (int k = 0; k < HS / 16; ++k)
+                    umma_bf16(tmem_base + TM_G + BJ * st, umma_smem_desc(sQv + 32 * k, 16, 1024),
+                              umma_smem_desc(raddr + 32 * k, 16, 1024), idesc_kk, k != 0);
+                umma_commit(g_full + 8 * st);
+                umma_commit(r_empty + 8 * st);
+            };
+            auto mma_pv = [&](int tt) {
+                const int st = tt % KV_STAGES;
+                mbar_wait(p_full, tt & 1);
+                tcgen05_fence_after();
+                const uint32_t vaddr = sKV + st * (2 * BJ * HS * 2) + BJ * HS * 2;
+#pragma unroll
+                for (int k = 0; k < BJ / 16; ++k)
+                    umma_bf16(tmem_base + TM_O, umma_smem_desc(sP + 32 * k, 16, 1024),
+                              umma_smem_desc(vaddr + 2048 * k, 8192, 1024), idesc_pv, k != 0);
+                umma_commit(o_full);
+                umma_commit(kv_empty + 8 * st);
+            };
+            issue_kv(0); issue_kv(1);
+            issue_r(0); issue_r(1);
+            mma_s(0);
+            mma_g(0); issue_r(2);
+            mma_g(1); issue_r(3);
+            mma_g(2);
+            for (int tt = 0; tt < nt; ++tt) {
+                issue_kv(tt + 2);
+                issue_r(tt + 4);
+                mma_s(tt + 1);
+                mma_g(tt + 3);
+                mma_pv(tt);
+            }
+        }
+    } else {
+        // =========================== row warps: softmax / rel-shift / dropout ===========================
+        const int ii = threadIdx.x;
+        const int i = i0 + ii;
+        const bool live = ii < rows_here;
+        const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
+        float m = -INFINITY, l = 0.f, corr = 1.f;
+        float acc[HS];
+#pragma unroll
+        for (int d = 0; d < HS; ++d) acc[d] = 0.f;
+        int consumed = 0;
+        const uint64_t drop_base = ((uint64_t)bn * p.Q + i) * p.K;
+        for (int tt = 0; tt < nt; ++tt) {
+            // 1. pull new G chunks (tile tt needs chunks tt .. tt+2) into the thread-private ring
+            while (consumed <= tt + 2 && consumed < nc) {
+                const int st = consumed & 1;
+                mbar_wait(g_full + 8 * st, (consumed >> 1) & 1);
+                tcgen05_fence_after();
+                uint32_t g[64];
+                tmem_ld32(tmem_base + TM_G + BJ * st + lane_off, g);
+                tmem_ld32(tmem_base + TM_G + BJ * st + 32 + lane_off, g + 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(g_empty + 8 * st);
+                __half* dst = ring + (consumed % 3) * (BJ * BQ) + ii;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
+                ++consumed;
+            }
+            // 2. content scores
+            mbar_wait(s_full + 8 * (tt & 1), (tt >> 1) & 1);
+            tcgen05_fence_after();
+            uint32_t sr[64];
+            tmem_ld32(tmem_base + TM_S + BJ * (tt & 1) + lane_off, sr);
+            tmem_ld32(tmem_base + TM_S + BJ * (tt & 1) + 32 + lane_off, sr + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + 8 * (tt & 1));
+            // 3. add the shifted position scores, mask, running max
+            const int j0 = (t_lo + tt) * BJ;
+            int lim_hi = live ? (i + p.M - j0) : -1;              // jj <= lim_hi  (causal + memory)
+            int lim_lo = 0;                                        // jj >= lim_lo
+            if (p.same_length) lim_lo = max(lim_lo, i - p.msl + 1 - j0);
+            if (reset_b) lim_lo = max(lim_lo, p.M - j0);
+            lim_hi = min(lim_hi, p.K - 1 - j0);
+            int start = (BQ - 1 - ii + BJ * tt) % RING_COLS;      // ring column of jj = 0
+            float s[64];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < 64; ++jj) {
+                int col = start + jj;
+                col -= (col >= RING_COLS) ? RING_COLS : 0;
+                float v = (__uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii])) * p.scale_log2;
+                v = (jj >= lim_lo && jj <= lim_hi) ? v : -INFINITY;
+                s[jj] = v;
+                mx = fmaxf(mx, v);
+            }
+            const float m_new = fmaxf(m, mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            corr = (m == -INFINITY) ? 0.f : exp2f(m - m_use);
+            m = m_new;
+            // 4. fold the previous tile's P V into the running output (it finished long ago)
+            if (tt > 0) {
+                mbar_wait(o_full, (tt - 1) & 1);
+                tcgen05_fence_after();
+                uint32_t o[64];
+                tmem_ld32(tmem_base + TM_O + lane_off, o);
+                tmem_ld32(tmem_base + TM_O + 32 + lane_off, o + 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+#pragma unroll
+                for (int d = 0; d < HS; ++d) acc[d] = (acc[d] + __uint_as_float(o[d])) * corr;
+            }
+            // 5. probabilities -> (dropout) -> bf16 A operand for P V
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float pv[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int jj = 8 * c + t;
+                    float e = exp2f(s[jj] - m_use);
+                    lsum += e;
+                    if (p.drop_thresh)
+                        e = dropout_keep_k(p.drop_key, drop_base + (uint64_t)(j0 + jj), p.drop_thresh) ? e * p.drop_scale : 0.f;
+                    pv[t] = e;
+                }
+                store8(reinterpret_cast<bf16*>(gbase + OFF_P + sw128_off(ii, c)), pv);
+            }
+            l = l * corr + lsum;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // last tile's P V
+        mbar_wait(o_full, (nt - 1) & 1);
+        tcgen05_fence_after();
+        {
+            uint32_t o[64];
+            tmem_ld32(tmem_base + TM_O + lane_off, o);
+            tmem_ld32(tmem_base + TM_O + 32 + lane_off, o + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            if (live) {
+                bf16* orow = p.out + ((int64_t)i * p.B + b) * p.ldo + n * HS;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float v8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v8[t] = (acc[8 * c + t] + __uint_as_float(o[8 * c + t])) * inv;
+                    store8(orow + 8 * c, v8);
+                }
+                p.lse[(int64_t)bn * p.Q + i] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TM_COLS);
+    }
+}
+
+// =================================================================================================================
+// Backward.  One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.
+// Per 64-key tile t (TMEM columns in brackets):
+//     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO V_t^T
+//   row threads:  P = exp2(S2 - lse2),  dS = P (drop(dP) - delta) scale,  P~ = drop(P)  -> bf16 tiles in smem,
+//                 dS also scattered into a thread-private bf16 ring at the INVERSE shift (column p = j + Q-1-i)
+//     dV_t [384] = P~^T dO     dK_t [320] = dS^T (q+u)     dqK [192] += dS K_t            (after the tiles are written)
+//     dqR [256] += dG_c R_c    dR_c [448] = dG_c^T (q+v)   where dG_c = chunk c of the dS ring (complete after tile c)
+// dR chunks are reduced over the batch with red.global.add.v4.f32; du / dvb are the column sums of dqK / dqR.
+// =================================================================================================================
+constexpr int B_OFF_QU = 0;
+constexpr int B_OFF_QV = B_OFF_QU + 16384;
+constexpr int B_OFF_DO = B_OFF_QV + 16384;
+constexpr int B_OFF_K = B_OFF_DO + 16384;    // 2 stages x 8 KB
+constexpr int B_OFF_V = B_OFF_K + 2 * 8192;  // 1 stage
+constexpr int B_OFF_R = B_OFF_V + 8192;      // 3 stages x 8 KB
+constexpr int B_OFF_PT = B_OFF_R + 3 * 8192; // P~ tile, later the dG tile
+constexpr int B_OFF_DS = B_OFF_PT + 16384;
+constexpr int B_OFF_GRING = B_OFF_DS + 16384;                 // fp16 [192][128]
+constexpr int B_OFF_DRING = B_OFF_GRING + RING_COLS * BQ * 2; // bf16 [192][128]
+constexpr int B_OFF_BAR = B_OFF_DRING + RING_COLS * BQ * 2;
+constexpr int B_NUM_BARS = 4 + 2 + 6 + 2 + 2 + 2 + 4;
+constexpr int BWD_SMEM = B_OFF_BAR + B_NUM_BARS * 8 + 16 + 1024;
+constexpr int TB_S = 0, TB_G = 64, TB_DP = 128, TB_DQK = 192, TB_DQR = 256, TB_DK = 320, TB_DV = 384, TB_DR = 448;
+
+struct BwdParams {
+    const bf16* q; int64_t ldq;
+    const bf16* out; const bf16* dout; int64_t ldo;
+    const float* lse;
+    const float* u; const float* vb;
+    const uint8_t* reset;
+    bf16* dq; bf16* dk; bf16* dv; int64_t lddkv;
+    float* dr; int64_t lddr;
+    float* du; float* dvb;
+    int B, N, Q, M, K, msl, same_length;
+    float scale, scale_log2;
+    float drop_scale; uint32_t drop_thresh; uint32_t drop_key;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(160, 1)
+relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ CUtensorMap tmR, BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sQu = base + B_OFF_QU, sQv = base + B_OFF_QV, sDO = base + B_OFF_DO, sK = base + B_OFF_K,
+                   sV = base + B_OFF_V, sR = base + B_OFF_R, sPT = base + B_OFF_PT, sDS = base + B_OFF_DS;
+    __half* gring = reinterpret_cast<__half*>(gbase + B_OFF_GRING);
+    bf16* dring = reinterpret_cast<bf16*>(gbase + B_OFF_DRING);
+    const uint32_t bar0 = base + B_OFF_BAR;
+    const uint32_t k_full = bar0, k_empty = k_full + 16, v_full = k_empty + 16, v_empty = v_full + 8,
+                   r_full = v_empty + 8, r_empty = r_full + 24, s_full = r_empty + 24, s_empty = s_full + 8,
+                   dp_full = s_empty + 8, dp_empty = dp_full + 8, g_full = dp_empty + 8, g_empty = g_full + 8,
+                   p_full = g_empty + 8, kdone = p_full + 8, dg_full = kdone + 8, rdone = dg_full + 8;
+    const uint32_t sTmemPtr = rdone + 8;
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bn = blockIdx.x, b = bn / p.N, n = bn % p.N;
+    const int rows_here = p.Q;  // Q <= 128, single query tile (i0 = 0)
+    const bool reset_b = p.reset && p.reset[b];
+    int jlo = 0, jhi = min(p.K - 1, rows_here - 1 + p.M);
+    if (p.same_length) jlo = max(0, -p.msl + 1);
+    if (reset_b) jlo = max(jlo, p.M);
+    const int t_lo = jlo / BJ, t_hi = jhi / BJ;
+    const int nt = t_hi - t_lo + 1;
+    const int nc = nt + 2;
+    const int P0 = p.Q - 1 - (BQ - 1) + BJ * t_lo;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
+        mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        for (int s = 0; s < 3; ++s) { mbar_init(r_full + 8 * s, 1); mbar_init(r_empty + 8 * s, 1); }
+        mbar_init(s_full, 1); mbar_init(s_empty, 4);
+        mbar_init(dp_full, 1); mbar_init(dp_empty, 4);
+        mbar_init(g_full, 1); mbar_init(g_empty, 4);
+        mbar_init(p_full, 4); mbar_init(kdone, 1); mbar_init(dg_full, 4); mbar_init(rdone, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(sTmemPtr, TM_COLS);
+
+    float delta = 0.f, lse2 = 0.f;
+    if (warp < 4) {
+        const int ii = threadIdx.x;
+        const bool live = ii < rows_here;
+        const int64_t row = (int64_t)ii * p.B + b;
+        const bf16* qrow = p.q + row * p.ldq + n * HS;
+        const bf16* orow = p.out + row * p.ldo + n * HS;
+        const bf16* grow = p.dout + row * p.ldo + n * HS;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float x[8], o[8], g[8], a[8], bb[8];
+            if (live) { load8(qrow + 8 * c, x); load8(orow + 8 * c, o); load8(grow + 8 * c, g); }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                a[t] = live ? x[t] + p.u[n * HS + 8 * c + t] : 0.f;
+                bb[t] = live ? x[t] + p.vb[n * HS + 8 * c + t] : 0.f;
+                g[t] = live ? g[t] : 0.f;
+                delta += live ? g[t] * o[t] : 0.f;
+            }
+            store8(reinterpret_cast<bf16*>(gbase + B_OFF_QU + sw128_off(ii, c)), a);
+            store8(reinterpret_cast<bf16*>(gbase + B_OFF_QV + sw128_off(ii, c)), bb);
+            store8(reinterpret_cast<bf16*>(gbase + B_OFF_DO + sw128_off(ii, c)), g);
+        }
+        lse2 = live ? p.lse[(int64_t)bn * p.Q + ii] * 1.4426950408889634f : 0.f;
+        for (int c = 0; c < RING_COLS; ++c) dring[c * BQ + ii] = __float2bfloat16_rn(0.f);
+        // keys this (b, n) never attends to get zero gradients
+        for (int j = ii; j < p.K; j += BQ) {
+            if (j >= t_lo * BJ && j < (t_hi + 1) * BJ) continue;
+            uint4 z = make_uint4(0, 0, 0, 0);
+            uint4* dkr = reinterpret_cast<uint4*>(p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS);
+            uint4* dvr = reinterpret_cast<uint4*>(p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { dkr[c] = z; dvr[c] = z; }
+        }
+        fence_proxy_async_smem();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t id_kk = umma_idesc_bf16(128, 64, 0, 0);   // S, G, dP: A, B K-major
+            constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dqK, dqR: A K-major, B MN-major
+            constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);    // dV, dK, dR: A, B MN-major (M = 64)
+            auto issue_k = [&](int tt) {
+                if (tt >= nt) return;
+                const int st = tt & 1;
+                mbar_wait(k_empty + 8 * st, ((tt >> 1) & 1) ^ 1);
+                mbar_expect_tx(k_full + 8 * st, 8192);
+                tma_load_3d(sK + st * 8192, &tmK, k_full + 8 * st, n * HS, b, (t_lo + tt) * BJ);
+            };
+            auto issue_v = [&](int tt) {
+                if (tt >= nt) return;
+                mbar_wait(v_empty, (tt & 1) ^ 1);
+                mbar_expect_tx(v_full, 8192);
+                tma_load_3d(sV, &tmV, v_full, n * HS, b, (t_lo + tt) * BJ);
+            };
+            auto issue_r = [&](int cc) {
+                if (cc >= nc) return;
+                const int st = cc % 3;
+                mbar_wait(r_empty + 8 * st, ((cc / 3) & 1) ^ 1);
+                mbar_expect_tx(r_full + 8 * st, 8192);
+                tma_load_2d(sR + st * 8192, &tmR, r_full + 8 * st, n * HS, P0 + BJ * cc);
+            };
+            auto mma_s = [&](int tt) {
+                if (tt >= nt) return;
+                mbar_wait(k_full + 8 * (tt & 1), (tt >> 1) & 1);
+                mbar_wait(s_empty, (tt & 1) ^ 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + TB_S, umma_smem_desc(sQu + 32 * k, 16, 1024),
+                              umma_smem_desc(sK + (tt & 1) * 8192 + 32 * k, 16, 1024), id_kk, k != 0);
+                umma_commit(s_full);
+            };
+            auto mma_dp = [&](int tt) {
+                if (tt >= nt) return;
+                mbar_wait(v_full, tt & 1);
+                mbar_wait(dp_empty, (tt & 1) ^ 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + TB_DP, umma_smem_desc(sDO + 32 * k, 16, 1024),
+                              umma_smem_desc(sV + 32 * k, 16, 1024), id_kk, k != 0);
+                umma_commit(dp_full);
+                umma_commit(v_empty);
+            };
+            auto mma_g = [&](int cc) {
+                if (cc >= nc) return;
+                mbar_wait(r_full + 8 * (cc % 3), (cc / 3) & 1);
+                mbar_wait(g_empty, (cc & 1) ^ 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + TB_G, umma_smem_desc(sQv + 32 * k, 16, 1024),
+                              umma_smem_desc(sR + (cc % 3) * 8192 + 32 * k, 16, 1024), id_kk, k != 0);
+                umma_commit(g_full);
+            };
+            auto mma_key = [&](int tt) {
+                mbar_wait(p_full, tt & 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)  // dV = P~^T dO   (contraction over the 128 query rows)
+                    umma_bf16(tmem_base + TB_DV, umma_smem_desc(sPT + 2048 * k, 8192, 1024),
+                              umma_smem_desc(sDO + 2048 * k, 8192, 1024), id_nn, k != 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)  // dK = dS^T (q + u)
+                    umma_bf16(tmem_base + TB_DK, umma_smem_desc(sDS + 2048 * k, 8192, 1024),
+                              umma_smem_desc(sQu + 2048 * k, 8192, 1024), id_nn, k != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // dqK += dS K_t   (contraction over the 64 keys)
+                    umma_bf16(tmem_base + TB_DQK, umma_smem_desc(sDS + 32 * k, 16, 1024),
+                              umma_smem_desc(sK + (tt & 1) * 8192 + 2048 * k, 8192, 1024), id_kn, (tt | k) != 0);
+                umma_commit(kdone);
+                umma_commit(k_empty + 8 * (tt & 1));
+            };
+            auto mma_rel = [&](int cc) {
+                mbar_wait(dg_full, cc & 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // dqR += dG_c R_c
+                    umma_bf16(tmem_base + TB_DQR, umma_smem_desc(sPT + 32 * k, 16, 1024),
+                              umma_smem_desc(sR + (cc % 3) * 8192 + 2048 * k, 8192, 1024), id_kn, (cc | k) != 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)  // dR_c = dG_c^T (q + v)
+                    umma_bf16(tmem_base + TB_DR, umma_smem_desc(sPT + 2048 * k, 8192, 1024),
+                              umma_smem_desc(sQv + 2048 * k, 8192, 1024), id_nn, k != 0);
+                umma_commit(rdone);
+                umma_commit(r_empty + 8 * (cc % 3));
+            };
+            issue_k(0); issue_v(0); issue_r(0); issue_r(1); issue_r(2); issue_k(1);
+            mma_s(0); mma_dp(0); mma_g(0); mma_g(1); mma_g(2);
+            issue_v(1);
+            for (int tt = 0; tt < nt; ++tt) {
+                mma_key(tt);
+                mma_s(tt + 1);
+                mma_dp(tt + 1);
+                issue_v(tt + 2);
+                mma_rel(tt);
+                issue_r(tt + 3);
+                mma_g(tt + 3);
+                issue_k(tt + 2);
+            }
+            for (int cc = nt; cc < nc; ++cc) mma_rel(cc);
+        }
+    } else {
+        const int ii = threadIdx.x;
+        const bool live = ii < rows_here;
+        const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
+        const uint64_t drop_base = ((uint64_t)bn * p.Q + ii) * p.K;
+        int consumed = 0;
+        // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * warp + lane
+        auto flush_dr = [&](int cc) {
+            mbar_wait(rdone, cc & 1);
+            tcgen05_fence_after();
+            uint32_t v[64];
+            tmem_ld32(tmem_base + TB_DR + lane_off, v);
+            tmem_ld32(tmem_base + TB_DR + 32 + lane_off, v + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            const int pr = P0 + BJ * cc + 16 * warp + lane;
+            if (lane < 16 && pr >= 0 && pr < p.K) {
+                float* dst = p.dr + (int64_t)pr * p.lddr + n * HS;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    red_add_v4(dst + 4 * c, __uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                               __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+            }
+        };
+        // chunk cc of the dS ring -> bf16 K-major tile (the dG A operand), then clear the ring third for reuse
+        auto extract_dg = [&](int cc) {
+            bf16* src = dring + (cc % 3) * (BJ * BQ) + ii;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 pk;
+                __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(&pk);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    h[t] = src[(8 * c + t) * BQ];
+                    src[(8 * c + t) * BQ] = __float2bfloat16_rn(0.f);
+                }
+                *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, c)) = pk;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dg_full);
+        };
+        for (int tt = 0; tt < nt; ++tt) {
+            while (consumed <= tt + 2 && consumed < nc) {
+                mbar_wait(g_full, consumed & 1);
+                tcgen05_fence_after();
+                uint32_t g[64];
+                tmem_ld32(tmem_base + TB_G + lane_off, g);
+                tmem_ld32(tmem_base + TB_G + 32 + lane_off, g + 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(g_empty);
+                __half* dst = gring + (consumed % 3) * (BJ * BQ) + ii;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
+                ++consumed;
+            }
+            const int j0 = (t_lo + tt) * BJ;
+            int lim_hi = live ? (ii + p.M - j0) : -1;
+            int lim_lo = 0;
+            if (p.same_length) lim_lo = max(lim_lo, ii - p.msl + 1 - j0);
+            if (reset_b) lim_lo = max(lim_lo, p.M - j0);
+            lim_hi = min(lim_hi, p.K - 1 - j0);
+            const int start = (BQ - 1 - ii + BJ * tt) % RING_COLS;
+            float pr[64];
+            {
+                mbar_wait(s_full, tt & 1);
+                tcgen05_fence_after();
+                uint32_t sr[64];
+                tmem_ld32(tmem_base + TB_S + lane_off, sr);
+                tmem_ld32(tmem_base + TB_S + 32 + lane_off, sr + 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);
+#pragma unroll
+                for (int jj = 0; jj < 64; ++jj) {
+                    int col = start + jj;
+                    col -= (col >= RING_COLS) ? RING_COLS : 0;
+                    float v = (__uint_as_float(sr[jj]) + __half2float(gring[col * BQ + ii])) * p.scale_log2;
+                    pr[jj] = (jj >= lim_lo && jj <= lim_hi) ? exp2f(v - lse2) : 0.f;
+                }
+            }
+            mbar_wait(dp_full, tt & 1);
+            tcgen05_fence_after();
+            uint32_t dpr[64];
+            tmem_ld32(tmem_base + TB_DP + lane_off, dpr);
+            tmem_ld32(tmem_base + TB_DP + 32 + lane_off, dpr + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dp_empty);
+            // the P~ / dG buffer and the dR accumulator are free once the previous chunk's MMAs have been drained
+            if (tt > 0) flush_dr(tt - 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float pt8[8], ds8[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int jj = 8 * c + t;
+                    float pj = pr[jj], dp = __uint_as_float(dpr[jj]);
+                    bool keep = true;
+                    if (p.drop_thresh) keep = dropout_keep_k(p.drop_key, drop_base + (uint64_t)(j0 + jj), p.drop_thresh);
+                    dp = keep ? dp * p.drop_scale : 0.f;
+                    pt8[t] = keep ? pj * p.drop_scale : 0.f;
+                    ds8[t] = pj * (dp - delta) * p.scale;
+                    int col = start + jj;
+                    col -= (col >= RING_COLS) ? RING_COLS : 0;
+                    dring[col * BQ + ii] = __float2bfloat16_rn(ds8[t]);
+                }
+                store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + sw128_off(ii, c)), pt8);
+                store8(reinterpret_cast<bf16*>(gbase + B_OFF_DS + sw128_off(ii, c)), ds8);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            // key-side results of this tile (M = 64 layout: row r = 16 * warp + lane, lanes 0..15)
+            mbar_wait(kdone, tt & 1);
+            tcgen05_fence_after();
+            {
+                uint32_t a[64];
+                const int j = j0 + 16 * warp + lane;
+                const bool wr = lane < 16 && j < p.K;
+                tmem_ld32(tmem_base + TB_DK + lane_off, a);
+                tmem_ld32(tmem_base + TB_DK + 32 + lane_off, a + 32);
+                tmem_ld_wait();
+                if (wr) {
+                    bf16* dst = p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
+                        store8(dst + 8 * c, f);
+                    }
+                }
+                tmem_ld32(tmem_base + TB_DV + lane_off, a);
+                tmem_ld32(tmem_base + TB_DV + 32 + lane_off, a + 32);
+                tmem_ld_wait();
+                if (wr) {
+                    bf16* dst = p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
+                        store8(dst + 8 * c, f);
+                    }
+                }
+                tcgen05_fence_before();
+            }
+            extract_dg(tt);  // chunk tt is complete: tiles > tt only touch chunks > tt
+        }
+        for (int cc = nt; cc < nc; ++cc) {
+            flush_dr(cc - 1);
+            extract_dg(cc);
+        }
+        flush_dr(nc - 1);
+        // dq = dqK + dqR (ds already carries the 1/sqrt(d) scale); du / dvb = column sums over the query rows
+        {
+            uint32_t a[64], c2[64];
+            tmem_ld32(tmem_base + TB_DQK + lane_off, a);
+            tmem_ld32(tmem_base + TB_DQK + 32 + lane_off, a + 32);
+            tmem_ld32(tmem_base + TB_DQR + lane_off, c2);
+            tmem_ld32(tmem_base + TB_DQR + 32 + lane_off, c2 + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            if (live) {
+                bf16* dst = p.dq + ((int64_t)ii * p.B + b) * p.ldq + n * HS;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float f[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) + __uint_as_float(c2[8 * c + t]);
+                    store8(dst + 8 * c, f);
+                }
+            }
+            float su0 = 0.f, su1 = 0.f, sv0 = 0.f, sv1 = 0.f;
+#pragma unroll
+            for (int d = 0; d < 64; ++d) {
+                float tk = warp_sum(live ? __uint_as_float(a[d]) : 0.f);
+                float tr = warp_sum(live ? __uint_as_float(c2[d]) : 0.f);
+                if (d == lane) { su0 = tk; sv0 = tr; }
+                if (d == lane + 32) { su1 = tk; sv1 = tr; }
+            }
+            atomicAdd(&p.du[n * HS + lane], su0);
+            atomicAdd(&p.du[n * HS + lane + 32], su1);
+            atomicAdd(&p.dvb[n * HS + lane], sv0);
+            atomicAdd(&p.dvb[n * HS + lane + 32], sv1);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TM_COLS);
+    }
+}
+}  // namespace
+
+int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
+                        int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out, int64_t ldo,
+                        float* lse, int B, int N, int Q, int M, int msl, int same_length, float scale, float drop_p,
+                        uint64_t seed, uint64_t site, cudaStream_t st) {
+    const int K = M + Q;
+    const bool ok = Q >= 32 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)out) & 15) == 0;
+    if (!ok) {
+        tgan_set_error("tgan_relattn_fwd: shape not eligible for the tcgen05 kernel (needs Q >= 32, 16-byte alignment)");
+        return -1;
+    }
+    CUtensorMap tmK, tmV, tmR;
+    // k / v: [K, B, N*64] with row pitch ldkv: dims (d, b, j), box (64, 1, 64)
+    int rc = tc::make_tmap_3d(&tmK, k, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)ldkv, (uint64_t)B * ldkv, HS, 1, BJ);
+    if (rc) return rc;
+    rc = tc::make_tmap_3d(&tmV, v, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)ldkv, (uint64_t)B * ldkv, HS, 1, BJ);
+    if (rc) return rc;
+    rc = tc::make_tmap_2d(&tmR, r, (uint64_t)K, (uint64_t)N * HS, (uint64_t)ldr, BJ, HS);
+    if (rc) return rc;
+    FwdParams p;
+    p.q = (const bf16*)q; p.ldq = ldq; p.out = (bf16*)out; p.ldo = ldo; p.lse = lse; p.u = u; p.vb = vb; p.reset = reset;
+    p.B = B; p.N = N; p.Q = Q; p.M = M; p.K = K; p.msl = msl; p.same_length = same_length;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    p.drop_thresh = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    p.drop_key = dropout_key(seed, site);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(Q, BQ), B * N);
+    relattn_fwd_tc_kernel<<<grid, 160, FWD_SMEM, st>>>(tmK, tmV, tmR, p);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
+                        int64_t ldr, const float* u, const float* vb, const uint8_t* reset, const void* out,
+                        const void* dout, int64_t ldo, const float* lse, float* delta, void* dq, void* dk, void* dv,
+                        int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B, int N, int Q, int M,
+                        int msl, int same_length, float scale, float drop_p, uint64_t seed, uint64_t site,
+                        cudaStream_t st) {
+    (void)delta;
+    const int K = M + Q;
+    const uintptr_t al = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)out | (uintptr_t)dout |
+                         (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dr;
+    if (!(Q >= 32 && Q <= BQ && (al & 15) == 0 && lddr % 4 == 0)) {
+        tgan_set_error("tgan_relattn_bwd: shape not eligible for the tcgen05 kernel (needs 32 <= Q <= 128, 16-byte alignment)");
+        return -1;
+    }
+    CUtensorMap tmK, tmV, tmR;
+    int rc = tc::make_tmap_3d(&tmK, k, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)ldkv, (uint64_t)B * ldkv, HS, 1, BJ);
+    if (rc) return rc;
+    rc = tc::make_tmap_3d(&tmV, v, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)ldkv, (uint64_t)B * ldkv, HS, 1, BJ);
+    if (rc) return rc;
+    rc = tc::make_tmap_2d(&tmR, r, (uint64_t)K, (uint64_t)N * HS, (uint64_t)ldr, BJ, HS);
+    if (rc) return rc;
+    BwdParams p;
+    p.q = (const bf16*)q; p.ldq = ldq; p.out = (const bf16*)out; p.dout = (const bf16*)dout; p.ldo = ldo; p.lse = lse;
+    p.u = u; p.vb = vb; p.reset = reset; p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddkv = lddkv;
+    p.dr = dr; p.lddr = lddr; p.du = du; p.dvb = dvb;
+    p.B = B; p.N = N; p.Q = Q; p.M = M; p.K = K; p.msl = msl; p.same_length = same_length;
+    p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+    p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    p.drop_thresh = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    p.drop_key = dropout_key(seed, site);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        attr_set = true;
+    }
+    TGAN_CUDA_OK(cudaMemset2DAsync(dr, lddr * sizeof(float), 0, (size_t)N * HS * sizeof(float), K, st));
+    relattn_bwd_tc_kernel<<<B * N, 160, BWD_SMEM, st>>>(tmK, tmV, tmR, p);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
 }
