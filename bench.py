@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--warm-segments", type=int, default=None,
+                    help="untimed steps before timing (default: enough to fill the recurrence memory, >= --warmup)")
     return ap.parse_args()
 
 
@@ -309,7 +311,7 @@ def main():
         return ms.item(), L.launch_count() - l0
 
     # warm the recurrence memory to its steady-state length (M = mem_len) before timing: 8 segments
-    warm_segments = max(args.warmup, WORK["mem_len"] // Q)
+    warm_segments = args.warm_segments if args.warm_segments is not None else max(args.warmup, WORK["mem_len"] // Q)
     for _ in range(warm_segments):
         train_step(False)
     sampler = ClockSampler(local)

@@ -130,6 +130,30 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t site, 
     for (int t = 0; t < 8; ++t) m |= (uint32_t)dropout_keep_k(key, e0 + t, thresh) << t;
     return m;
 }
+// attention-probability dropout: one hash yields the keep decisions of a pair of adjacent keys (16 bits each);
+// the per-row key is hashed once per query row.  Shared by the SIMT and the tcgen05 attention kernels so that
+// both generate identical masks.
+__host__ __device__ __forceinline__ uint32_t attn_drop_rowkey(uint32_t key, uint32_t bn_row) {
+    return mix32(key ^ (bn_row * 0x9E3779B1u));
+}
+__host__ __device__ __forceinline__ uint32_t attn_drop_pair(uint32_t rowkey, uint32_t j_pair) {
+    return mix32(rowkey + j_pair * 0x85EBCA77u);
+}
+__host__ __device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int j, uint32_t thresh16) {
+    uint32_t h = attn_drop_pair(rowkey, (uint32_t)j >> 1);
+    return ((j & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh16;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
+    double t = (double)p * 65536.0 + 0.5;
+    if (t < 0) t = 0;
+    if (t > 65535.0) t = 65535.0;
+    return (uint32_t)t;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) {
     double t = (double)p * 4294967296.0;
     if (t < 0) t = 0;

@@ -20,8 +20,8 @@ constexpr int WARPS = 4;
 struct AttnArgs {
     int B, N, Q, M, K, msl, same_length;
     float scale, drop_scale;
-    uint32_t thresh;
-    uint64_t seed, site;
+    uint32_t thresh;  // 16-bit threshold (0 = dropout off)
+    uint32_t key;
 };
 
 template <typename T>
@@ -61,8 +61,7 @@ __device__ __forceinline__ bool attn_masked(int i, int j, int b_reset, const Att
 
 __device__ __forceinline__ bool drop_keep_ij(const AttnArgs& a, int bn, int i, int j) {
     if (!a.thresh) return true;
-    uint64_t e = ((uint64_t)bn * a.Q + i) * a.K + j;
-    return dropout_keep(a.seed, a.site, e, a.thresh);
+    return attn_drop_keep(attn_drop_rowkey(a.key, (uint32_t)(bn * a.Q + i)), j, a.thresh);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -360,8 +359,8 @@ AttnArgs make_args(int B, int N, int Q, int M, int msl, int same_length, float s
     AttnArgs a;
     a.B = B; a.N = N; a.Q = Q; a.M = M; a.K = M + Q; a.msl = msl; a.same_length = same_length; a.scale = scale;
     a.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    a.thresh = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
-    a.seed = seed; a.site = site;
+    a.thresh = drop_p > 0.f ? dropout_thresh16(drop_p) : 0u;
+    a.key = dropout_key(seed, site);
     return a;
 }
 }  // namespace

@@ -210,7 +210,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
 #pragma unroll
         for (int d = 0; d < HS; ++d) acc[d] = 0.f;
         int consumed = 0;
-        const uint64_t drop_base = ((uint64_t)bn * p.Q + i) * p.K;
+        const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + i));
         for (int tt = 0; tt < nt; ++tt) {
             // 1. pull new G chunks (tile tt needs chunks tt .. tt+2) into the thread-private ring
             while (consumed <= tt + 2 && consumed < nc) {
@@ -249,18 +249,32 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             int start = (BQ - 1 - ii + BJ * tt) % RING_COLS;      // ring column of jj = 0
             float s[64];
             float mx = -INFINITY;
+            // CTA-uniform: a tile strictly inside every row's [lower, causal] window needs no per-element mask
+            const bool interior = rows_here == BQ && j0 + BJ - 1 <= i0 + p.M &&
+                                  (!p.same_length || i0 + BQ - p.msl - j0 <= 0) && (!reset_b || p.M <= j0);
+            if (interior) {
 #pragma unroll
-            for (int jj = 0; jj < 64; ++jj) {
-                int col = start + jj;
-                col -= (col >= RING_COLS) ? RING_COLS : 0;
-                float v = (__uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii])) * p.scale_log2;
-                v = (jj >= lim_lo && jj <= lim_hi) ? v : -INFINITY;
-                s[jj] = v;
-                mx = fmaxf(mx, v);
+                for (int jj = 0; jj < 64; ++jj) {
+                    int col = start + jj;
+                    col -= (col >= RING_COLS) ? RING_COLS : 0;
+                    float v = (__uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii])) * p.scale_log2;
+                    s[jj] = v;
+                    mx = fmaxf(mx, v);
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 64; ++jj) {
+                    int col = start + jj;
+                    col -= (col >= RING_COLS) ? RING_COLS : 0;
+                    float v = (__uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii])) * p.scale_log2;
+                    v = (jj >= lim_lo && jj <= lim_hi) ? v : -INFINITY;
+                    s[jj] = v;
+                    mx = fmaxf(mx, v);
+                }
             }
             const float m_new = fmaxf(m, mx);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            corr = (m == -INFINITY) ? 0.f : exp2f(m - m_use);
+            corr = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
             m = m_new;
             // 4. fold the previous tile's P V into the running output (it finished long ago)
             if (tt > 0) {
@@ -276,17 +290,21 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             }
             // 5. probabilities -> (dropout) -> bf16 A operand for P V
             float lsum = 0.f;
+            const uint32_t rk_tile = rowkey + (uint32_t)(j0 >> 1) * 0x85EBCA77u;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float pv[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
+                for (int t = 0; t < 8; t += 2) {
                     const int jj = 8 * c + t;
-                    float e = exp2f(s[jj] - m_use);
-                    lsum += e;
-                    if (p.drop_thresh)
-                        e = dropout_keep_k(p.drop_key, drop_base + (uint64_t)(j0 + jj), p.drop_thresh) ? e * p.drop_scale : 0.f;
-                    pv[t] = e;
+                    float e0 = fast_exp2(s[jj] - m_use), e1 = fast_exp2(s[jj + 1] - m_use);
+                    lsum += e0 + e1;
+                    if (p.drop_thresh) {
+                        const uint32_t h = mix32(rk_tile + (uint32_t)(jj >> 1) * 0x85EBCA77u);
+                        e0 = (h & 0xffffu) >= p.drop_thresh ? e0 * p.drop_scale : 0.f;
+                        e1 = (h >> 16) >= p.drop_thresh ? e1 * p.drop_scale : 0.f;
+                    }
+                    pv[t] = e0; pv[t + 1] = e1;
                 }
                 store8(reinterpret_cast<bf16*>(gbase + OFF_P + sw128_off(ii, c)), pv);
             }
@@ -562,7 +580,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const int ii = threadIdx.x;
         const bool live = ii < rows_here;
         const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
-        const uint64_t drop_base = ((uint64_t)bn * p.Q + ii) * p.K;
+        const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + ii));
         int consumed = 0;
         // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * warp + lane
         auto flush_dr = [&](int cc) {
@@ -639,7 +657,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     int col = start + jj;
                     col -= (col >= RING_COLS) ? RING_COLS : 0;
                     float v = (__uint_as_float(sr[jj]) + __half2float(gring[col * BQ + ii])) * p.scale_log2;
-                    pr[jj] = (jj >= lim_lo && jj <= lim_hi) ? exp2f(v - lse2) : 0.f;
+                    pr[jj] = (jj >= lim_lo && jj <= lim_hi) ? fast_exp2(v - lse2) : 0.f;
                 }
             }
             mbar_wait(dp_full, tt & 1);
@@ -653,15 +671,18 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             if (lane == 0) mbar_arrive(dp_empty);
             // the P~ / dG buffer and the dR accumulator are free once the previous chunk's MMAs have been drained
             if (tt > 0) flush_dr(tt - 1);
+            const uint32_t rk_tile = rowkey + (uint32_t)(j0 >> 1) * 0x85EBCA77u;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 float pt8[8], ds8[8];
+                uint32_t hh[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) hh[t] = p.drop_thresh ? mix32(rk_tile + (uint32_t)(4 * c + t) * 0x85EBCA77u) : 0xffffffffu;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int jj = 8 * c + t;
                     float pj = pr[jj], dp = __uint_as_float(dpr[jj]);
-                    bool keep = true;
-                    if (p.drop_thresh) keep = dropout_keep_k(p.drop_key, drop_base + (uint64_t)(j0 + jj), p.drop_thresh);
+                    const bool keep = ((t & 1) ? (hh[t >> 1] >> 16) : (hh[t >> 1] & 0xffffu)) >= p.drop_thresh;
                     dp = keep ? dp * p.drop_scale : 0.f;
                     pt8[t] = keep ? pj * p.drop_scale : 0.f;
                     ds8[t] = pj * (dp - delta) * p.scale;
@@ -782,7 +803,7 @@ int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v
     p.B = B; p.N = N; p.Q = Q; p.M = M; p.K = K; p.msl = msl; p.same_length = same_length;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    p.drop_thresh = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    p.drop_thresh = drop_p > 0.f ? dropout_thresh16(drop_p) : 0u;
     p.drop_key = dropout_key(seed, site);
     static bool attr_set = false;
     if (!attr_set) {
@@ -824,7 +845,7 @@ int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v
     p.B = B; p.N = N; p.Q = Q; p.M = M; p.K = K; p.msl = msl; p.same_length = same_length;
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    p.drop_thresh = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
+    p.drop_thresh = drop_p > 0.f ? dropout_thresh16(drop_p) : 0u;
     p.drop_key = dropout_key(seed, site);
     static bool attr_set = false;
     if (!attr_set) {

@@ -54,37 +54,38 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const T* __res
     }
 }
 
-// embedding backward: one CTA per vocabulary id (no atomics, deterministic).  dE[v, c] += scale * sum dout[row, c]
+// embedding backward.  dE[v, c] += scale * sum_{rows: ids[row] == v} dropmask(dout[row, c]).
+// grid = (column blocks of 64, row slabs); each CTA accumulates its slab into a shared-memory table [V][64] with
+// shared-memory reductions (bank = column: conflict-free within a warp) and flushes non-zero entries with one
+// global reduction each.
 template <typename T>
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout, int64_t ldo,
-                                 float* __restrict__ dE, int64_t ldde, int rows, int D, float scale,
-                                 float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
-    __shared__ int s_ids[1024];
-    const int v = blockIdx.x;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // columns threadIdx.x + 256*t, D <= 1024
-    for (int r0 = 0; r0 < rows; r0 += 1024) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < 1024 && r0 + t < rows; t += blockDim.x) s_ids[t] = (int)ids[r0 + t];
-        __syncthreads();
-        int n = min(1024, rows - r0);
-        for (int t = 0; t < n; ++t) {
-            if (s_ids[t] != v) continue;  // block-uniform branch
-            int64_t row = r0 + t;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int c = threadIdx.x + 256 * u;
-                if (c < D) {
-                    float g = to_f(dout[row * ldo + c]);
-                    if (thresh) g = dropout_keep(seed, site, (uint64_t)row * ldo + c, thresh) ? g * drop_scale : 0.f;
-                    acc[u] += g;
-                }
-            }
+                                 float* __restrict__ dE, int64_t ldde, int rows, int V, int D, float scale,
+                                 float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site, int rows_per_block) {
+    extern __shared__ float tab[];  // [V][64]
+    const int c0 = blockIdx.x * 64;
+    for (int e = threadIdx.x; e < V * 64; e += blockDim.x) tab[e] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    const uint32_t key = dropout_key(seed, site);
+    const int c = c0 + 2 * lane;
+    for (int row = r0 + warp; row < r1; row += nwarps) {
+        const int v = (int)ids[row];
+        float g0 = c < D ? to_f(dout[(int64_t)row * ldo + c]) : 0.f;
+        float g1 = c + 1 < D ? to_f(dout[(int64_t)row * ldo + c + 1]) : 0.f;
+        if (thresh) {
+            g0 = dropout_keep_k(key, (uint64_t)row * ldo + c, thresh) ? g0 * drop_scale : 0.f;
+            g1 = dropout_keep_k(key, (uint64_t)row * ldo + c + 1, thresh) ? g1 * drop_scale : 0.f;
         }
+        atomicAdd(&tab[v * 64 + 2 * lane], g0);
+        atomicAdd(&tab[v * 64 + 2 * lane + 1], g1);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        int c = threadIdx.x + 256 * u;
-        if (c < D && acc[u] != 0.f) dE[(int64_t)v * ldde + c] += scale * acc[u];
+    __syncthreads();
+    for (int e = threadIdx.x; e < V * 64; e += blockDim.x) {
+        const float t = tab[e];
+        const int cc = c0 + (e & 63);
+        if (t != 0.f && cc < D) atomicAdd(&dE[(int64_t)(e >> 6) * ldde + cc], scale * t);
     }
 }
 
@@ -510,11 +511,21 @@ extern "C" int tgan_embed_bwd(int dtype, const int64_t* ids, const void* dout, i
                               int rows, int V, int D, float scale, float drop_p, uint64_t seed, uint64_t site,
                               void* stream) {
     if (rows <= 0) return 0;
-    TGAN_CHECK_ARG(D <= 1024, "tgan_embed_bwd: D <= 1024 supported");
+    const size_t smem = (size_t)V * 64 * sizeof(float);
+    TGAN_CHECK_ARG(smem <= 200 * 1024, "tgan_embed_bwd: vocabulary too large for the shared-memory table (V <= 800)");
     uint32_t th = drop_p > 0.f ? dropout_thresh(drop_p) : 0u;
     float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    DISPATCH_T(dtype, (embed_bwd_kernel<T><<<V, 256, 0, ST>>>(ids, (const T*)dout, ldo, dE, ldde, rows, D, scale, ds,
-                                                               th, seed, site)));
+    int slabs = min(ceil_div(rows, 256), 32);
+    int rpb = ceil_div(rows, slabs);
+    slabs = ceil_div(rows, rpb);
+    dim3 grid(ceil_div(D, 64), slabs);
+    if (dtype == TGAN_F32) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(embed_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        embed_bwd_kernel<float><<<grid, 512, smem, ST>>>(ids, (const float*)dout, ldo, dE, ldde, rows, V, D, scale, ds, th, seed, site, rpb);
+    } else if (dtype == TGAN_BF16) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(embed_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        embed_bwd_kernel<bf16><<<grid, 512, smem, ST>>>(ids, (const bf16*)dout, ldo, dE, ldde, rows, V, D, scale, ds, th, seed, site, rpb);
+    } else { tgan_set_error("bad dtype %d", dtype); return 1; }
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
