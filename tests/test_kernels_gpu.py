@@ -89,6 +89,12 @@ def test_gemm_tc_large_k_accumulation_and_persistence():
     L.gemm(A, B, C, transA=True, transB=False, M=M, N=N, K=K, impl=2)
     ref = A.float().t() @ B.float()
     assert (C - ref).abs().max().item() < 2e-2
+    # split-K with accumulation onto an existing fp32 gradient, ragged N, row pitch wider than N
+    C0 = _rand(M, N + 8, seed=21)
+    C = C0.clone()
+    L.gemm(A, B, C, transA=True, transB=False, M=M, N=N - 3, K=K, flags=L.EPI_ACCUM, alpha=0.5, impl=2)
+    assert (C[:, :N - 3] - (C0[:, :N - 3] + 0.5 * ref[:, :N - 3])).abs().max().item() < 2e-2
+    assert torch.equal(C[:, N - 3:], C0[:, N - 3:])
     M, N, K = 148 * 128 * 2 + 77, 256, 192
     A, B = _rand(M, K, dtype=torch.bfloat16, seed=11), _rand(N, K, dtype=torch.bfloat16, seed=12)
     C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)

@@ -115,20 +115,35 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __host__ __device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint64_t site) {
     return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) ^ mix32((uint32_t)site ^ mix32((uint32_t)(site >> 32) + 0x9E3779B9u))));
 }
-__host__ __device__ __forceinline__ bool dropout_keep_k(uint32_t key, uint64_t e, uint32_t thresh) {
-    uint32_t x = mix32(((uint32_t)e * 0x9E3779B1u) ^ ((uint32_t)(e >> 32) * 0x85EBCA77u) ^ key);
-    return x >= thresh;  // thresh = p * 2^32
+// one hash decides a PAIR of consecutive elements (16 random bits each): halves the integer work per element.
+__host__ __device__ __forceinline__ uint32_t dropout_hash_pair(uint32_t key, uint64_t pair) {
+    return mix32(((uint32_t)pair * 0x9E3779B1u) ^ ((uint32_t)(pair >> 32) * 0x85EBCA77u) ^ key);
 }
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t site, uint64_t e, uint32_t thresh) {
-    return dropout_keep_k(dropout_key(seed, site), e, thresh);
+__host__ __device__ __forceinline__ bool dropout_keep_k(uint32_t key, uint64_t e, uint32_t thresh16) {
+    const uint32_t h = dropout_hash_pair(key, e >> 1);
+    return ((e & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh16;  // thresh16 = p * 2^16
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t site, uint64_t e, uint32_t thresh16) {
+    return dropout_keep_k(dropout_key(seed, site), e, thresh16);
 }
 // keep bits for the 8 consecutive elements e0 .. e0+7
-__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t site, uint64_t e0, uint32_t thresh) {
-    const uint32_t key = dropout_key(seed, site);
+__host__ __device__ __forceinline__ uint32_t dropout_keep8_k(uint32_t key, uint64_t e0, uint32_t thresh16) {
     uint32_t m = 0;
+    if ((e0 & 1) == 0) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) m |= (uint32_t)dropout_keep_k(key, e0 + t, thresh) << t;
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t h = dropout_hash_pair(key, (e0 >> 1) + t);
+            m |= (uint32_t)((h & 0xffffu) >= thresh16) << (2 * t);
+            m |= (uint32_t)((h >> 16) >= thresh16) << (2 * t + 1);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) m |= (uint32_t)dropout_keep_k(key, e0 + t, thresh16) << t;
+    }
     return m;
+}
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t site, uint64_t e0, uint32_t thresh16) {
+    return dropout_keep8_k(dropout_key(seed, site), e0, thresh16);
 }
 // attention-probability dropout: one hash yields the keep decisions of a pair of adjacent keys (16 bits each);
 // the per-row key is hashed once per query row.  Shared by the SIMT and the tcgen05 attention kernels so that
@@ -154,12 +169,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) {
-    double t = (double)p * 4294967296.0;
-    if (t < 0) t = 0;
-    if (t > 4294967295.0) t = 4294967295.0;
-    return (uint32_t)t;
-}
+// every dropout site uses 16-bit thresholds (p quantised to 2^-16)
+__host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) { return dropout_thresh16(p); }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -203,7 +214,7 @@ struct EpiParams {
     int flags;
     float alpha;
     float drop_scale;      // 1/(1-p)
-    uint32_t drop_thresh;  // p * 2^32
+    uint32_t drop_thresh;  // p * 2^16
     uint32_t drop_key;     // dropout_key(seed, site)
     int aux_is_f32;        // aux element type when the flag says so (TGAN_EPI_AUX_F32)
 };

@@ -78,41 +78,149 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = 64;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int STG_BYTES = 4 * 32 * 33 * 4;
+constexpr int EPI_ATOMIC = 1 << 20;   // internal: split-K partial sums are added with red.global.add (fp32 C)
+constexpr int EPI_VEC = 1 << 21;      // internal: C / aux rows are 16-byte aligned -> 8-wide vector accesses
+constexpr int EPI_BIAS_VEC = 1 << 22; // internal: bias pointer is 16-byte aligned
 
 template <int BN> struct Cfg {
     static constexpr int STAGES = BN == 256 ? 4 : 6;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + STG_BYTES + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 8 * (2 * STAGES + 4) + 16 + 1024;
 };
+
+__device__ __forceinline__ void red_add_f32x4(float* addr, const float* v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                 : "memory");
+}
+
+// Epilogue of one accumulator row segment: 32 consecutive columns [col0, col0+32) of row `row`, owned by one thread
+// (thread = TMEM lane = output row, so every global access is a row-contiguous 16/32-byte vector).
+template <typename TC>
+__device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int col0, int N, TC* __restrict__ C,
+                                          int64_t ldc, const EpiParams& ep) {
+    const int flags = ep.flags;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int col = col0 + 8 * g;
+        if (col >= N) break;
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(regs[8 * g + t]) * ep.alpha;
+        TC* cp = C + row * ldc + col;
+        if ((flags & EPI_VEC) && col + 8 <= N) {
+            if (flags & TGAN_EPI_BIAS) {
+                float b[8];
+                if (flags & EPI_BIAS_VEC) load8(ep.bias + col, b);
+                else {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) b[t] = __ldg(ep.bias + col + t);
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] += b[t];
+            }
+            if (flags & TGAN_EPI_RELU) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+            }
+            float a[8];
+            if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX)) {
+                if (ep.aux_is_f32) load8((const float*)ep.aux + row * ep.ldaux + col, a);
+                else load8((const bf16*)ep.aux + row * ep.ldaux + col, a);
+            }
+            if (flags & TGAN_EPI_MASK_POS) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = a[t] > 0.f ? v[t] : 0.f;
+            }
+            if (flags & TGAN_EPI_DROPOUT) {
+                const uint32_t keep = dropout_keep8_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * ep.drop_scale : 0.f;
+            }
+            if (flags & TGAN_EPI_ADD_AUX) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] += a[t];
+            }
+            if (flags & EPI_ATOMIC) {
+                red_add_f32x4((float*)cp, v);
+                red_add_f32x4((float*)cp + 4, v + 4);
+            } else {
+                if (flags & TGAN_EPI_ACCUM) {
+                    float c[8];
+                    load8(cp, c);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[t] += c[t];
+                }
+                store8(cp, v);
+            }
+        } else {
+            const int nv = min(8, N - col);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (t < nv) {
+                    float x = v[t];
+                    if (flags & TGAN_EPI_BIAS) x += __ldg(ep.bias + col + t);
+                    if (flags & TGAN_EPI_RELU) x = fmaxf(x, 0.f);
+                    float a = 0.f;
+                    if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX))
+                        a = ep.aux_is_f32 ? ((const float*)ep.aux)[row * ep.ldaux + col + t]
+                                          : to_f(((const bf16*)ep.aux)[row * ep.ldaux + col + t]);
+                    if (flags & TGAN_EPI_MASK_POS) x = a > 0.f ? x : 0.f;
+                    if (flags & TGAN_EPI_DROPOUT)
+                        x = dropout_keep_k(ep.drop_key, (uint64_t)row * ldc + col + t, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
+                    if (flags & TGAN_EPI_ADD_AUX) x += a;
+                    if (flags & EPI_ATOMIC) atomicAdd((float*)(cp + t), x);
+                    else {
+                        if (flags & TGAN_EPI_ACCUM) x += to_f(cp[t]);
+                        cp[t] = from_f<TC>(x);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// work item w -> (output tile, K split).  Consecutive CTAs share the A row block (tiles of one m are adjacent).
+struct Work {
+    int m0, n0, kb0, kb1;
+};
+template <int BN>
+__device__ __forceinline__ Work get_work(int w, int num_tiles, int tiles_n, int nk, int kb_per_split) {
+    const int tile = w % num_tiles, split = w / num_tiles;
+    Work r;
+    r.m0 = (tile / tiles_n) * BM;
+    r.n0 = (tile % tiles_n) * BN;
+    r.kb0 = split * kb_per_split;
+    r.kb1 = min(nk, r.kb0 + kb_per_split);
+    return r;
+}
 
 template <int BN, bool A_MN, bool B_MN, typename TC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TC* __restrict__ C,
-               int64_t ldc, int M, int N, int K, EpiParams ep) {
+               int64_t ldc, int M, int N, int K, int splits, int kb_per_split, EpiParams ep) {
     constexpr int STAGES = Cfg<BN>::STAGES;
     constexpr int B_BYTES = Cfg<BN>::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base, sB = base + STAGES * A_BYTES;
-    const uint32_t sStg = sB + STAGES * B_BYTES;
-    const uint32_t sBar = sStg + STG_BYTES;
+    const uint32_t sBar = sB + STAGES * B_BYTES;
     const uint32_t full0 = sBar, empty0 = sBar + 8 * STAGES, tfull0 = sBar + 16 * STAGES, tempty0 = tfull0 + 16;
     const uint32_t sTmemPtr = tempty0 + 16;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    float* stg_all = reinterpret_cast<float*>(gen_base + STAGES * (A_BYTES + B_BYTES));
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
     const int num_tiles = tiles_m * tiles_n;
+    const int num_work = num_tiles * splits;
     const int nk = (K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
@@ -126,22 +234,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-                for (int kb = 0; kb < nk; ++kb) {
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+                const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
+                for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const uint32_t fb = full0 + 8 * s;
                     mbar_expect_tx(fb, A_BYTES + B_BYTES);
                     const uint32_t a_dst = sA + s * A_BYTES, b_dst = sB + s * B_BYTES;
-                    if (!A_MN) tma_load_2d(a_dst, &tmA, fb, kb * BK, m0);
+                    if (!A_MN) tma_load_2d(a_dst, &tmA, fb, kb * BK, wk.m0);
                     else {
 #pragma unroll
-                        for (int bx = 0; bx < BM / 64; ++bx) tma_load_2d(a_dst + bx * 8192, &tmA, fb, m0 + 64 * bx, kb * BK);
+                        for (int bx = 0; bx < BM / 64; ++bx) tma_load_2d(a_dst + bx * 8192, &tmA, fb, wk.m0 + 64 * bx, kb * BK);
                     }
-                    if (!B_MN) tma_load_2d(b_dst, &tmB, fb, kb * BK, n0);
+                    if (!B_MN) tma_load_2d(b_dst, &tmB, fb, kb * BK, wk.n0);
                     else {
 #pragma unroll
-                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(b_dst + bx * 8192, &tmB, fb, n0 + 64 * bx, kb * BK);
+                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(b_dst + bx * 8192, &tmB, fb, wk.n0 + 64 * bx, kb * BK);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -152,12 +260,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             int s = 0; uint32_t ph = 0; int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+                const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
                 const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * as, aph ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
                     mbar_wait(full0 + 8 * s, ph);
                     tcgen05_fence_after();
                     const uint32_t a_src = sA + s * A_BYTES, b_src = sB + s * B_BYTES;
@@ -167,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                  : umma_smem_desc(a_src + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? umma_smem_desc(b_src + k * 2048, 8192, 1024)
                                                  : umma_smem_desc(b_src + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, da, db, idesc, (kb != wk.kb0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -177,47 +286,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue warps =====================
-        const int ew = warp & 3;  // TMEM lane quarter this warp may access
-        float* stg = stg_all + (warp - 2) * (32 * 33);
-        const int flags = ep.flags;
+        // warp w may only touch TMEM lanes 32*(w%4) .. +31; the two warps sharing a lane quarter split the columns
+        const int eq = warp & 3, eh = (warp - 2) >> 2;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+            const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
             const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull0 + 8 * as, aph);
             tcgen05_fence_after();
-            const int row_base = m0 + 32 * ew;
+            const int64_t row = wk.m0 + 32 * eq + lane;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (n0 + c0 >= N || row_base >= M) break;  // warp-uniform
+            for (int c0 = eh * (BN / 2); c0 < (eh + 1) * (BN / 2); c0 += 32) {
+                if (wk.n0 + c0 >= N) break;  // warp-uniform
                 uint32_t regs[32];
-                tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * ew) << 16), regs);
+                tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * eq) << 16), regs);
                 tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(regs[c]);
-                __syncwarp();
-                const int col = n0 + c0 + lane;
-                if (col < N) {
-                    const float bias_v = (flags & TGAN_EPI_BIAS) ? ep.bias[col] : 0.f;
-                    const int rmax = min(32, M - row_base);
-                    for (int rr = 0; rr < rmax; ++rr) {
-                        const int64_t row = row_base + rr;
-                        float v = stg[rr * 33 + lane] * ep.alpha + bias_v;
-                        if (flags & TGAN_EPI_RELU) v = fmaxf(v, 0.f);
-                        float a = 0.f;
-                        if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX))
-                            a = ep.aux_is_f32 ? ((const float*)ep.aux)[row * ep.ldaux + col]
-                                              : to_f(((const bf16*)ep.aux)[row * ep.ldaux + col]);
-                        if (flags & TGAN_EPI_MASK_POS) v = a > 0.f ? v : 0.f;
-                        if (flags & TGAN_EPI_DROPOUT)
-                            v = dropout_keep_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
-                        if (flags & TGAN_EPI_ADD_AUX) v += a;
-                        TC* cp = C + row * ldc + col;
-                        if (flags & TGAN_EPI_ACCUM) v += to_f(*cp);
-                        *cp = from_f<TC>(v);
-                    }
-                }
-                __syncwarp();
+                if (row < M) epi_row32<TC>(regs, row, wk.n0 + c0, N, C, ldc, ep);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -233,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, bool A_MN, bool B_MN, typename TC>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M, int N, int K,
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M, int N, int K, int splits,
               const EpiParams& ep, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC>;
     static bool attr_set = false;
@@ -241,9 +325,12 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t l
         TGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         attr_set = true;
     }
-    const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, (TC*)C, ldc, M, N, K, ep);
+    const int nk = ceil_div(K, BK);
+    const int kb_per_split = ceil_div(nk, splits);
+    splits = ceil_div(nk, kb_per_split);  // no empty split
+    const int work = ceil_div(M, BM) * ceil_div(N, BN) * splits;
+    const int grid = work < sm_count() ? work : sm_count();
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, (TC*)C, ldc, M, N, K, splits, kb_per_split, ep);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
@@ -251,12 +338,12 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t l
 
 template <int BN, typename TC>
 int launch_layout(int transA, int transB, const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M,
-                  int N, int K, const EpiParams& ep, cudaStream_t st) {
+                  int N, int K, int splits, const EpiParams& ep, cudaStream_t st) {
     // transA = 1 -> A stored [K, M] -> MN-major A;  transB = 0 -> B stored [K, N] -> MN-major B
-    if (!transA && transB) return launch_tc<BN, false, false, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
-    if (!transA && !transB) return launch_tc<BN, false, true, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
-    if (transA && transB) return launch_tc<BN, true, false, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
-    return launch_tc<BN, true, true, TC>(tmA, tmB, C, ldc, M, N, K, ep, st);
+    if (!transA && transB) return launch_tc<BN, false, false, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    if (!transA && !transB) return launch_tc<BN, false, true, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    if (transA && transB) return launch_tc<BN, true, false, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    return launch_tc<BN, true, true, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
 }
 }  // namespace
 
@@ -291,11 +378,37 @@ int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const
     ep.drop_thresh = dropout_thresh(drop_p);
     ep.drop_key = dropout_key(seed, site);
     ep.aux_is_f32 = (flags & TGAN_EPI_AUX_F32) ? 1 : 0;
-    if (drop_p <= 0.f) ep.flags &= ~TGAN_EPI_DROPOUT;
-    if (dtype_c == TGAN_F32) {
-        if (BN == 256) return launch_layout<256, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
-        return launch_layout<128, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
+    if (drop_p <= 0.f || ep.drop_thresh == 0) ep.flags &= ~TGAN_EPI_DROPOUT;
+    // vector epilogue: rows of C (and aux) start 16-byte aligned
+    const int esz_c = dtype_c == TGAN_F32 ? 4 : 2;
+    bool vec = (((uintptr_t)C & 15) == 0) && ((ldc * esz_c) % 16 == 0);
+    if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX)) {
+        const int esz_a = ep.aux_is_f32 ? 4 : 2;
+        vec = vec && (((uintptr_t)aux & 15) == 0) && ((ldaux * esz_a) % 16 == 0);
     }
-    if (BN == 256) return launch_layout<256, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
-    return launch_layout<128, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, ep, st);
+    if (vec) ep.flags |= EPI_VEC;
+    if ((flags & TGAN_EPI_BIAS) && (((uintptr_t)bias & 15) == 0)) ep.flags |= EPI_BIAS_VEC;
+    // split-K: weight-gradient shapes (few output tiles, very long K) would leave most SMs idle.  Partial sums are
+    // added into the fp32 output with red.global.add; without ACCUM the output is zeroed first.
+    int splits = 1;
+    {
+        const int tiles = ceil_div(M, BM) * ceil_div(N, BN), nk = ceil_div(K, BK);
+        const int plain = flags & ~(TGAN_EPI_ACCUM | TGAN_EPI_AUX_F32);
+        if (dtype_c == TGAN_F32 && plain == 0 && tiles * 2 <= sm_count() && nk >= 16) {
+            splits = sm_count() / tiles;
+            if (splits > nk / 8) splits = nk / 8;
+            if (splits < 1) splits = 1;
+        }
+        if (splits > 1) {
+            if (!(flags & TGAN_EPI_ACCUM))
+                TGAN_CUDA_OK(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+            ep.flags = (ep.flags & ~TGAN_EPI_ACCUM) | EPI_ATOMIC;
+        }
+    }
+    if (dtype_c == TGAN_F32) {
+        if (BN == 256) return launch_layout<256, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+        return launch_layout<128, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    }
+    if (BN == 256) return launch_layout<256, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    return launch_layout<128, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
 }
