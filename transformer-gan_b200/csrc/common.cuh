@@ -151,8 +151,13 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t site, 
 __host__ __device__ __forceinline__ uint32_t attn_drop_rowkey(uint32_t key, uint32_t bn_row) {
     return mix32(key ^ (bn_row * 0x9E3779B1u));
 }
+// one-multiply finaliser: the row key is already fully mixed, so a Weyl step + multiply + two xor-shifts suffice
+__host__ __device__ __forceinline__ uint32_t attn_mixlite(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15;
+    return x;
+}
 __host__ __device__ __forceinline__ uint32_t attn_drop_pair(uint32_t rowkey, uint32_t j_pair) {
-    return mix32(rowkey + j_pair * 0x85EBCA77u);
+    return attn_mixlite(rowkey + j_pair * 0x85EBCA77u);
 }
 __host__ __device__ __forceinline__ bool attn_drop_keep(uint32_t rowkey, int j, uint32_t thresh16) {
     uint32_t h = attn_drop_pair(rowkey, (uint32_t)j >> 1);

@@ -40,310 +40,6 @@ constexpr int FWD_SMEM = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
 // TMEM columns
 constexpr int TM_S = 0, TM_G = 128, TM_O = 256, TM_COLS = 512;
 
-struct FwdParams {
-    const bf16* q; int64_t ldq;
-    bf16* out; int64_t ldo;
-    float* lse;
-    const float* u; const float* vb;
-    const uint8_t* reset;
-    int B, N, Q, M, K, msl, same_length;
-    float scale_log2;  // scale * log2(e)
-    float drop_scale; uint32_t drop_thresh; uint32_t drop_key;
-};
-
-// byte offset of the 16-byte chunk `c` (8 bf16) of row `r` inside a K-major SWIZZLE_128B tile with 128-byte rows
-__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
-
-__global__ void __launch_bounds__(160, 1)
-relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                      const __grid_constant__ CUtensorMap tmR, FwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sQu = base + OFF_QU, sQv = base + OFF_QV, sKV = base + OFF_KV, sR = base + OFF_R, sP = base + OFF_P;
-    __half* ring = reinterpret_cast<__half*>(gbase + OFF_RING);
-    const uint32_t bar0 = base + OFF_BAR;
-    // barrier map
-    const uint32_t kv_full = bar0, kv_empty = kv_full + 8 * KV_STAGES, r_full = kv_empty + 8 * KV_STAGES,
-                   r_empty = r_full + 16, s_full = r_empty + 16, s_empty = s_full + 16, g_full = s_empty + 16,
-                   g_empty = g_full + 16, p_full = g_empty + 16, o_full = p_full + 8;
-    const uint32_t sTmemPtr = o_full + 8;
-    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bn = blockIdx.y, b = bn / p.N, n = bn % p.N;
-    const int i0 = blockIdx.x * BQ;
-    const int rows_here = min(BQ, p.Q - i0);
-    const bool reset_b = p.reset && p.reset[b];
-
-    // key range needed by this query tile (CTA-uniform)
-    int jlo = 0, jhi = min(p.K - 1, i0 + rows_here - 1 + p.M);
-    if (p.same_length) jlo = max(0, i0 - p.msl + 1);
-    if (reset_b) jlo = max(jlo, p.M);
-    const int t_lo = jlo / BJ, t_hi = jhi / BJ;
-    const int nt = t_hi - t_lo + 1;  // >= 1
-    const int nc = nt + 2;           // G chunks
-    const int P0 = p.Q - 1 - i0 - (BQ - 1) + BJ * t_lo;  // relative position of column 0 of chunk 0
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(r_full + 8 * s, 1); mbar_init(r_empty + 8 * s, 1);
-            mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, 4);
-            mbar_init(g_full + 8 * s, 1); mbar_init(g_empty + 8 * s, 4);
-        }
-        mbar_init(p_full, 4);
-        mbar_init(o_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 4) tmem_alloc(sTmemPtr, TM_COLS);
-
-    // ---- stage (q + u), (q + vb) as swizzled K-major A operands (row warps) ----
-    if (warp < 4) {
-        const int ii = threadIdx.x;  // 0..127
-        const bool live = ii < rows_here;
-        const bf16* qrow = p.q + ((int64_t)(i0 + ii) * p.B + b) * p.ldq + n * HS;
-#pragma unroll
-        for (int c = 0; c < HS / 8; ++c) {
-            float x[8], a[8], bb[8];
-            if (live) load8(qrow + 8 * c, x);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                float qv = live ? x[t] : 0.f;
-                a[t] = live ? qv + p.u[n * HS + 8 * c + t] : 0.f;
-                bb[t] = live ? qv + p.vb[n * HS + 8 * c + t] : 0.f;
-            }
-            store8(reinterpret_cast<bf16*>(gbase + OFF_QU + sw128_off(ii, c)), a);
-            store8(reinterpret_cast<bf16*>(gbase + OFF_QV + sw128_off(ii, c)), bb);
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_gen;
-
-    if (warp == 4) {
-        // =========================== control thread: TMA + MMA issue ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc_kk = umma_idesc_bf16(BQ, BJ, 0, 0);  // A, B K-major
-            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HS, 0, 1);  // B (= V tile [keys][d]) MN-major
-            auto issue_kv = [&](int tt) {
-                if (tt >= nt) return;
-                const int st = tt % KV_STAGES;
-                mbar_wait(kv_empty + 8 * st, ((tt / KV_STAGES) & 1) ^ 1);
-                mbar_expect_tx(kv_full + 8 * st, 2 * BJ * HS * 2);
-                const uint32_t dst = sKV + st * (2 * BJ * HS * 2);
-                tma_load_3d(dst, &tmK, kv_full + 8 * st, n * HS, b, (t_lo + tt) * BJ);
-                tma_load_3d(dst + BJ * HS * 2, &tmV, kv_full + 8 * st, n * HS, b, (t_lo + tt) * BJ);
-            };
-            auto issue_r = [&](int cc) {
-                if (cc >= nc) return;
-                const int st = cc & 1;
-                mbar_wait(r_empty + 8 * st, ((cc >> 1) & 1) ^ 1);
-                mbar_expect_tx(r_full + 8 * st, BJ * HS * 2);
-                tma_load_2d(sR + st * (BJ * HS * 2), &tmR, r_full + 8 * st, n * HS, P0 + BJ * cc);
-            };
-            auto mma_s = [&](int tt) {
-                if (tt >= nt) return;
-                const int st = tt % KV_STAGES;
-                mbar_wait(kv_full + 8 * st, (tt / KV_STAGES) & 1);
-                mbar_wait(s_empty + 8 * (tt & 1), ((tt >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                const uint32_t kaddr = sKV + st * (2 * BJ * HS * 2);
-#pragma unroll
-                for (int k = 0; k < HS / 16; ++k)
-                    umma_bf16(tmem_base + TM_S + BJ * (tt & 1), umma_smem_desc(sQu + 32 * k, 16, 1024),
-                              umma_smem_desc(kaddr + 32 * k, 16, 1024), idesc_kk, k != 0);
-                umma_commit(s_full + 8 * (tt & 1));
-            };
-            auto mma_g = [&](int cc) {
-                if (cc >= nc) return;
-                const int st = cc & 1;
-                mbar_wait(r_full + 8 * st, (cc >> 1) & 1);
-                mbar_wait(g_empty + 8 * st, ((cc >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                const uint32_t raddr = sR + st * (BJ * HS * 2);
-#pragma unroll
-                for (int k = 0; k < HS / 16; ++k)
-                    umma_bf16(tmem_base + TM_G + BJ * st, umma_smem_desc(sQv + 32 * k, 16, 1024),
-                              umma_smem_desc(raddr + 32 * k, 16, 1024), idesc_kk, k != 0);
-                umma_commit(g_full + 8 * st);
-                umma_commit(r_empty + 8 * st);
-            };
-            auto mma_pv = [&](int tt) {
-                const int st = tt % KV_STAGES;
-                mbar_wait(p_full, tt & 1);
-                tcgen05_fence_after();
-                const uint32_t vaddr = sKV + st * (2 * BJ * HS * 2) + BJ * HS * 2;
-#pragma unroll
-                for (int k = 0; k < BJ / 16; ++k)
-                    umma_bf16(tmem_base + TM_O, umma_smem_desc(sP + 32 * k, 16, 1024),
-                              umma_smem_desc(vaddr + 2048 * k, 8192, 1024), idesc_pv, k != 0);
-                umma_commit(o_full);
-                umma_commit(kv_empty + 8 * st);
-            };
-            issue_kv(0); issue_kv(1);
-            issue_r(0); issue_r(1);
-            mma_s(0);
-            mma_g(0); issue_r(2);
-            mma_g(1); issue_r(3);
-            mma_g(2);
-            for (int tt = 0; tt < nt; ++tt) {
-                issue_kv(tt + 2);
-                issue_r(tt + 4);
-                mma_s(tt + 1);
-                mma_g(tt + 3);
-                mma_pv(tt);
-            }
-        }
-    } else {
-        // =========================== row warps: softmax / rel-shift / dropout ===========================
-        const int ii = threadIdx.x;
-        const int i = i0 + ii;
-        const bool live = ii < rows_here;
-        const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
-        float m = -INFINITY, l = 0.f, corr = 1.f;
-        float acc[HS];
-#pragma unroll
-        for (int d = 0; d < HS; ++d) acc[d] = 0.f;
-        int consumed = 0;
-        const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + i));
-        for (int tt = 0; tt < nt; ++tt) {
-            // 1. pull new G chunks (tile tt needs chunks tt .. tt+2) into the thread-private ring
-            while (consumed <= tt + 2 && consumed < nc) {
-                const int st = consumed & 1;
-                mbar_wait(g_full + 8 * st, (consumed >> 1) & 1);
-                tcgen05_fence_after();
-                uint32_t g[64];
-                tmem_ld32(tmem_base + TM_G + BJ * st + lane_off, g);
-                tmem_ld32(tmem_base + TM_G + BJ * st + 32 + lane_off, g + 32);
-                tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(g_empty + 8 * st);
-                __half* dst = ring + (consumed % 3) * (BJ * BQ) + ii;
-#pragma unroll
-                for (int c = 0; c < 64; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
-                ++consumed;
-            }
-            // 2. content scores
-            mbar_wait(s_full + 8 * (tt & 1), (tt >> 1) & 1);
-            tcgen05_fence_after();
-            uint32_t sr[64];
-            tmem_ld32(tmem_base + TM_S + BJ * (tt & 1) + lane_off, sr);
-            tmem_ld32(tmem_base + TM_S + BJ * (tt & 1) + 32 + lane_off, sr + 32);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty + 8 * (tt & 1));
-            // 3. add the shifted position scores, mask, running max
-            const int j0 = (t_lo + tt) * BJ;
-            int lim_hi = live ? (i + p.M - j0) : -1;              // jj <= lim_hi  (causal + memory)
-            int lim_lo = 0;                                        // jj >= lim_lo
-            if (p.same_length) lim_lo = max(lim_lo, i - p.msl + 1 - j0);
-            if (reset_b) lim_lo = max(lim_lo, p.M - j0);
-            lim_hi = min(lim_hi, p.K - 1 - j0);
-            int start = (BQ - 1 - ii + BJ * tt) % RING_COLS;      // ring column of jj = 0
-            float s[64];
-            float mx = -INFINITY;
-            // CTA-uniform: a tile strictly inside every row's [lower, causal] window needs no per-element mask
-            const bool interior = rows_here == BQ && j0 + BJ - 1 <= i0 + p.M &&
-                                  (!p.same_length || i0 + BQ - p.msl - j0 <= 0) && (!reset_b || p.M <= j0);
-            if (interior) {
-#pragma unroll
-                for (int jj = 0; jj < 64; ++jj) {
-                    int col = start + jj;
-                    col -= (col >= RING_COLS) ? RING_COLS : 0;
-                    float v = (__uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii])) * p.scale_log2;
-                    s[jj] = v;
-                    mx = fmaxf(mx, v);
-                }
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < 64; ++jj) {
-                    int col = start + jj;
-                    col -= (col >= RING_COLS) ? RING_COLS : 0;
-                    float v = (__uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii])) * p.scale_log2;
-                    v = (jj >= lim_lo && jj <= lim_hi) ? v : -INFINITY;
-                    s[jj] = v;
-                    mx = fmaxf(mx, v);
-                }
-            }
-            const float m_new = fmaxf(m, mx);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            corr = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
-            m = m_new;
-            // 4. fold the previous tile's P V into the running output (it finished long ago)
-            if (tt > 0) {
-                mbar_wait(o_full, (tt - 1) & 1);
-                tcgen05_fence_after();
-                uint32_t o[64];
-                tmem_ld32(tmem_base + TM_O + lane_off, o);
-                tmem_ld32(tmem_base + TM_O + 32 + lane_off, o + 32);
-                tmem_ld_wait();
-                tcgen05_fence_before();
-#pragma unroll
-                for (int d = 0; d < HS; ++d) acc[d] = (acc[d] + __uint_as_float(o[d])) * corr;
-            }
-            // 5. probabilities -> (dropout) -> bf16 A operand for P V
-            float lsum = 0.f;
-            const uint32_t rk_tile = rowkey + (uint32_t)(j0 >> 1) * 0x85EBCA77u;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float pv[8];
-#pragma unroll
-                for (int t = 0; t < 8; t += 2) {
-                    const int jj = 8 * c + t;
-                    float e0 = fast_exp2(s[jj] - m_use), e1 = fast_exp2(s[jj + 1] - m_use);
-                    lsum += e0 + e1;
-                    if (p.drop_thresh) {
-                        const uint32_t h = mix32(rk_tile + (uint32_t)(jj >> 1) * 0x85EBCA77u);
-                        e0 = (h & 0xffffu) >= p.drop_thresh ? e0 * p.drop_scale : 0.f;
-                        e1 = (h >> 16) >= p.drop_thresh ? e1 * p.drop_scale : 0.f;
-                    }
-                    pv[t] = e0; pv[t + 1] = e1;
-                }
-                store8(reinterpret_cast<bf16*>(gbase + OFF_P + sw128_off(ii, c)), pv);
-            }
-            l = l * corr + lsum;
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        // last tile's P V
-        mbar_wait(o_full, (nt - 1) & 1);
-        tcgen05_fence_after();
-        {
-            uint32_t o[64];
-            tmem_ld32(tmem_base + TM_O + lane_off, o);
-            tmem_ld32(tmem_base + TM_O + 32 + lane_off, o + 32);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            const float inv = l > 0.f ? 1.f / l : 0.f;
-            if (live) {
-                bf16* orow = p.out + ((int64_t)i * p.B + b) * p.ldo + n * HS;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float v8[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) v8[t] = (acc[8 * c + t] + __uint_as_float(o[8 * c + t])) * inv;
-                    store8(orow + 8 * c, v8);
-                }
-                p.lse[(int64_t)bn * p.Q + i] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
-            }
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TM_COLS);
-    }
-}
-
 // =================================================================================================================
 // Backward.  One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.
 // Per 64-key tile t (TMEM columns in brackets):
@@ -677,7 +373,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 float pt8[8], ds8[8];
                 uint32_t hh[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) hh[t] = p.drop_thresh ? mix32(rk_tile + (uint32_t)(4 * c + t) * 0x85EBCA77u) : 0xffffffffu;
+                for (int t = 0; t < 4; ++t) hh[t] = p.drop_thresh ? attn_mixlite(rk_tile + (uint32_t)(4 * c + t) * 0x85EBCA77u) : 0xffffffffu;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int jj = 8 * c + t;
@@ -779,43 +475,6 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     }
 }
 }  // namespace
-
-int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
-                        int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out, int64_t ldo,
-                        float* lse, int B, int N, int Q, int M, int msl, int same_length, float scale, float drop_p,
-                        uint64_t seed, uint64_t site, cudaStream_t st) {
-    const int K = M + Q;
-    const bool ok = Q >= 32 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)out) & 15) == 0;
-    if (!ok) {
-        tgan_set_error("tgan_relattn_fwd: shape not eligible for the tcgen05 kernel (needs Q >= 32, 16-byte alignment)");
-        return -1;
-    }
-    CUtensorMap tmK, tmV, tmR;
-    // k / v: [K, B, N*64] with row pitch ldkv: dims (d, b, j), box (64, 1, 64)
-    int rc = tc::make_tmap_3d(&tmK, k, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)ldkv, (uint64_t)B * ldkv, HS, 1, BJ);
-    if (rc) return rc;
-    rc = tc::make_tmap_3d(&tmV, v, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)ldkv, (uint64_t)B * ldkv, HS, 1, BJ);
-    if (rc) return rc;
-    rc = tc::make_tmap_2d(&tmR, r, (uint64_t)K, (uint64_t)N * HS, (uint64_t)ldr, BJ, HS);
-    if (rc) return rc;
-    FwdParams p;
-    p.q = (const bf16*)q; p.ldq = ldq; p.out = (bf16*)out; p.ldo = ldo; p.lse = lse; p.u = u; p.vb = vb; p.reset = reset;
-    p.B = B; p.N = N; p.Q = Q; p.M = M; p.K = K; p.msl = msl; p.same_length = same_length;
-    p.scale_log2 = scale * 1.4426950408889634f;
-    p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    p.drop_thresh = drop_p > 0.f ? dropout_thresh16(drop_p) : 0u;
-    p.drop_key = dropout_key(seed, site);
-    static bool attr_set = false;
-    if (!attr_set) {
-        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-        attr_set = true;
-    }
-    dim3 grid(ceil_div(Q, BQ), B * N);
-    relattn_fwd_tc_kernel<<<grid, 160, FWD_SMEM, st>>>(tmK, tmV, tmR, p);
-    TGAN_COUNT_LAUNCH();
-    TGAN_LAUNCH_OK();
-    return 0;
-}
 
 int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, const void* out,

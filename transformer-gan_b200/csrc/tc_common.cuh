@@ -91,6 +91,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 16 consecutive 32-bit columns, register -> TMEM (thread t writes lane base_lane + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors -----------------------------------------------------------------------------------------
@@ -122,6 +153,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, bf16 pairs packed per 32-bit column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // make the mbarrier track completion of all tcgen05 ops issued so far by this thread (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -135,6 +176,11 @@ __device__ __forceinline__ bool elect_one() {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(pred));
     return pred != 0;
+}
+
+// byte offset of the 16-byte chunk `c` (8 bf16) of row `r` inside a K-major SWIZZLE_128B tile with 128-byte rows
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----------------
