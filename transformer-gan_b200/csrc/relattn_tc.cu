@@ -1,18 +1,20 @@
-// tcgen05 relative-position attention for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+// tcgen05 relative-position attention BACKWARD for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+// Reference: autograd of mem_transformer.py:201-244 (+ _rel_shift :133-147, mask :495-547); SURVEY.md section 9.
 //
-// One CTA per (batch b, head n, 128-row query tile).  Five warps:
-//   warps 0..3  "row" warps: thread = query row = TMEM lane.  Online softmax, rel-shift, mask, dropout.
-//   warp  4     control: one thread issues the TMA loads (K / V tiles, R chunks) and every tcgen05.mma.
-// Per 64-key tile t the tensor core produces, into TMEM,
-//     S_ac = (q + u) K_t^T            [128 x 64]
-//     G_c  = (q + v) R_c^T            [128 x 64]   for ONE new 64-wide chunk c of relative positions
-//     O_t  = P_t V_t                  [128 x 64]
-// The relative shift  BD[i, j] = G[i, j + Q - 1 - i]  is a row-dependent column offset.  TMEM rows are thread
-// private (thread = lane), so the shift is done through a thread-private ring of the last three G chunks kept in
-// shared memory as ring[column][row] (bank = row: conflict-free for any per-row offset).  Every G element is
-// computed exactly once: tile t needs chunks t, t+1, t+2 and only chunk t+2 is new.  No [Q, K] score / mask /
-// shifted copy ever exists (reference: mem_transformer.py:133-147, 201-244, 495-547).
-// The running output stays in registers: acc = (acc + O_{t-1}) * exp2(m_{t-1} - m_t).
+// One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.  Twelve warps:
+//   warps 0..7  "row" warps: thread = (query row = TMEM lane, column half h): warp w owns lane quarter w & 3 and the
+//               32-column half w >> 2 of every 64-wide tile, so each query row is served by two threads.
+//   warp  8     one thread issues every tcgen05.mma
+//   warp  9     K / V tile loads (TMA)        warp 10  R chunks for the G product        warp 11  R chunks for dqR
+// Per 64-key tile t (TMEM columns in brackets):
+//     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO' V_t^T
+//   row threads:  P = exp2(S2 - lse2),  dS = P (keep(dP) - delta),  P~ = keep(P)   -> bf16 tiles in shared memory;
+//                 dS is also scattered into a bf16 ring at the INVERSE shift (column p = j + Q-1-i)
+//     dV_t [384] = P~^T dO'    dK_t [320] = dS^T (q+u)     dqK [192] += dS K_t            (after the tiles are written)
+//     dqR [256] += dG_c R_c    dR_c [448] = dG_c^T (q+v)   where dG_c = chunk c of the dS ring (complete after tile c)
+// dO' = dO / (1 - p_drop) is formed once while staging, so neither P~ nor dP needs a per-element dropout scale;
+// the 1/sqrt(d_head) factor of dS is applied when dq / dK / dR / du / dvb leave the CTA.
+// dR chunks are reduced over the batch with red.global.add.v4.f32; du / dvb are the column sums of dqK / dqR.
 #include <cuda_fp16.h>
 
 #include "tc_common.cuh"
@@ -23,47 +25,27 @@ using namespace tc;
 constexpr int HS = TGAN_HS;  // 64
 constexpr int BQ = 128;      // query rows per CTA
 constexpr int BJ = 64;       // keys per tile
-constexpr int KV_STAGES = 3;
 constexpr int RING_COLS = 192;
+constexpr int ROW_WARPS = 8;
+constexpr int NTHREADS = 32 * (ROW_WARPS + 4);
 
-// shared-memory carve-up (bytes, relative to a 1024-aligned base)
-constexpr int OFF_QU = 0;                               // [128][64] bf16, K-major SW128
-constexpr int OFF_QV = OFF_QU + BQ * HS * 2;            // 16 KB
-constexpr int OFF_KV = OFF_QV + BQ * HS * 2;            // KV_STAGES x (K tile 8 KB + V tile 8 KB)
-constexpr int OFF_R = OFF_KV + KV_STAGES * 2 * BJ * HS * 2;
-constexpr int OFF_P = OFF_R + 2 * BJ * HS * 2;          // [128][64] bf16
-constexpr int OFF_RING = OFF_P + BQ * BJ * 2;           // [192][128] fp16 (thread-private G ring)
-constexpr int OFF_BAR = OFF_RING + RING_COLS * BQ * 2;
-constexpr int NUM_BARS = 2 * KV_STAGES + 4 + 4 + 4 + 2;
-constexpr int FWD_SMEM = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
-
-// TMEM columns
-constexpr int TM_S = 0, TM_G = 128, TM_O = 256, TM_COLS = 512;
-
-// =================================================================================================================
-// Backward.  One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.
-// Per 64-key tile t (TMEM columns in brackets):
-//     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO V_t^T
-//   row threads:  P = exp2(S2 - lse2),  dS = P (drop(dP) - delta) scale,  P~ = drop(P)  -> bf16 tiles in smem,
-//                 dS also scattered into a thread-private bf16 ring at the INVERSE shift (column p = j + Q-1-i)
-//     dV_t [384] = P~^T dO     dK_t [320] = dS^T (q+u)     dqK [192] += dS K_t            (after the tiles are written)
-//     dqR [256] += dG_c R_c    dR_c [448] = dG_c^T (q+v)   where dG_c = chunk c of the dS ring (complete after tile c)
-// dR chunks are reduced over the batch with red.global.add.v4.f32; du / dvb are the column sums of dqK / dqR.
-// =================================================================================================================
 constexpr int B_OFF_QU = 0;
 constexpr int B_OFF_QV = B_OFF_QU + 16384;
 constexpr int B_OFF_DO = B_OFF_QV + 16384;
 constexpr int B_OFF_K = B_OFF_DO + 16384;    // 2 stages x 8 KB
 constexpr int B_OFF_V = B_OFF_K + 2 * 8192;  // 1 stage
-constexpr int B_OFF_R = B_OFF_V + 8192;      // 3 stages x 8 KB
-constexpr int B_OFF_PT = B_OFF_R + 3 * 8192; // P~ tile, later the dG tile
+constexpr int B_OFF_RG = B_OFF_V + 8192;     // R chunks for G: 2 stages x 8 KB
+constexpr int B_OFF_RD = B_OFF_RG + 2 * 8192; // R chunk for dqR: 1 stage
+constexpr int B_OFF_PT = B_OFF_RD + 8192;    // P~ tile, later the dG tile
 constexpr int B_OFF_DS = B_OFF_PT + 16384;
 constexpr int B_OFF_GRING = B_OFF_DS + 16384;                 // fp16 [192][128]
 constexpr int B_OFF_DRING = B_OFF_GRING + RING_COLS * BQ * 2; // bf16 [192][128]
 constexpr int B_OFF_BAR = B_OFF_DRING + RING_COLS * BQ * 2;
-constexpr int B_NUM_BARS = 4 + 2 + 6 + 2 + 2 + 2 + 4;
+constexpr int B_NUM_BARS = 24;
 constexpr int BWD_SMEM = B_OFF_BAR + B_NUM_BARS * 8 + 16 + 1024;
+static_assert(BWD_SMEM <= 232448, "shared memory budget");
 constexpr int TB_S = 0, TB_G = 64, TB_DP = 128, TB_DQK = 192, TB_DQR = 256, TB_DK = 320, TB_DV = 384, TB_DR = 448;
+constexpr int TM_COLS = 512;
 
 struct BwdParams {
     const bf16* q; int64_t ldq;
@@ -82,22 +64,28 @@ struct BwdParams {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// the two warps serving one lane quarter (w and w + 4) meet on named barrier 1 + quarter
+__device__ __forceinline__ void pair_sync(int quarter) {
+    asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmR, BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sQu = base + B_OFF_QU, sQv = base + B_OFF_QV, sDO = base + B_OFF_DO, sK = base + B_OFF_K,
-                   sV = base + B_OFF_V, sR = base + B_OFF_R, sPT = base + B_OFF_PT, sDS = base + B_OFF_DS;
+                   sV = base + B_OFF_V, sRG = base + B_OFF_RG, sRD = base + B_OFF_RD, sPT = base + B_OFF_PT,
+                   sDS = base + B_OFF_DS;
     __half* gring = reinterpret_cast<__half*>(gbase + B_OFF_GRING);
     bf16* dring = reinterpret_cast<bf16*>(gbase + B_OFF_DRING);
     const uint32_t bar0 = base + B_OFF_BAR;
     const uint32_t k_full = bar0, k_empty = k_full + 16, v_full = k_empty + 16, v_empty = v_full + 8,
-                   r_full = v_empty + 8, r_empty = r_full + 24, s_full = r_empty + 24, s_empty = s_full + 8,
-                   dp_full = s_empty + 8, dp_empty = dp_full + 8, g_full = dp_empty + 8, g_empty = g_full + 8,
-                   p_full = g_empty + 8, kdone = p_full + 8, dg_full = kdone + 8, rdone = dg_full + 8;
+                   rg_full = v_empty + 8, rg_empty = rg_full + 16, rd_full = rg_empty + 16, rd_empty = rd_full + 8,
+                   s_full = rd_empty + 8, s_empty = s_full + 8, dp_full = s_empty + 8, dp_empty = dp_full + 8,
+                   g_full = dp_empty + 8, g_empty = g_full + 8, p_full = g_empty + 8, kdone = p_full + 8,
+                   dg_full = kdone + 8, rdone = dg_full + 8;
     const uint32_t sTmemPtr = rdone + 8;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
 
@@ -114,20 +102,25 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     const int P0 = p.Q - 1 - (BQ - 1) + BJ * t_lo;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
+            mbar_init(rg_full + 8 * s, 1); mbar_init(rg_empty + 8 * s, 1);
+        }
         mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        for (int s = 0; s < 3; ++s) { mbar_init(r_full + 8 * s, 1); mbar_init(r_empty + 8 * s, 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, 4);
-        mbar_init(dp_full, 1); mbar_init(dp_empty, 4);
-        mbar_init(g_full, 1); mbar_init(g_empty, 4);
-        mbar_init(p_full, 4); mbar_init(kdone, 1); mbar_init(dg_full, 4); mbar_init(rdone, 1);
+        mbar_init(rd_full, 1); mbar_init(rd_empty, 1);
+        mbar_init(s_full, 1); mbar_init(s_empty, ROW_WARPS);
+        mbar_init(dp_full, 1); mbar_init(dp_empty, ROW_WARPS);
+        mbar_init(g_full, 1); mbar_init(g_empty, ROW_WARPS);
+        mbar_init(p_full, ROW_WARPS); mbar_init(kdone, 1); mbar_init(dg_full, ROW_WARPS); mbar_init(rdone, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(sTmemPtr, TM_COLS);
+    if (warp == ROW_WARPS) tmem_alloc(sTmemPtr, TM_COLS);
 
+    // row-thread identity
+    const int quarter = warp & 3, half = (warp >> 2) & 1;
+    const int ii = 32 * quarter + lane;
     float delta = 0.f, lse2 = 0.f;
-    if (warp < 4) {
-        const int ii = threadIdx.x;
+    if (warp < ROW_WARPS) {
         const bool live = ii < rows_here;
         const int64_t row = (int64_t)ii * p.B + b;
         const bf16* qrow = p.q + row * p.ldq + n * HS;
@@ -135,23 +128,35 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const bf16* grow = p.dout + row * p.ldo + n * HS;
 #pragma unroll
         for (int c = 0; c < HS / 8; ++c) {
-            float x[8], o[8], g[8], a[8], bb[8];
-            if (live) { load8(qrow + 8 * c, x); load8(orow + 8 * c, o); load8(grow + 8 * c, g); }
+            float o[8], g[8];
+            if (live) { load8(orow + 8 * c, o); load8(grow + 8 * c, g); }
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                a[t] = live ? x[t] + p.u[n * HS + 8 * c + t] : 0.f;
-                bb[t] = live ? x[t] + p.vb[n * HS + 8 * c + t] : 0.f;
-                g[t] = live ? g[t] : 0.f;
-                delta += live ? g[t] * o[t] : 0.f;
+            for (int t = 0; t < 8; ++t) delta += live ? g[t] * o[t] : 0.f;
+            if ((c >> 2) == half) {  // this thread stages its half of the row
+                float x[8], a[8], bb[8], uu[8], vv[8];
+                if (live) load8(qrow + 8 * c, x);
+                load8(p.u + n * HS + 8 * c, uu);
+                load8(p.vb + n * HS + 8 * c, vv);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    a[t] = live ? x[t] + uu[t] : 0.f;
+                    bb[t] = live ? x[t] + vv[t] : 0.f;
+                    g[t] = live ? g[t] * p.drop_scale : 0.f;
+                }
+                store8(reinterpret_cast<bf16*>(gbase + B_OFF_QU + sw128_off(ii, c)), a);
+                store8(reinterpret_cast<bf16*>(gbase + B_OFF_QV + sw128_off(ii, c)), bb);
+                store8(reinterpret_cast<bf16*>(gbase + B_OFF_DO + sw128_off(ii, c)), g);
             }
-            store8(reinterpret_cast<bf16*>(gbase + B_OFF_QU + sw128_off(ii, c)), a);
-            store8(reinterpret_cast<bf16*>(gbase + B_OFF_QV + sw128_off(ii, c)), bb);
-            store8(reinterpret_cast<bf16*>(gbase + B_OFF_DO + sw128_off(ii, c)), g);
         }
         lse2 = live ? p.lse[(int64_t)bn * p.Q + ii] * 1.4426950408889634f : 0.f;
-        for (int c = 0; c < RING_COLS; ++c) dring[c * BQ + ii] = __float2bfloat16_rn(0.f);
+        // zero the dS ring: 48 KB / 256 threads = 192 contiguous bytes each
+        {
+            uint4* z = reinterpret_cast<uint4*>(gbase + B_OFF_DRING) + threadIdx.x * 12;
+#pragma unroll
+            for (int c = 0; c < 12; ++c) z[c] = make_uint4(0, 0, 0, 0);
+        }
         // keys this (b, n) never attends to get zero gradients
-        for (int j = ii; j < p.K; j += BQ) {
+        for (int j = threadIdx.x; j < p.K; j += 32 * ROW_WARPS) {
             if (j >= t_lo * BJ && j < (t_hi + 1) * BJ) continue;
             uint4 z = make_uint4(0, 0, 0, 0);
             uint4* dkr = reinterpret_cast<uint4*>(p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS);
@@ -166,31 +171,44 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
-    if (warp == 4) {
+    if (warp == ROW_WARPS + 1) {
+        // =========================== K / V producer ===========================
         if (lane == 0) {
-            constexpr uint32_t id_kk = umma_idesc_bf16(128, 64, 0, 0);   // S, G, dP: A, B K-major
-            constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dqK, dqR: A K-major, B MN-major
-            constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);    // dV, dK, dR: A, B MN-major (M = 64)
-            auto issue_k = [&](int tt) {
-                if (tt >= nt) return;
+            for (int tt = 0; tt < nt; ++tt) {
                 const int st = tt & 1;
                 mbar_wait(k_empty + 8 * st, ((tt >> 1) & 1) ^ 1);
                 mbar_expect_tx(k_full + 8 * st, 8192);
                 tma_load_3d(sK + st * 8192, &tmK, k_full + 8 * st, n * HS, b, (t_lo + tt) * BJ);
-            };
-            auto issue_v = [&](int tt) {
-                if (tt >= nt) return;
                 mbar_wait(v_empty, (tt & 1) ^ 1);
                 mbar_expect_tx(v_full, 8192);
                 tma_load_3d(sV, &tmV, v_full, n * HS, b, (t_lo + tt) * BJ);
-            };
-            auto issue_r = [&](int cc) {
-                if (cc >= nc) return;
-                const int st = cc % 3;
-                mbar_wait(r_empty + 8 * st, ((cc / 3) & 1) ^ 1);
-                mbar_expect_tx(r_full + 8 * st, 8192);
-                tma_load_2d(sR + st * 8192, &tmR, r_full + 8 * st, n * HS, P0 + BJ * cc);
-            };
+            }
+        }
+    } else if (warp == ROW_WARPS + 2) {
+        // =========================== R chunks feeding G = (q+v) R^T ===========================
+        if (lane == 0) {
+            for (int cc = 0; cc < nc; ++cc) {
+                const int st = cc & 1;
+                mbar_wait(rg_empty + 8 * st, ((cc >> 1) & 1) ^ 1);
+                mbar_expect_tx(rg_full + 8 * st, 8192);
+                tma_load_2d(sRG + st * 8192, &tmR, rg_full + 8 * st, n * HS, P0 + BJ * cc);
+            }
+        }
+    } else if (warp == ROW_WARPS + 3) {
+        // =========================== R chunks feeding dqR += dG R ===========================
+        if (lane == 0) {
+            for (int cc = 0; cc < nc; ++cc) {
+                mbar_wait(rd_empty, (cc & 1) ^ 1);
+                mbar_expect_tx(rd_full, 8192);
+                tma_load_2d(sRD, &tmR, rd_full, n * HS, P0 + BJ * cc);
+            }
+        }
+    } else if (warp == ROW_WARPS) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            constexpr uint32_t id_kk = umma_idesc_bf16(128, 64, 0, 0);   // S, G, dP: A, B K-major
+            constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dqK, dqR: A K-major, B MN-major
+            constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);    // dV, dK, dR: A, B MN-major (M = 64)
             auto mma_s = [&](int tt) {
                 if (tt >= nt) return;
                 mbar_wait(k_full + 8 * (tt & 1), (tt >> 1) & 1);
@@ -216,20 +234,21 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             };
             auto mma_g = [&](int cc) {
                 if (cc >= nc) return;
-                mbar_wait(r_full + 8 * (cc % 3), (cc / 3) & 1);
+                mbar_wait(rg_full + 8 * (cc & 1), (cc >> 1) & 1);
                 mbar_wait(g_empty, (cc & 1) ^ 1);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_bf16(tmem_base + TB_G, umma_smem_desc(sQv + 32 * k, 16, 1024),
-                              umma_smem_desc(sR + (cc % 3) * 8192 + 32 * k, 16, 1024), id_kk, k != 0);
+                              umma_smem_desc(sRG + (cc & 1) * 8192 + 32 * k, 16, 1024), id_kk, k != 0);
                 umma_commit(g_full);
+                umma_commit(rg_empty + 8 * (cc & 1));
             };
             auto mma_key = [&](int tt) {
                 mbar_wait(p_full, tt & 1);
                 tcgen05_fence_after();
 #pragma unroll
-                for (int k = 0; k < 8; ++k)  // dV = P~^T dO   (contraction over the 128 query rows)
+                for (int k = 0; k < 8; ++k)  // dV = P~^T dO'   (contraction over the 128 query rows)
                     umma_bf16(tmem_base + TB_DV, umma_smem_desc(sPT + 2048 * k, 8192, 1024),
                               umma_smem_desc(sDO + 2048 * k, 8192, 1024), id_nn, k != 0);
 #pragma unroll
@@ -245,62 +264,59 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             };
             auto mma_rel = [&](int cc) {
                 mbar_wait(dg_full, cc & 1);
+                mbar_wait(rd_full, cc & 1);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // dqR += dG_c R_c
                     umma_bf16(tmem_base + TB_DQR, umma_smem_desc(sPT + 32 * k, 16, 1024),
-                              umma_smem_desc(sR + (cc % 3) * 8192 + 2048 * k, 8192, 1024), id_kn, (cc | k) != 0);
+                              umma_smem_desc(sRD + 2048 * k, 8192, 1024), id_kn, (cc | k) != 0);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)  // dR_c = dG_c^T (q + v)
                     umma_bf16(tmem_base + TB_DR, umma_smem_desc(sPT + 2048 * k, 8192, 1024),
                               umma_smem_desc(sQv + 2048 * k, 8192, 1024), id_nn, k != 0);
                 umma_commit(rdone);
-                umma_commit(r_empty + 8 * (cc % 3));
+                umma_commit(rd_empty);
             };
-            issue_k(0); issue_v(0); issue_r(0); issue_r(1); issue_r(2); issue_k(1);
             mma_s(0); mma_dp(0); mma_g(0); mma_g(1); mma_g(2);
-            issue_v(1);
             for (int tt = 0; tt < nt; ++tt) {
+                mma_g(tt + 3);       // needs only the previous chunk pulled: ready long before tile tt+1 starts
                 mma_key(tt);
                 mma_s(tt + 1);
                 mma_dp(tt + 1);
-                issue_v(tt + 2);
                 mma_rel(tt);
-                issue_r(tt + 3);
-                mma_g(tt + 3);
-                issue_k(tt + 2);
             }
             for (int cc = nt; cc < nc; ++cc) mma_rel(cc);
         }
     } else {
-        const int ii = threadIdx.x;
+        // =========================== row warps ===========================
         const bool live = ii < rows_here;
-        const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
+        const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
+        const int hc = 32 * half;  // first column of this thread's half
         const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + ii));
+        const uint32_t th_hi = p.drop_thresh << 16;
         int consumed = 0;
-        // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * warp + lane
+        // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * quarter + lane
         auto flush_dr = [&](int cc) {
             mbar_wait(rdone, cc & 1);
             tcgen05_fence_after();
-            uint32_t v[64];
-            tmem_ld32(tmem_base + TB_DR + lane_off, v);
-            tmem_ld32(tmem_base + TB_DR + 32 + lane_off, v + 32);
+            uint32_t v[32];
+            tmem_ld32(tmem_base + TB_DR + hc + lane_off, v);
             tmem_ld_wait();
             tcgen05_fence_before();
-            const int pr = P0 + BJ * cc + 16 * warp + lane;
+            const int pr = P0 + BJ * cc + 16 * quarter + lane;
             if (lane < 16 && pr >= 0 && pr < p.K) {
-                float* dst = p.dr + (int64_t)pr * p.lddr + n * HS;
+                float* dst = p.dr + (int64_t)pr * p.lddr + n * HS + hc;
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    red_add_v4(dst + 4 * c, __uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
-                               __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+                for (int c = 0; c < 8; ++c)
+                    red_add_v4(dst + 4 * c, __uint_as_float(v[4 * c]) * p.scale, __uint_as_float(v[4 * c + 1]) * p.scale,
+                               __uint_as_float(v[4 * c + 2]) * p.scale, __uint_as_float(v[4 * c + 3]) * p.scale);
             }
         };
-        // chunk cc of the dS ring -> bf16 K-major tile (the dG A operand), then clear the ring third for reuse
+        // this thread's half of chunk cc of the dS ring -> bf16 K-major tile (the dG A operand); clears it for reuse
         auto extract_dg = [&](int cc) {
-            bf16* src = dring + (cc % 3) * (BJ * BQ) + ii;
+            bf16* src = dring + ((cc % 3) * BJ + hc) * BQ + ii;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 uint4 pk;
                 __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(&pk);
 #pragma unroll
@@ -308,117 +324,138 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     h[t] = src[(8 * c + t) * BQ];
                     src[(8 * c + t) * BQ] = __float2bfloat16_rn(0.f);
                 }
-                *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, c)) = pk;
+                *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, 4 * half + c)) = pk;
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(dg_full);
         };
+#pragma unroll 1
         for (int tt = 0; tt < nt; ++tt) {
+            // 1. new G chunks (tile tt reads chunks tt .. tt+2): this thread converts its 32-column half
             while (consumed <= tt + 2 && consumed < nc) {
                 mbar_wait(g_full, consumed & 1);
                 tcgen05_fence_after();
-                uint32_t g[64];
-                tmem_ld32(tmem_base + TB_G + lane_off, g);
-                tmem_ld32(tmem_base + TB_G + 32 + lane_off, g + 32);
+                uint32_t g[32];
+                tmem_ld32(tmem_base + TB_G + hc + lane_off, g);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(g_empty);
-                __half* dst = gring + (consumed % 3) * (BJ * BQ) + ii;
+                __half* dst = gring + ((consumed % 3) * BJ + hc) * BQ + ii;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
+                for (int c = 0; c < 32; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
                 ++consumed;
             }
+            // both halves of the new chunk are in the ring; the partner has also finished extracting the dS-ring
+            // chunk of the previous tile, so this tile's scatter may reuse that ring third
+            pair_sync(quarter);
             const int j0 = (t_lo + tt) * BJ;
-            int lim_hi = live ? (ii + p.M - j0) : -1;
-            int lim_lo = 0;
-            if (p.same_length) lim_lo = max(lim_lo, ii - p.msl + 1 - j0);
-            if (reset_b) lim_lo = max(lim_lo, p.M - j0);
-            lim_hi = min(lim_hi, p.K - 1 - j0);
-            const int start = (BQ - 1 - ii + BJ * tt) % RING_COLS;
-            float pr[64];
+            const int start = (BQ - 1 - ii + BJ * tt + hc) % RING_COLS;  // ring column of this thread's jj = 0
+            const int wrap = RING_COLS - start;                         // first jj that wraps around
+            const __half* g0 = gring + start * BQ + ii;
+            const __half* g1 = g0 - RING_COLS * BQ;
+            // 2. P = exp2((S + G) * scale * log2e - lse2)
+            float pr[32];
             {
                 mbar_wait(s_full, tt & 1);
                 tcgen05_fence_after();
-                uint32_t sr[64];
-                tmem_ld32(tmem_base + TB_S + lane_off, sr);
-                tmem_ld32(tmem_base + TB_S + 32 + lane_off, sr + 32);
+                uint32_t sr[32];
+                tmem_ld32(tmem_base + TB_S + hc + lane_off, sr);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty);
+                const bool interior = rows_here == BQ && j0 + BJ - 1 <= p.M && (!p.same_length || BQ - p.msl - j0 <= 0) &&
+                                      (!reset_b || p.M <= j0);
+                if (interior) {
 #pragma unroll
-                for (int jj = 0; jj < 64; ++jj) {
-                    int col = start + jj;
-                    col -= (col >= RING_COLS) ? RING_COLS : 0;
-                    float v = (__uint_as_float(sr[jj]) + __half2float(gring[col * BQ + ii])) * p.scale_log2;
-                    pr[jj] = (jj >= lim_lo && jj <= lim_hi) ? fast_exp2(v - lse2) : 0.f;
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const float gv = __half2float((jj < wrap ? g0 : g1)[jj * BQ]);
+                        pr[jj] = fast_exp2(fmaf(__uint_as_float(sr[jj]) + gv, p.scale_log2, -lse2));
+                    }
+                } else {
+                    int lim_hi = live ? (ii + p.M - j0 - hc) : -1;
+                    int lim_lo = 0;
+                    if (p.same_length) lim_lo = max(lim_lo, ii - p.msl + 1 - j0 - hc);
+                    if (reset_b) lim_lo = max(lim_lo, p.M - j0 - hc);
+                    lim_hi = min(lim_hi, p.K - 1 - j0 - hc);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const float gv = __half2float((jj < wrap ? g0 : g1)[jj * BQ]);
+                        const float e = fast_exp2(fmaf(__uint_as_float(sr[jj]) + gv, p.scale_log2, -lse2));
+                        pr[jj] = (jj >= lim_lo && jj <= lim_hi) ? e : 0.f;
+                    }
                 }
             }
+            // 3. dP
             mbar_wait(dp_full, tt & 1);
             tcgen05_fence_after();
-            uint32_t dpr[64];
-            tmem_ld32(tmem_base + TB_DP + lane_off, dpr);
-            tmem_ld32(tmem_base + TB_DP + 32 + lane_off, dpr + 32);
+            uint32_t dpr[32];
+            tmem_ld32(tmem_base + TB_DP + hc + lane_off, dpr);
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dp_empty);
             // the P~ / dG buffer and the dR accumulator are free once the previous chunk's MMAs have been drained
             if (tt > 0) flush_dr(tt - 1);
-            const uint32_t rk_tile = rowkey + (uint32_t)(j0 >> 1) * 0x85EBCA77u;
+            // 4. P~ = keep(P), dS = P (keep(dP) - delta): bf16 tiles + inverse-shift scatter into the dS ring
+            const uint32_t rk_tile = rowkey + (uint32_t)((j0 + hc) >> 1) * 0x85EBCA77u;
+            bf16* d0 = dring + start * BQ + ii;
+            bf16* d1 = d0 - RING_COLS * BQ;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float pt8[8], ds8[8];
-                uint32_t hh[4];
+            for (int c = 0; c < 4; ++c) {
+                uint32_t ptw[4], dsw[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) hh[t] = p.drop_thresh ? attn_mixlite(rk_tile + (uint32_t)(4 * c + t) * 0x85EBCA77u) : 0xffffffffu;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int jj = 8 * c + t;
-                    float pj = pr[jj], dp = __uint_as_float(dpr[jj]);
-                    const bool keep = ((t & 1) ? (hh[t >> 1] >> 16) : (hh[t >> 1] & 0xffffu)) >= p.drop_thresh;
-                    dp = keep ? dp * p.drop_scale : 0.f;
-                    pt8[t] = keep ? pj * p.drop_scale : 0.f;
-                    ds8[t] = pj * (dp - delta) * p.scale;
-                    int col = start + jj;
-                    col -= (col >= RING_COLS) ? RING_COLS : 0;
-                    dring[col * BQ + ii] = __float2bfloat16_rn(ds8[t]);
+                for (int t = 0; t < 4; ++t) {
+                    const int jj = 8 * c + 2 * t;
+                    float p0 = pr[jj], p1 = pr[jj + 1];
+                    float dp0 = __uint_as_float(dpr[jj]), dp1 = __uint_as_float(dpr[jj + 1]);
+                    float pt0 = p0, pt1 = p1;
+                    if (p.drop_thresh) {
+                        const uint32_t h = attn_mixlite(rk_tile + (uint32_t)(4 * c + t) * 0x85EBCA77u);
+                        const bool k0 = (h << 16) >= th_hi, k1 = h >= th_hi;
+                        pt0 = k0 ? p0 : 0.f; pt1 = k1 ? p1 : 0.f;
+                        dp0 = k0 ? dp0 : 0.f; dp1 = k1 ? dp1 : 0.f;
+                    }
+                    __nv_bfloat162 a = __floats2bfloat162_rn(pt0, pt1);
+                    __nv_bfloat162 d = __floats2bfloat162_rn(p0 * (dp0 - delta), p1 * (dp1 - delta));
+                    ptw[t] = *reinterpret_cast<uint32_t*>(&a);
+                    dsw[t] = *reinterpret_cast<uint32_t*>(&d);
+                    (jj < wrap ? d0 : d1)[jj * BQ] = d.x;
+                    (jj + 1 < wrap ? d0 : d1)[(jj + 1) * BQ] = d.y;
                 }
-                store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + sw128_off(ii, c)), pt8);
-                store8(reinterpret_cast<bf16*>(gbase + B_OFF_DS + sw128_off(ii, c)), ds8);
+                *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, 4 * half + c)) = make_uint4(ptw[0], ptw[1], ptw[2], ptw[3]);
+                *reinterpret_cast<uint4*>(gbase + B_OFF_DS + sw128_off(ii, 4 * half + c)) = make_uint4(dsw[0], dsw[1], dsw[2], dsw[3]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            // key-side results of this tile (M = 64 layout: row r = 16 * warp + lane, lanes 0..15)
+            // 5. key-side results of this tile (M = 64 layout: row r = 16 * quarter + lane, lanes 0..15)
             mbar_wait(kdone, tt & 1);
             tcgen05_fence_after();
             {
-                uint32_t a[64];
-                const int j = j0 + 16 * warp + lane;
+                uint32_t a[32];
+                const int j = j0 + 16 * quarter + lane;
                 const bool wr = lane < 16 && j < p.K;
-                tmem_ld32(tmem_base + TB_DK + lane_off, a);
-                tmem_ld32(tmem_base + TB_DK + 32 + lane_off, a + 32);
+                tmem_ld32(tmem_base + TB_DK + hc + lane_off, a);
                 tmem_ld_wait();
                 if (wr) {
-                    bf16* dst = p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS;
+                    bf16* dst = p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < 4; ++c) {
                         float f[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
+                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * p.scale;
                         store8(dst + 8 * c, f);
                     }
                 }
-                tmem_ld32(tmem_base + TB_DV + lane_off, a);
-                tmem_ld32(tmem_base + TB_DV + 32 + lane_off, a + 32);
+                tmem_ld32(tmem_base + TB_DV + hc + lane_off, a);
                 tmem_ld_wait();
                 if (wr) {
-                    bf16* dst = p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS;
+                    bf16* dst = p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < 4; ++c) {
                         float f[8];
 #pragma unroll
                         for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
@@ -427,49 +464,46 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 }
                 tcgen05_fence_before();
             }
-            extract_dg(tt);  // chunk tt is complete: tiles > tt only touch chunks > tt
+            // 6. chunk tt of the dS ring is complete once BOTH halves have scattered this tile
+            pair_sync(quarter);
+            extract_dg(tt);
         }
         for (int cc = nt; cc < nc; ++cc) {
             flush_dr(cc - 1);
             extract_dg(cc);
         }
         flush_dr(nc - 1);
-        // dq = dqK + dqR (ds already carries the 1/sqrt(d) scale); du / dvb = column sums over the query rows
+        // dq = (dqK + dqR) / sqrt(d); du / dvb = column sums over the query rows
         {
-            uint32_t a[64], c2[64];
-            tmem_ld32(tmem_base + TB_DQK + lane_off, a);
-            tmem_ld32(tmem_base + TB_DQK + 32 + lane_off, a + 32);
-            tmem_ld32(tmem_base + TB_DQR + lane_off, c2);
-            tmem_ld32(tmem_base + TB_DQR + 32 + lane_off, c2 + 32);
+            uint32_t a[32], c2[32];
+            tmem_ld32(tmem_base + TB_DQK + hc + lane_off, a);
+            tmem_ld32(tmem_base + TB_DQR + hc + lane_off, c2);
             tmem_ld_wait();
             tcgen05_fence_before();
             if (live) {
-                bf16* dst = p.dq + ((int64_t)ii * p.B + b) * p.ldq + n * HS;
+                bf16* dst = p.dq + ((int64_t)ii * p.B + b) * p.ldq + n * HS + hc;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     float f[8];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) + __uint_as_float(c2[8 * c + t]);
+                    for (int t = 0; t < 8; ++t) f[t] = (__uint_as_float(a[8 * c + t]) + __uint_as_float(c2[8 * c + t])) * p.scale;
                     store8(dst + 8 * c, f);
                 }
             }
-            float su0 = 0.f, su1 = 0.f, sv0 = 0.f, sv1 = 0.f;
+            float su = 0.f, sv = 0.f;
 #pragma unroll
-            for (int d = 0; d < 64; ++d) {
-                float tk = warp_sum(live ? __uint_as_float(a[d]) : 0.f);
-                float tr = warp_sum(live ? __uint_as_float(c2[d]) : 0.f);
-                if (d == lane) { su0 = tk; sv0 = tr; }
-                if (d == lane + 32) { su1 = tk; sv1 = tr; }
+            for (int d = 0; d < 32; ++d) {
+                const float tk = warp_sum(live ? __uint_as_float(a[d]) : 0.f);
+                const float tr = warp_sum(live ? __uint_as_float(c2[d]) : 0.f);
+                if (d == lane) { su = tk; sv = tr; }
             }
-            atomicAdd(&p.du[n * HS + lane], su0);
-            atomicAdd(&p.du[n * HS + lane + 32], su1);
-            atomicAdd(&p.dvb[n * HS + lane], sv0);
-            atomicAdd(&p.dvb[n * HS + lane + 32], sv1);
+            atomicAdd(&p.du[n * HS + hc + lane], su * p.scale);
+            atomicAdd(&p.dvb[n * HS + hc + lane], sv * p.scale);
         }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == ROW_WARPS) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TM_COLS);
     }
@@ -485,7 +519,7 @@ int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v
     (void)delta;
     const int K = M + Q;
     const uintptr_t al = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)out | (uintptr_t)dout |
-                         (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dr;
+                         (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)dr | (uintptr_t)u | (uintptr_t)vb;
     if (!(Q >= 32 && Q <= BQ && (al & 15) == 0 && lddr % 4 == 0)) {
         tgan_set_error("tgan_relattn_bwd: shape not eligible for the tcgen05 kernel (needs 32 <= Q <= 128, 16-byte alignment)");
         return -1;
@@ -512,7 +546,7 @@ int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v
         attr_set = true;
     }
     TGAN_CUDA_OK(cudaMemset2DAsync(dr, lddr * sizeof(float), 0, (size_t)N * HS * sizeof(float), K, st));
-    relattn_bwd_tc_kernel<<<B * N, 160, BWD_SMEM, st>>>(tmK, tmV, tmR, p);
+    relattn_bwd_tc_kernel<<<B * N, NTHREADS, BWD_SMEM, st>>>(tmK, tmV, tmR, p);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
