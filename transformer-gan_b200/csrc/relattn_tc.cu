@@ -9,9 +9,13 @@
 // Per 64-key tile t (TMEM columns in brackets):
 //     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO' V_t^T
 //   row threads:  P = exp2(S2 - lse2),  dS = P (keep(dP) - delta),  P~ = keep(P)   -> bf16 tiles in shared memory;
-//                 dS is also scattered into a bf16 ring at the INVERSE shift (column p = j + Q-1-i)
+//                 dS is also scattered into a bf16 ring at the INVERSE shift (column p = j + Q-1-i).  The ring is laid
+//                 out as un-swizzled 8 x 16-byte core matrices ([i / 8][p][i % 8]), so a finished 64-position chunk IS
+//                 a valid tcgen05 operand both as dG (MN-major, M = i) and as dG^T (K-major, M = p): no extraction pass
 //     dV_t [384] = P~^T dO'    dK_t [320] = dS^T (q+u)     dqK [192] += dS K_t            (after the tiles are written)
 //     dqR [256] += dG_c R_c    dR_c [448] = dG_c^T (q+v)   where dG_c = chunk c of the dS ring (complete after tile c)
+// The key-side results of tile t and the dR chunk t are drained one tile later (just before tile t+1 publishes its
+// own tiles), so the row warps never sit idle behind the dV / dK / dqK / dqR / dR MMAs.
 // dO' = dO / (1 - p_drop) is formed once while staging, so neither P~ nor dP needs a per-element dropout scale;
 // the 1/sqrt(d_head) factor of dS is applied when dq / dK / dR / du / dvb leave the CTA.
 // dR chunks are reduced over the batch with red.global.add.v4.f32; du / dvb are the column sums of dqK / dqR.
@@ -36,11 +40,13 @@ constexpr int B_OFF_K = B_OFF_DO + 16384;    // 2 stages x 8 KB
 constexpr int B_OFF_V = B_OFF_K + 2 * 8192;  // 1 stage
 constexpr int B_OFF_RG = B_OFF_V + 8192;     // R chunks for G: 2 stages x 8 KB
 constexpr int B_OFF_RD = B_OFF_RG + 2 * 8192; // R chunk for dqR: 1 stage
-constexpr int B_OFF_PT = B_OFF_RD + 8192;    // P~ tile, later the dG tile
+constexpr int B_OFF_PT = B_OFF_RD + 8192;    // P~ tile
 constexpr int B_OFF_DS = B_OFF_PT + 16384;
 constexpr int B_OFF_GRING = B_OFF_DS + 16384;                 // fp16 [192][128]
-constexpr int B_OFF_DRING = B_OFF_GRING + RING_COLS * BQ * 2; // bf16 [192][128]
-constexpr int B_OFF_BAR = B_OFF_DRING + RING_COLS * BQ * 2;
+constexpr int B_OFF_DRING = B_OFF_GRING + RING_COLS * BQ * 2; // bf16 [16 row groups][192 positions][8 rows]
+constexpr int DR_GROUP = RING_COLS * 16 + 32;                 // byte stride between 8-row groups (+32: bank spread)
+constexpr int DRING_BYTES = 16 * DR_GROUP;
+constexpr int B_OFF_BAR = B_OFF_DRING + DRING_BYTES;
 constexpr int B_NUM_BARS = 24;
 constexpr int BWD_SMEM = B_OFF_BAR + B_NUM_BARS * 8 + 16 + 1024;
 static_assert(BWD_SMEM <= 232448, "shared memory budget");
@@ -79,13 +85,13 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                    sV = base + B_OFF_V, sRG = base + B_OFF_RG, sRD = base + B_OFF_RD, sPT = base + B_OFF_PT,
                    sDS = base + B_OFF_DS;
     __half* gring = reinterpret_cast<__half*>(gbase + B_OFF_GRING);
-    bf16* dring = reinterpret_cast<bf16*>(gbase + B_OFF_DRING);
+    const uint32_t sDR = base + B_OFF_DRING;
     const uint32_t bar0 = base + B_OFF_BAR;
     const uint32_t k_full = bar0, k_empty = k_full + 16, v_full = k_empty + 16, v_empty = v_full + 8,
                    rg_full = v_empty + 8, rg_empty = rg_full + 16, rd_full = rg_empty + 16, rd_empty = rd_full + 8,
                    s_full = rd_empty + 8, s_empty = s_full + 8, dp_full = s_empty + 8, dp_empty = dp_full + 8,
                    g_full = dp_empty + 8, g_empty = g_full + 8, p_full = g_empty + 8, kdone = p_full + 8,
-                   dg_full = kdone + 8, rdone = dg_full + 8;
+                   dr_empty = kdone + 8, rdone = dr_empty + 8;
     const uint32_t sTmemPtr = rdone + 8;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
 
@@ -111,7 +117,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         mbar_init(s_full, 1); mbar_init(s_empty, ROW_WARPS);
         mbar_init(dp_full, 1); mbar_init(dp_empty, ROW_WARPS);
         mbar_init(g_full, 1); mbar_init(g_empty, ROW_WARPS);
-        mbar_init(p_full, ROW_WARPS); mbar_init(kdone, 1); mbar_init(dg_full, ROW_WARPS); mbar_init(rdone, 1);
+        mbar_init(p_full, ROW_WARPS); mbar_init(kdone, 1); mbar_init(dr_empty, ROW_WARPS); mbar_init(rdone, 1);
         fence_barrier_init();
     }
     if (warp == ROW_WARPS) tmem_alloc(sTmemPtr, TM_COLS);
@@ -149,12 +155,9 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             }
         }
         lse2 = live ? p.lse[(int64_t)bn * p.Q + ii] * 1.4426950408889634f : 0.f;
-        // zero the dS ring: 48 KB / 256 threads = 192 contiguous bytes each
-        {
-            uint4* z = reinterpret_cast<uint4*>(gbase + B_OFF_DRING) + threadIdx.x * 12;
-#pragma unroll
-            for (int c = 0; c < 12; ++c) z[c] = make_uint4(0, 0, 0, 0);
-        }
+        // zero the dS ring
+        for (int o = threadIdx.x * 16; o < DRING_BYTES; o += 32 * ROW_WARPS * 16)
+            *reinterpret_cast<uint4*>(gbase + B_OFF_DRING + o) = make_uint4(0, 0, 0, 0);
         // keys this (b, n) never attends to get zero gradients
         for (int j = threadIdx.x; j < p.K; j += 32 * ROW_WARPS) {
             if (j >= t_lo * BJ && j < (t_hi + 1) * BJ) continue;
@@ -208,7 +211,9 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         if (lane == 0) {
             constexpr uint32_t id_kk = umma_idesc_bf16(128, 64, 0, 0);   // S, G, dP: A, B K-major
             constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dqK, dqR: A K-major, B MN-major
-            constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);    // dV, dK, dR: A, B MN-major (M = 64)
+            constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);    // dV, dK: A, B MN-major (M = 64)
+            constexpr uint32_t id_nn128 = umma_idesc_bf16(128, 64, 1, 1); // dqR: A (ring chunk), B MN-major
+            constexpr uint32_t id_kn64 = umma_idesc_bf16(64, 64, 0, 1);   // dR: A (ring chunk) K-major, B MN-major
             auto mma_s = [&](int tt) {
                 if (tt >= nt) return;
                 mbar_wait(k_full + 8 * (tt & 1), (tt >> 1) & 1);
@@ -263,26 +268,27 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 umma_commit(k_empty + 8 * (tt & 1));
             };
             auto mma_rel = [&](int cc) {
-                mbar_wait(dg_full, cc & 1);
                 mbar_wait(rd_full, cc & 1);
+                if (cc > 0) mbar_wait(dr_empty, (cc - 1) & 1);  // the row warps have drained dR of chunk cc-1
                 tcgen05_fence_after();
+                const uint32_t cb = sDR + (cc % 3) * (BJ * 16);  // chunk cc = ring positions 64*(cc%3) .. +63
 #pragma unroll
-                for (int k = 0; k < 4; ++k)  // dqR += dG_c R_c
-                    umma_bf16(tmem_base + TB_DQR, umma_smem_desc(sPT + 32 * k, 16, 1024),
-                              umma_smem_desc(sRD + 2048 * k, 8192, 1024), id_kn, (cc | k) != 0);
+                for (int k = 0; k < 4; ++k)  // dqR += dG_c R_c   (A = dG: M = i, MN-major, un-swizzled ring chunk)
+                    umma_bf16(tmem_base + TB_DQR, umma_smem_desc_noswz(cb + 256 * k, 128, DR_GROUP),
+                              umma_smem_desc(sRD + 2048 * k, 8192, 1024), id_nn128, (cc | k) != 0);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)  // dR_c = dG_c^T (q + v)
-                    umma_bf16(tmem_base + TB_DR, umma_smem_desc(sPT + 2048 * k, 8192, 1024),
-                              umma_smem_desc(sQv + 2048 * k, 8192, 1024), id_nn, k != 0);
+                for (int k = 0; k < 8; ++k)  // dR_c = dG_c^T (q + v)   (A = dG^T: M = p, K-major, same chunk)
+                    umma_bf16(tmem_base + TB_DR, umma_smem_desc_noswz(cb + 2 * k * DR_GROUP, DR_GROUP, 128),
+                              umma_smem_desc(sQv + 2048 * k, 8192, 1024), id_kn64, k != 0);
                 umma_commit(rdone);
                 umma_commit(rd_empty);
             };
             mma_s(0); mma_dp(0); mma_g(0); mma_g(1); mma_g(2);
             for (int tt = 0; tt < nt; ++tt) {
-                mma_g(tt + 3);       // needs only the previous chunk pulled: ready long before tile tt+1 starts
-                mma_key(tt);
-                mma_s(tt + 1);
+                mma_g(tt + 3);       // needs only the previous chunk pulled
+                mma_s(tt + 1);       // issued BEFORE the long key / rel MMAs of tile tt so the next tile never waits
                 mma_dp(tt + 1);
+                mma_key(tt);
                 mma_rel(tt);
             }
             for (int cc = nt; cc < nc; ++cc) mma_rel(cc);
@@ -295,6 +301,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + ii));
         const uint32_t th_hi = p.drop_thresh << 16;
         int consumed = 0;
+        uint8_t* drow = gbase + B_OFF_DRING + (ii >> 3) * DR_GROUP + (ii & 7) * 2;  // ring entry (p, ii) at drow + 16 p
         // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * quarter + lane
         auto flush_dr = [&](int cc) {
             mbar_wait(rdone, cc & 1);
@@ -303,6 +310,8 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             tmem_ld32(tmem_base + TB_DR + hc + lane_off, v);
             tmem_ld_wait();
             tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dr_empty);
             const int pr = P0 + BJ * cc + 16 * quarter + lane;
             if (lane < 16 && pr >= 0 && pr < p.K) {
                 float* dst = p.dr + (int64_t)pr * p.lddr + n * HS + hc;
@@ -312,27 +321,43 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                                __uint_as_float(v[4 * c + 2]) * p.scale, __uint_as_float(v[4 * c + 3]) * p.scale);
             }
         };
-        // this thread's half of chunk cc of the dS ring -> bf16 K-major tile (the dG A operand); clears it for reuse
-        auto extract_dg = [&](int cc) {
-            bf16* src = dring + ((cc % 3) * BJ + hc) * BQ + ii;
+        // key-side results of tile tk (M = 64 layout: row r = 16 * quarter + lane, lanes 0..15)
+        auto flush_keys = [&](int tk) {
+            mbar_wait(kdone, tk & 1);
+            tcgen05_fence_after();
+            uint32_t a[32];
+            const int j = (t_lo + tk) * BJ + 16 * quarter + lane;
+            const bool wr = lane < 16 && j < p.K;
+            tmem_ld32(tmem_base + TB_DK + hc + lane_off, a);
+            tmem_ld_wait();
+            if (wr) {
+                bf16* dst = p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 pk;
-                __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(&pk);
+                for (int c = 0; c < 4; ++c) {
+                    float f[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    h[t] = src[(8 * c + t) * BQ];
-                    src[(8 * c + t) * BQ] = __float2bfloat16_rn(0.f);
+                    for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * p.scale;
+                    store8(dst + 8 * c, f);
                 }
-                *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, 4 * half + c)) = pk;
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dg_full);
+            tmem_ld32(tmem_base + TB_DV + hc + lane_off, a);
+            tmem_ld_wait();
+            if (wr) {
+                bf16* dst = p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float f[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
+                    store8(dst + 8 * c, f);
+                }
+            }
+            tcgen05_fence_before();
         };
 #pragma unroll 1
         for (int tt = 0; tt < nt; ++tt) {
-            // 1. new G chunks (tile tt reads chunks tt .. tt+2): this thread converts its 32-column half
+            // 1. new G chunks (tile tt reads chunks tt .. tt+2): this thread converts its 32-column half.  The ring third
+            //    being overwritten was last read in tile tt-1, which both threads of the row finished before pair sync B.
             while (consumed <= tt + 2 && consumed < nc) {
                 mbar_wait(g_full, consumed & 1);
                 tcgen05_fence_after();
@@ -347,9 +372,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 for (int c = 0; c < 32; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
                 ++consumed;
             }
-            // both halves of the new chunk are in the ring; the partner has also finished extracting the dS-ring
-            // chunk of the previous tile, so this tile's scatter may reuse that ring third
-            pair_sync(quarter);
+            pair_sync(quarter);  // A: both halves of the new chunk are in the ring
             const int j0 = (t_lo + tt) * BJ;
             const int start = (BQ - 1 - ii + BJ * tt + hc) % RING_COLS;  // ring column of this thread's jj = 0
             const int wrap = RING_COLS - start;                         // first jj that wraps around
@@ -388,6 +411,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     }
                 }
             }
+            pair_sync(quarter);  // B: both threads of the row are done reading the G ring for this tile
             // 3. dP
             mbar_wait(dp_full, tt & 1);
             tcgen05_fence_after();
@@ -397,82 +421,64 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dp_empty);
-            // the P~ / dG buffer and the dR accumulator are free once the previous chunk's MMAs have been drained
-            if (tt > 0) flush_dr(tt - 1);
-            // 4. P~ = keep(P), dS = P (keep(dP) - delta): bf16 tiles + inverse-shift scatter into the dS ring
-            const uint32_t rk_tile = rowkey + (uint32_t)((j0 + hc) >> 1) * 0x85EBCA77u;
-            bf16* d0 = dring + start * BQ + ii;
-            bf16* d1 = d0 - RING_COLS * BQ;
+            // 4. P~ = keep(P), dS = P (keep(dP) - delta), packed to bf16 pairs in registers
+            uint32_t ptw[16], dsw[16];
+            {
+                const uint32_t rk_tile = rowkey + (uint32_t)((j0 + hc) >> 1) * 0x85EBCA77u;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t ptw[4], dsw[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int jj = 8 * c + 2 * t;
-                    float p0 = pr[jj], p1 = pr[jj + 1];
-                    float dp0 = __uint_as_float(dpr[jj]), dp1 = __uint_as_float(dpr[jj + 1]);
+                for (int c = 0; c < 16; ++c) {
+                    float p0 = pr[2 * c], p1 = pr[2 * c + 1];
+                    float dp0 = __uint_as_float(dpr[2 * c]), dp1 = __uint_as_float(dpr[2 * c + 1]);
                     float pt0 = p0, pt1 = p1;
                     if (p.drop_thresh) {
-                        const uint32_t h = attn_mixlite(rk_tile + (uint32_t)(4 * c + t) * 0x85EBCA77u);
+                        const uint32_t h = attn_mixlite(rk_tile + (uint32_t)c * 0x85EBCA77u);
                         const bool k0 = (h << 16) >= th_hi, k1 = h >= th_hi;
                         pt0 = k0 ? p0 : 0.f; pt1 = k1 ? p1 : 0.f;
                         dp0 = k0 ? dp0 : 0.f; dp1 = k1 ? dp1 : 0.f;
                     }
                     __nv_bfloat162 a = __floats2bfloat162_rn(pt0, pt1);
                     __nv_bfloat162 d = __floats2bfloat162_rn(p0 * (dp0 - delta), p1 * (dp1 - delta));
-                    ptw[t] = *reinterpret_cast<uint32_t*>(&a);
-                    dsw[t] = *reinterpret_cast<uint32_t*>(&d);
-                    (jj < wrap ? d0 : d1)[jj * BQ] = d.x;
-                    (jj + 1 < wrap ? d0 : d1)[(jj + 1) * BQ] = d.y;
+                    ptw[c] = *reinterpret_cast<uint32_t*>(&a);
+                    dsw[c] = *reinterpret_cast<uint32_t*>(&d);
                 }
-                *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, 4 * half + c)) = make_uint4(ptw[0], ptw[1], ptw[2], ptw[3]);
-                *reinterpret_cast<uint4*>(gbase + B_OFF_DS + sw128_off(ii, 4 * half + c)) = make_uint4(dsw[0], dsw[1], dsw[2], dsw[3]);
+            }
+            // 5. drain the previous tile: its dK / dV (frees the P~ / dS buffers) and its dR chunk (frees the ring
+            //    third that this tile's scatter is about to reuse).  Those MMAs ran while this tile was being computed.
+            if (tt > 0) {
+                flush_keys(tt - 1);
+                flush_dr(tt - 1);
+            }
+            if (tt + 2 >= nt) {
+                // chunk tt+2 is one of the two tail chunks whose upper positions are never written: clear this thread's
+                // half of the ring third before anyone scatters into it
+                uint8_t* z = drow + (((tt + 2) % 3) * BJ + hc) * 16;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) *reinterpret_cast<uint16_t*>(z + 16 * c) = 0;
+                pair_sync(quarter);
+            }
+            // 6. publish: P~ and dS tiles (swizzled K-major) + inverse-shift scatter of dS into the ring
+            {
+                uint8_t* d0 = drow + start * 16;
+                uint8_t* d1 = d0 - RING_COLS * 16;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, 4 * half + c)) =
+                        make_uint4(ptw[4 * c], ptw[4 * c + 1], ptw[4 * c + 2], ptw[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(gbase + B_OFF_DS + sw128_off(ii, 4 * half + c)) =
+                        make_uint4(dsw[4 * c], dsw[4 * c + 1], dsw[4 * c + 2], dsw[4 * c + 3]);
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    *reinterpret_cast<uint16_t*>((2 * c < wrap ? d0 : d1) + 32 * c) = (uint16_t)(dsw[c] & 0xffffu);
+                    *reinterpret_cast<uint16_t*>((2 * c + 1 < wrap ? d0 : d1) + 32 * c + 16) = (uint16_t)(dsw[c] >> 16);
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            // 5. key-side results of this tile (M = 64 layout: row r = 16 * quarter + lane, lanes 0..15)
-            mbar_wait(kdone, tt & 1);
-            tcgen05_fence_after();
-            {
-                uint32_t a[32];
-                const int j = j0 + 16 * quarter + lane;
-                const bool wr = lane < 16 && j < p.K;
-                tmem_ld32(tmem_base + TB_DK + hc + lane_off, a);
-                tmem_ld_wait();
-                if (wr) {
-                    bf16* dst = p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float f[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * p.scale;
-                        store8(dst + 8 * c, f);
-                    }
-                }
-                tmem_ld32(tmem_base + TB_DV + hc + lane_off, a);
-                tmem_ld_wait();
-                if (wr) {
-                    bf16* dst = p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float f[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
-                        store8(dst + 8 * c, f);
-                    }
-                }
-                tcgen05_fence_before();
-            }
-            // 6. chunk tt of the dS ring is complete once BOTH halves have scattered this tile
-            pair_sync(quarter);
-            extract_dg(tt);
         }
-        for (int cc = nt; cc < nc; ++cc) {
-            flush_dr(cc - 1);
-            extract_dg(cc);
-        }
-        flush_dr(nc - 1);
+        flush_keys(nt - 1);
+        for (int cc = nt - 1; cc < nc; ++cc) flush_dr(cc);
         // dq = (dqK + dqR) / sqrt(d); du / dvb = column sums over the query rows
         {
             uint32_t a[32], c2[32];

@@ -138,6 +138,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)2 << 61;  // SWIZZLE_128B
     return d;
 }
+// shared-memory matrix descriptor WITHOUT swizzle (layout_type 0, "interleaved" 8 x 16-byte core matrices):
+//   K-major : 8 rows (MN) are 16 bytes apart; SBO = byte stride between 8-row groups; LBO = byte stride between the two
+//             16-byte K chunks of one MMA (K = 16 bf16)
+//   MN-major: 8 k-rows are 16 bytes apart (each holds 8 contiguous MN elements); SBO = byte stride between groups of
+//             8 MN elements; LBO = byte stride between groups of 8 k-rows
+__device__ __forceinline__ uint64_t umma_smem_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // version
+    return d;
+}
 // instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
