@@ -257,31 +257,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-            int s = 0; uint32_t ph = 0; int it = 0;
-            for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-                const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
-                const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(tempty0 + 8 * as, aph ^ 1);
+        // The whole warp runs the loop (converged waits); one elected lane issues.  Descriptors are built once per
+        // operand and advanced by adding to the 14-bit start-address field, so each tcgen05.mma costs a few uniform ops.
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        const uint64_t da0 = A_MN ? umma_smem_desc(sA, 8192, 1024) : umma_smem_desc(sA, 16, 1024);
+        const uint64_t db0 = B_MN ? umma_smem_desc(sB, 8192, 1024) : umma_smem_desc(sB, 16, 1024);
+        constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4, b_kstep = (B_MN ? 2048 : 32) >> 4;
+        int s = 0; uint32_t ph = 0; int it = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+            const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
+            const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tempty0 + 8 * as, aph ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+                mbar_wait(full0 + 8 * s, ph);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
-                    mbar_wait(full0 + 8 * s, ph);
-                    tcgen05_fence_after();
-                    const uint32_t a_src = sA + s * A_BYTES, b_src = sB + s * B_BYTES;
+                if (elect_one()) {
+                    const uint64_t da = da0 + (uint64_t)((s * A_BYTES) >> 4), db = db0 + (uint64_t)((s * B_BYTES) >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = A_MN ? umma_smem_desc(a_src + k * 2048, 8192, 1024)
-                                                 : umma_smem_desc(a_src + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? umma_smem_desc(b_src + k * 2048, 8192, 1024)
-                                                 : umma_smem_desc(b_src + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb != wk.kb0 || k != 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(d_tmem, da + k * a_kstep, db + k * b_kstep, idesc, (kb != wk.kb0 || k != 0) ? 1u : 0u);
                     umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (kb == wk.kb1 - 1) umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
                 }
-                umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
     } else {

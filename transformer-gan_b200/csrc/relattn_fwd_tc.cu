@@ -157,55 +157,65 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc_kk = umma_idesc_bf16(BQ, BJ, 0, 0);  // S, G: A, B K-major, N = 32
-            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HS, 0, 1);  // O: A from TMEM, B (= V tile [keys][d]) MN-major
-            auto mma_s = [&](int tt) {
-                if (tt >= nt) return;
-                const int st = tt % KV_STAGES;
-                mbar_wait(kv_full + 8 * st, (tt / KV_STAGES) & 1);
-                mbar_wait(s_empty + 8 * (tt & 1), ((tt >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                const uint32_t kaddr = sKV + st * (2 * TILE_BYTES);
+        // The whole warp runs the schedule (converged barrier waits); one elected lane issues the tcgen05 ops.
+        // Descriptors are built once and advanced by adding to their start-address field (16-byte units).
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(BQ, BJ, 0, 0);  // S, G: A, B K-major, N = 32
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HS, 0, 1);  // O: A from TMEM, B (= V tile [keys][d]) MN-major
+        const uint64_t d_qu = umma_smem_desc(sQu, 16, 1024), d_qv = umma_smem_desc(sQv, 16, 1024);
+        const uint64_t d_k0 = umma_smem_desc(sKV, 16, 1024), d_v0 = umma_smem_desc(sKV + TILE_BYTES, 8192, 1024);
+        const uint64_t d_r0 = umma_smem_desc(sR, 16, 1024);
+        auto mma_s = [&](int tt) {
+            if (tt >= nt) return;
+            const int st = tt % KV_STAGES;
+            mbar_wait(kv_full + 8 * st, (tt / KV_STAGES) & 1);
+            mbar_wait(s_empty + 8 * (tt & 1), ((tt >> 1) & 1) ^ 1);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t dk = d_k0 + (uint64_t)((st * 2 * TILE_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < HS / 16; ++k)
-                    umma_bf16(tmem_base + TM_S + BJ * (tt & 1), umma_smem_desc(sQu + 32 * k, 16, 1024),
-                              umma_smem_desc(kaddr + 32 * k, 16, 1024), idesc_kk, k != 0);
+                    umma_bf16(tmem_base + TM_S + BJ * (tt & 1), d_qu + 2 * k, dk + 2 * k, idesc_kk, k != 0);
                 umma_commit(s_full + 8 * (tt & 1));
-            };
-            auto mma_g = [&](int cc) {
-                if (cc >= nc) return;
-                const int st = cc % R_STAGES;
-                mbar_wait(r_full + 8 * st, (cc / R_STAGES) & 1);
-                mbar_wait(g_empty + 8 * (cc & 1), ((cc >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                const uint32_t raddr = sR + st * TILE_BYTES;
+            }
+            __syncwarp();
+        };
+        auto mma_g = [&](int cc) {
+            if (cc >= nc) return;
+            const int st = cc % R_STAGES;
+            mbar_wait(r_full + 8 * st, (cc / R_STAGES) & 1);
+            mbar_wait(g_empty + 8 * (cc & 1), ((cc >> 1) & 1) ^ 1);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t dr = d_r0 + (uint64_t)((st * TILE_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < HS / 16; ++k)
-                    umma_bf16(tmem_base + TM_G + BJ * (cc & 1), umma_smem_desc(sQv + 32 * k, 16, 1024),
-                              umma_smem_desc(raddr + 32 * k, 16, 1024), idesc_kk, k != 0);
+                    umma_bf16(tmem_base + TM_G + BJ * (cc & 1), d_qv + 2 * k, dr + 2 * k, idesc_kk, k != 0);
                 umma_commit(g_full + 8 * (cc & 1));
                 umma_commit(r_empty + 8 * st);
-            };
-            auto mma_pv = [&](int tt) {
-                const int st = tt % KV_STAGES;
-                mbar_wait(p_full + 8 * (tt & 1), (tt >> 1) & 1);
-                tcgen05_fence_after();
-                const uint32_t vaddr = sKV + st * (2 * TILE_BYTES) + TILE_BYTES;
+            }
+            __syncwarp();
+        };
+        auto mma_pv = [&](int tt) {
+            const int st = tt % KV_STAGES;
+            mbar_wait(p_full + 8 * (tt & 1), (tt >> 1) & 1);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t dv = d_v0 + (uint64_t)((st * 2 * TILE_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < BJ / 16; ++k)
-                    umma_bf16_ts(tmem_base + TM_O, tmem_base + TM_P + 16 * (tt & 1) + 8 * k,
-                                 umma_smem_desc(vaddr + 2048 * k, 8192, 1024), idesc_pv, (tt | k) != 0);
+                    umma_bf16_ts(tmem_base + TM_O, tmem_base + TM_P + 16 * (tt & 1) + 8 * k, dv + (2048 >> 4) * k, idesc_pv,
+                                 (tt | k) != 0);
                 umma_commit(o_done + 8 * (tt & 1));
                 umma_commit(kv_empty + 8 * st);
-            };
-            for (int cc = 0; cc < NCHUNK; ++cc) mma_g(cc);
-            mma_s(0);
-            for (int tt = 0; tt < nt; ++tt) {
-                mma_g(tt + NCHUNK);
-                mma_s(tt + 1);
-                mma_pv(tt);
             }
+            __syncwarp();
+        };
+        for (int cc = 0; cc < NCHUNK; ++cc) mma_g(cc);
+        mma_s(0);
+        for (int tt = 0; tt < nt; ++tt) {
+            mma_g(tt + NCHUNK);
+            mma_s(tt + 1);
+            mma_pv(tt);
         }
     } else {
         // =========================== row warps: rel-shift / softmax / dropout ===========================

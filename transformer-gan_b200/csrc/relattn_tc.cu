@@ -67,6 +67,20 @@ struct BwdParams {
     float drop_scale; uint32_t drop_thresh; uint32_t drop_key;
 };
 
+#ifdef TGAN_PROFILE
+__device__ long long g_bwd_prof[16];
+#define PROF_DECL long long _pt = clock64(); long long _acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF(i) { const long long _n = clock64(); _acc[i] += _n - _pt; _pt = _n; }
+#define PROF_DUMP() if (blockIdx.x == 200 && threadIdx.x == 0) { for (int _i = 0; _i < 13; ++_i) g_bwd_prof[_i] = _acc[_i]; }
+__device__ long long g_bwd_prof_mma[16];
+#define PROF_DUMP_MMA() if (blockIdx.x == 200) { for (int _i = 0; _i < 13; ++_i) g_bwd_prof_mma[_i] = _acc[_i]; }
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_DUMP()
+#define PROF_DUMP_MMA()
+#endif
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -79,6 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmR, BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
+    PROF_DECL
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sQu = base + B_OFF_QU, sQv = base + B_OFF_QV, sDO = base + B_OFF_DO, sK = base + B_OFF_K,
@@ -173,6 +188,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    PROF(0)
 
     if (warp == ROW_WARPS + 1) {
         // =========================== K / V producer ===========================
@@ -208,91 +224,124 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         }
     } else if (warp == ROW_WARPS) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t id_kk = umma_idesc_bf16(128, 64, 0, 0);   // S, G, dP: A, B K-major
-            constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dqK, dqR: A K-major, B MN-major
-            constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);    // dV, dK: A, B MN-major (M = 64)
-            constexpr uint32_t id_nn128 = umma_idesc_bf16(128, 64, 1, 1); // dqR: A (ring chunk), B MN-major
-            constexpr uint32_t id_kn64 = umma_idesc_bf16(64, 64, 0, 1);   // dR: A (ring chunk) K-major, B MN-major
-            auto mma_s = [&](int tt) {
-                if (tt >= nt) return;
-                mbar_wait(k_full + 8 * (tt & 1), (tt >> 1) & 1);
-                mbar_wait(s_empty, (tt & 1) ^ 1);
-                tcgen05_fence_after();
+        // The whole warp runs the schedule (converged barrier waits); one elected lane issues the tcgen05 ops.
+        // Descriptors are built once and advanced by adding to their start-address field (16-byte units).
+        constexpr uint32_t id_kk = umma_idesc_bf16(128, 64, 0, 0);    // S, G, dP: A, B K-major
+        constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);    // dqK: A K-major, B MN-major
+        constexpr uint32_t id_nn = umma_idesc_bf16(64, 64, 1, 1);     // dV, dK: A, B MN-major (M = 64)
+        constexpr uint32_t id_nn128 = umma_idesc_bf16(128, 64, 1, 1); // dqR: A (ring chunk), B MN-major
+        constexpr uint32_t id_kn64 = umma_idesc_bf16(64, 64, 0, 1);   // dR: A (ring chunk) K-major, B MN-major
+        const uint64_t k_qu = umma_smem_desc(sQu, 16, 1024), k_qv = umma_smem_desc(sQv, 16, 1024),
+                       k_do = umma_smem_desc(sDO, 16, 1024), k_k0 = umma_smem_desc(sK, 16, 1024),
+                       k_v = umma_smem_desc(sV, 16, 1024), k_rg0 = umma_smem_desc(sRG, 16, 1024),
+                       k_ds = umma_smem_desc(sDS, 16, 1024);
+        const uint64_t n_pt = umma_smem_desc(sPT, 8192, 1024), n_ds = umma_smem_desc(sDS, 8192, 1024),
+                       n_do = umma_smem_desc(sDO, 8192, 1024), n_qu = umma_smem_desc(sQu, 8192, 1024),
+                       n_qv = umma_smem_desc(sQv, 8192, 1024), n_k0 = umma_smem_desc(sK, 8192, 1024),
+                       n_rd = umma_smem_desc(sRD, 8192, 1024);
+        const uint64_t ring_mn0 = umma_smem_desc_noswz(sDR, 128, DR_GROUP), ring_k0 = umma_smem_desc_noswz(sDR, DR_GROUP, 128);
+        PROF(0)
+        auto mma_s = [&](int tt) {
+            if (tt >= nt) return;
+            PROF(0)
+            mbar_wait(k_full + 8 * (tt & 1), (tt >> 1) & 1);
+            PROF(1)
+            mbar_wait(s_empty, (tt & 1) ^ 1);
+            PROF(2)
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t dk = k_k0 + (uint64_t)(((tt & 1) * 8192) >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + TB_S, umma_smem_desc(sQu + 32 * k, 16, 1024),
-                              umma_smem_desc(sK + (tt & 1) * 8192 + 32 * k, 16, 1024), id_kk, k != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TB_S, k_qu + 2 * k, dk + 2 * k, id_kk, k != 0);
                 umma_commit(s_full);
-            };
-            auto mma_dp = [&](int tt) {
-                if (tt >= nt) return;
-                mbar_wait(v_full, tt & 1);
-                mbar_wait(dp_empty, (tt & 1) ^ 1);
-                tcgen05_fence_after();
+            }
+            __syncwarp();
+        };
+        auto mma_dp = [&](int tt) {
+            if (tt >= nt) return;
+            PROF(0)
+            mbar_wait(v_full, tt & 1);
+            PROF(3)
+            mbar_wait(dp_empty, (tt & 1) ^ 1);
+            PROF(4)
+            tcgen05_fence_after();
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + TB_DP, umma_smem_desc(sDO + 32 * k, 16, 1024),
-                              umma_smem_desc(sV + 32 * k, 16, 1024), id_kk, k != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TB_DP, k_do + 2 * k, k_v + 2 * k, id_kk, k != 0);
                 umma_commit(dp_full);
                 umma_commit(v_empty);
-            };
-            auto mma_g = [&](int cc) {
-                if (cc >= nc) return;
-                mbar_wait(rg_full + 8 * (cc & 1), (cc >> 1) & 1);
-                mbar_wait(g_empty, (cc & 1) ^ 1);
-                tcgen05_fence_after();
+            }
+            __syncwarp();
+        };
+        auto mma_g = [&](int cc) {
+            if (cc >= nc) return;
+            PROF(0)
+            mbar_wait(rg_full + 8 * (cc & 1), (cc >> 1) & 1);
+            PROF(5)
+            mbar_wait(g_empty, (cc & 1) ^ 1);
+            PROF(6)
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t dr = k_rg0 + (uint64_t)(((cc & 1) * 8192) >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_base + TB_G, umma_smem_desc(sQv + 32 * k, 16, 1024),
-                              umma_smem_desc(sRG + (cc & 1) * 8192 + 32 * k, 16, 1024), id_kk, k != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TB_G, k_qv + 2 * k, dr + 2 * k, id_kk, k != 0);
                 umma_commit(g_full);
                 umma_commit(rg_empty + 8 * (cc & 1));
-            };
-            auto mma_key = [&](int tt) {
-                mbar_wait(p_full, tt & 1);
-                tcgen05_fence_after();
+            }
+            __syncwarp();
+        };
+        auto mma_key = [&](int tt) {
+            PROF(0)
+            mbar_wait(p_full, tt & 1);
+            PROF(7)
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t dkn = n_k0 + (uint64_t)(((tt & 1) * 8192) >> 4);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)  // dV = P~^T dO'   (contraction over the 128 query rows)
-                    umma_bf16(tmem_base + TB_DV, umma_smem_desc(sPT + 2048 * k, 8192, 1024),
-                              umma_smem_desc(sDO + 2048 * k, 8192, 1024), id_nn, k != 0);
+                    umma_bf16(tmem_base + TB_DV, n_pt + 128 * k, n_do + 128 * k, id_nn, k != 0);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)  // dK = dS^T (q + u)
-                    umma_bf16(tmem_base + TB_DK, umma_smem_desc(sDS + 2048 * k, 8192, 1024),
-                              umma_smem_desc(sQu + 2048 * k, 8192, 1024), id_nn, k != 0);
+                    umma_bf16(tmem_base + TB_DK, n_ds + 128 * k, n_qu + 128 * k, id_nn, k != 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // dqK += dS K_t   (contraction over the 64 keys)
-                    umma_bf16(tmem_base + TB_DQK, umma_smem_desc(sDS + 32 * k, 16, 1024),
-                              umma_smem_desc(sK + (tt & 1) * 8192 + 2048 * k, 8192, 1024), id_kn, (tt | k) != 0);
+                    umma_bf16(tmem_base + TB_DQK, k_ds + 2 * k, dkn + 128 * k, id_kn, (tt | k) != 0);
                 umma_commit(kdone);
                 umma_commit(k_empty + 8 * (tt & 1));
-            };
-            auto mma_rel = [&](int cc) {
-                mbar_wait(rd_full, cc & 1);
-                if (cc > 0) mbar_wait(dr_empty, (cc - 1) & 1);  // the row warps have drained dR of chunk cc-1
-                tcgen05_fence_after();
-                const uint32_t cb = sDR + (cc % 3) * (BJ * 16);  // chunk cc = ring positions 64*(cc%3) .. +63
+            }
+            __syncwarp();
+        };
+        auto mma_rel = [&](int cc) {
+            PROF(0)
+            mbar_wait(rd_full, cc & 1);
+            PROF(8)
+            if (cc > 0) mbar_wait(dr_empty, (cc - 1) & 1);  // the row warps have drained dR of chunk cc-1
+            PROF(9)
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint32_t cboff = ((cc % 3) * (BJ * 16)) >> 4;  // chunk cc = ring positions 64*(cc%3) .. +63
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // dqR += dG_c R_c   (A = dG: M = i, MN-major, un-swizzled ring chunk)
-                    umma_bf16(tmem_base + TB_DQR, umma_smem_desc_noswz(cb + 256 * k, 128, DR_GROUP),
-                              umma_smem_desc(sRD + 2048 * k, 8192, 1024), id_nn128, (cc | k) != 0);
+                    umma_bf16(tmem_base + TB_DQR, ring_mn0 + cboff + 16 * k, n_rd + 128 * k, id_nn128, (cc | k) != 0);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)  // dR_c = dG_c^T (q + v)   (A = dG^T: M = p, K-major, same chunk)
-                    umma_bf16(tmem_base + TB_DR, umma_smem_desc_noswz(cb + 2 * k * DR_GROUP, DR_GROUP, 128),
-                              umma_smem_desc(sQv + 2048 * k, 8192, 1024), id_kn64, k != 0);
+                    umma_bf16(tmem_base + TB_DR, ring_k0 + cboff + ((2 * DR_GROUP) >> 4) * k, n_qv + 128 * k, id_kn64, k != 0);
                 umma_commit(rdone);
                 umma_commit(rd_empty);
-            };
-            mma_s(0); mma_dp(0); mma_g(0); mma_g(1); mma_g(2);
-            for (int tt = 0; tt < nt; ++tt) {
-                mma_g(tt + 3);       // needs only the previous chunk pulled
-                mma_s(tt + 1);       // issued BEFORE the long key / rel MMAs of tile tt so the next tile never waits
-                mma_dp(tt + 1);
-                mma_key(tt);
-                mma_rel(tt);
             }
-            for (int cc = nt; cc < nc; ++cc) mma_rel(cc);
+            __syncwarp();
+        };
+        mma_s(0); mma_dp(0); mma_g(0); mma_g(1); mma_g(2);
+        for (int tt = 0; tt < nt; ++tt) {
+            mma_g(tt + 3);       // needs only the previous chunk pulled
+            mma_s(tt + 1);       // issued BEFORE the long key / rel MMAs of tile tt so the next tile never waits
+            mma_dp(tt + 1);
+            mma_key(tt);
+            mma_rel(tt);
         }
+        for (int cc = nt; cc < nc; ++cc) mma_rel(cc);
+        PROF(0)
+        if (lane == 0) { PROF_DUMP_MMA() }
     } else {
         // =========================== row warps ===========================
         const bool live = ii < rows_here;
@@ -372,7 +421,9 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 for (int c = 0; c < 32; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
                 ++consumed;
             }
+            PROF(1)
             pair_sync(quarter);  // A: both halves of the new chunk are in the ring
+            PROF(2)
             const int j0 = (t_lo + tt) * BJ;
             const int start = (BQ - 1 - ii + BJ * tt + hc) % RING_COLS;  // ring column of this thread's jj = 0
             const int wrap = RING_COLS - start;                         // first jj that wraps around
@@ -389,6 +440,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty);
+                PROF(3)
                 const bool interior = rows_here == BQ && j0 + BJ - 1 <= p.M && (!p.same_length || BQ - p.msl - j0 <= 0) &&
                                       (!reset_b || p.M <= j0);
                 if (interior) {
@@ -411,7 +463,9 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     }
                 }
             }
+            PROF(4)
             pair_sync(quarter);  // B: both threads of the row are done reading the G ring for this tile
+            PROF(5)
             // 3. dP
             mbar_wait(dp_full, tt & 1);
             tcgen05_fence_after();
@@ -421,6 +475,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dp_empty);
+            PROF(6)
             // 4. P~ = keep(P), dS = P (keep(dP) - delta), packed to bf16 pairs in registers
             uint32_t ptw[16], dsw[16];
             {
@@ -444,9 +499,12 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             }
             // 5. drain the previous tile: its dK / dV (frees the P~ / dS buffers) and its dR chunk (frees the ring
             //    third that this tile's scatter is about to reuse).  Those MMAs ran while this tile was being computed.
+            PROF(7)
             if (tt > 0) {
                 flush_keys(tt - 1);
+                PROF(8)
                 flush_dr(tt - 1);
+                PROF(9)
             }
             if (tt + 2 >= nt) {
                 // chunk tt+2 is one of the two tail chunks whose upper positions are never written: clear this thread's
@@ -476,6 +534,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
+            PROF(10)
         }
         flush_keys(nt - 1);
         for (int cc = nt - 1; cc < nc; ++cc) flush_dr(cc);
@@ -506,6 +565,8 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             atomicAdd(&p.du[n * HS + hc + lane], su * p.scale);
             atomicAdd(&p.dvb[n * HS + hc + lane], sv * p.scale);
         }
+        PROF(11)
+        PROF_DUMP()
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -515,6 +576,13 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     }
 }
 }  // namespace
+
+#ifdef TGAN_PROFILE
+extern "C" int tgan_debug_bwd_prof(long long* host16) {
+    cudaMemcpyFromSymbol(host16 + 16, g_bwd_prof_mma, sizeof(long long) * 16);
+    return (int)cudaMemcpyFromSymbol(host16, g_bwd_prof, sizeof(long long) * 16);
+}
+#endif
 
 int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, const void* out,
