@@ -121,6 +121,51 @@ def run_generate_case(name, shape: O.TxlShape, seed, B, T, temperature):
     print("wrote", name)
 
 
+def run_gan_case(name, shape: O.TxlShape, seed, B, dis_type, loss_type, dis_tgt_len=16, context_len=5, chunks=2,
+                 temperature=0.8):
+    """One "dis_loss" and one "gen_loss" call of the UNMODIFIED reference TransformerGAN (fp32: its one-hot rows are
+    hard-coded float32, transformer_gan.py:268-271) with injected Gumbel noise and GP alphas."""
+    import tempfile
+    V = shape.n_token
+    bert_dir = ref_harness.tiny_bert_config_dir(os.path.join(tempfile.mkdtemp(), "bert"), V + 1)
+    cfg = ref_harness.make_gan_cfg(shape, dis_tgt_len, shape.mem_len, dis_type, dis_tgt_len, shape.mem_len, context_len,
+                                   chunks, loss_type, bert_path=bert_dir)
+    params = O.init_params(shape, seed, dtype=torch.float32)
+    torch.manual_seed(seed)
+    model = ref_harness.build_reference_gan(cfg, V, params, dtype=torch.float32)
+    dis_state = O.seeded_state(model.discriminator, seed + 1)
+    model.discriminator.load_state_dict(dis_state, strict=False)
+    if hasattr(model.discriminator, "dropout"):
+        model.discriminator.dropout.p = 0.0  # RelGAN_D hard-codes dropout 0.25 (transformer_gan.py:52): off for a fixture
+    model.temperature = temperature
+    g = torch.Generator().manual_seed(seed + 2)
+    data = token_stream(B, dis_tgt_len, offset=777)[:dis_tgt_len].contiguous()
+    n_steps = dis_tgt_len - context_len
+    U = [torch.rand(1, B, V, generator=g) for _ in range(n_steps)]
+    alphas = [torch.rand(B, 1, 1, generator=g) for _ in range(chunks)]
+    out = {"seed": seed, "B": B, "dis_type": dis_type, "loss_type": loss_type, "dis_tgt_len": dis_tgt_len,
+           "context_len": context_len, "chunks": chunks, "temperature": temperature, "data": data.numpy(),
+           "U": torch.cat(U, 0).numpy(), "alpha": torch.cat(alphas, 0).view(chunks, B).numpy(),
+           "shape": np.array([shape.n_layer, shape.n_head, shape.d_model, shape.d_inner, shape.n_token,
+                              shape.mem_len, int(shape.same_length), shape.clamp_len, int(shape.pre_lnorm)])}
+    # discriminator weights are regenerated by txl_oracle.seeded_state(module, seed + 1) (keyed by tensor name)
+    for mode in ("dis_loss", "gen_loss"):
+        model.zero_grad()
+        with ref_harness.injected_uniform(U, alphas):
+            r = model(data, None, None, mode)
+        for k in ("dis_loss", "gen_loss", "gp_loss"):
+            if r.get(k) is not None:
+                out[f"{mode}.{k}"] = np.array(float(r[k]))
+        owner = model.discriminator if mode == "dis_loss" else model.generator
+        for k, prm in owner.named_parameters():
+            if prm.grad is not None and prm.numel() <= 40000:  # keep the fixture small: skip the 1.4 M highway matrix etc.
+                out[f"{mode}.grad.{k}"] = prm.grad.numpy().copy()
+        if mode == "dis_loss":
+            assert all(prm.grad is None for prm in model.generator.parameters())
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, {k: float(v) for k, v in out.items() if k.endswith("_loss")})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -133,6 +178,9 @@ def main():
     run_mle_case("mle_real", real, seed=13, Q=16, B=2, nseg=3, reset_at=(2, 1), full_mems=False)
     gen = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=64, same_length=True)
     run_generate_case("generate_tiny", gen, seed=14, B=2, T=12, temperature=0.7)
+    gan = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=16)
+    run_gan_case("gan_bert_tiny", gan, seed=15, B=3, dis_type="bert", loss_type="wgan-gp")
+    run_gan_case("gan_cnn_tiny", gan, seed=16, B=2, dis_type="cnn", loss_type="rsgan")
 
 
 if __name__ == "__main__":

@@ -109,15 +109,19 @@ def build_reference_lm(shape, params, tgt_len, dtype=torch.float32):
 
 
 @contextmanager
-def injected_uniform(noise_list):
-    """Make the reference's ``torch.rand(shape)`` inside sample_gumbel (mem_transformer.py:610) return the
-    given tensors in order."""
+def injected_uniform(noise_list, alpha_list=None):
+    """Make the reference's ``torch.rand(shape)`` inside sample_gumbel (mem_transformer.py:610) return the given
+    tensors in order; with ``alpha_list`` the GP interpolation weights of calc_gradient_penalty
+    (``torch.rand([B,1,1], device=...)``, transformer_gan.py:204) are injected the same way."""
     it = iter(noise_list)
+    it_alpha = iter(alpha_list) if alpha_list is not None else None
     orig = torch.rand
 
     def fake_rand(*shape, **kw):
-        if kw.get("device") is not None:  # calc_gradient_penalty's alpha (transformer_gan.py:204): leave alone
-            return orig(*shape, **kw)
+        if kw.get("device") is not None:
+            if it_alpha is None:
+                return orig(*shape, **kw)
+            return next(it_alpha).clone().view(*shape[0]) if len(shape) == 1 else next(it_alpha).clone()
         return next(it).clone()
 
     torch.rand = fake_rand
@@ -125,3 +129,61 @@ def injected_uniform(noise_list):
         yield
     finally:
         torch.rand = orig
+
+
+# ---------------------------------------------------------------------------------------------- GAN step
+class TinyVocab:
+    """Stand-in for BaseVocab: the GAN step only needs ``len(vocab)`` and ``vocab.vec_len`` (transformer_gan.py:127-131)."""
+
+    def __init__(self, n, vec_len=0):
+        self.n, self.vec_len = n, vec_len
+
+    def __len__(self):
+        return self.n
+
+
+def make_gan_cfg(shape, tgt_len, mem_len, dis_type, dis_tgt_len, dis_mem_len, context_len, sample_chunks_mem, loss_type,
+                 bert_path="", batch_chunk=1, gen_loss_factor=1.0, dis_loss_factor=1.0):
+    """yacs-shaped config with every field TransformerGAN reads (utils/config_helper.py:51-147)."""
+    cfg = make_cfg(shape.n_layer, shape.n_head, shape.d_model, shape.d_inner, tgt_len, mem_len,
+                   same_length=shape.same_length, clamp_len=shape.clamp_len, pre_lnorm=shape.pre_lnorm)
+    cfg.DISCRIMINATOR = _Node(type=dis_type, tgt_len=dis_tgt_len, mem_len=dis_mem_len, context_len=context_len,
+                              sample_chunks_mem=sample_chunks_mem, truncate_backprop=False, backprop_outside=True,
+                              gen_loss_factor=gen_loss_factor, dis_loss_factor=dis_loss_factor, batch_chunk=batch_chunk,
+                              BERT=_Node(model_path=bert_path, loss_type=loss_type if dis_type == "bert" else "rsgan",
+                                         model_type="bert_lm", random_weights=True, freeze_layers=[]),
+                              CNN=_Node(embed_dim=64, hidden_dim=64, num_rep=64, init="uniform",
+                                        loss_type=loss_type if dis_type == "cnn" else "rsgan"))
+    cfg.PPO = _Node(dis_D_type="bert", dis_D_num_rep=1, clip_param=0.4)
+    return cfg
+
+
+def tiny_bert_config_dir(path, vocab_size, hidden=32, layers=2, heads=2, inter=64, max_pos=64):
+    """Write a config.json for a small BERT (dropout 0) so ``BertConfig.from_pretrained(path)`` works offline."""
+    import json
+    os.makedirs(path, exist_ok=True)
+    import txl_oracle
+    cfg = dict(txl_oracle.TINY_BERT, vocab_size=vocab_size, hidden_size=hidden, num_hidden_layers=layers,
+               num_attention_heads=heads, intermediate_size=inter, max_position_embeddings=max_pos)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(cfg, f)
+    return path
+
+
+def build_reference_gan(cfg, n_token, gen_params, dis_state=None, dtype=torch.float64):
+    """Unmodified reference TransformerGAN with the generator loaded from ``gen_params`` and (optionally) the
+    discriminator from ``dis_state``; returns the module in train() mode (dropout is 0 in these configs)."""
+    _, tg = load_reference(with_gan=True)
+    model = tg.TransformerGAN(cfg, TinyVocab(n_token)).to(dtype)
+    sd = {k: v.clone().to(dtype) for k, v in gen_params.items()}
+    sd["crit.out_layers.0.weight"] = sd["word_emb.emb_layers.0.weight"]
+    missing, unexpected = model.generator.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    if dis_state is not None:
+        model.discriminator.load_state_dict({k: v.to(dtype) for k, v in dis_state.items()}, strict=False)
+    if hasattr(model.discriminator, "config"):
+        # transformers >= 4.36 defaults to SDPA attention, whose double backward (needed by the reference's WGAN-GP,
+        # transformer_gan.py:220-223) does not exist; the pinned 2.5.1 only had the eager math path
+        model.discriminator.config._attn_implementation = "eager"
+    model.train()
+    return model

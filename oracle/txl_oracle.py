@@ -311,3 +311,125 @@ def sample_fake_chunks(data: torch.Tensor, p, shape_gen: TxlShape, temperature: 
         mems = mems.detach()                                                          # :507
         seq = [seq[-1]]
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# A11-A15  the adversarial part of TransformerGAN.forward            transformer_gan.py:232-533
+# ----------------------------------------------------------------------------------------------
+def adv_losses(d_real: torch.Tensor, d_fake: torch.Tensor, loss_type: str):
+    """(g_loss, d_loss) for the objectives the shipped configs use (utils/helpers.py:117-129)."""
+    if "wgan" in loss_type:                                             # experiment_spanbert.yml: 'wgan-gp'
+        return -d_fake.mean(), -d_real.mean() + d_fake.mean()
+    if "rsgan" in loss_type:                                            # experiment_cnn.yml default
+        bce = F.binary_cross_entropy_with_logits
+        return bce(d_fake - d_real, torch.ones_like(d_fake)), bce(d_real - d_fake, torch.ones_like(d_real))
+    raise NotImplementedError(loss_type)
+
+
+def gradient_penalty(disc_on_onehot, real_1h: torch.Tensor, fake: torch.Tensor, alpha: torch.Tensor, lam: float = 10.0,
+                     embed=None, disc_on_embeds=None):
+    """10 * mean_b (||d D / d x||_2 - 1)^2 with 1e-12 inside the sqrt (transformer_gan.py:203-230), where
+    x^ = alpha real + (1 - alpha) fake on one-hot rows [B, T, V'] and alpha: [B].
+    CNN discriminator: the gradient is taken w.r.t. x^ itself.  BERT discriminator: the reference re-binds
+    ``interpolates`` to the EMBEDDED rows x^ E (:211-216) before differentiating, so the norm is over [T, hidden]:
+    pass ``embed`` (x^ -> x^ E) and ``disc_on_embeds``."""
+    B = real_1h.shape[0]
+    a = alpha.to(real_1h.dtype).view(B, 1, 1)
+    x = a * real_1h + (1 - a) * fake.detach()
+    if embed is not None:
+        x = embed(x)
+        d = disc_on_embeds(x)
+    else:
+        x = x.detach().requires_grad_(True)
+        d = disc_on_onehot(x)
+    (g,) = torch.autograd.grad(d, x, grad_outputs=torch.ones_like(d), create_graph=True, retain_graph=True)
+    slopes = torch.sqrt(g.reshape(B, -1).pow(2).sum(1) + 1e-12)
+    return ((slopes - 1.0) ** 2).mean() * lam
+
+
+def gan_step(mode: str, data: torch.Tensor, p, shape_gen: TxlShape, disc_on_onehot, extra_col: int, loss_type: str,
+             temperature: float, noise: List[torch.Tensor], alphas: List[torch.Tensor], tgt_len: int, context_len: int,
+             sample_chunks_mem: int, batch_chunk: int = 1, gen_loss_factor: float = 1.0, dis_loss_factor: float = 1.0,
+             embed=None, disc_on_embeds=None):
+    """One ``"dis_loss"`` or ``"gen_loss"`` call of TransformerGAN.forward with ``backprop_outside`` (the shipped
+    setting): samples ``sample_chunks_mem`` chunks with the generator, scores real / fake with ``disc_on_onehot``
+    ([B, T, V + extra_col] -> logits [B or B*rep]), back-propagates each chunk's scaled loss immediately
+    (:487-502) and returns the detached sums exactly as the reference does (:515-531).
+    ``extra_col`` = 1 for the BERT discriminator (its vocabulary has one more id, :396-399), 0 for the CNN one."""
+    V = shape_gen.n_token
+    share = batch_chunk * sample_chunks_mem
+    chunks = sample_fake_chunks(data, p, shape_gen, temperature, noise, tgt_len, context_len, sample_chunks_mem)
+    g_sum = d_sum = gp_sum = 0.0
+    ids = []
+    for k, (cs, fake) in enumerate(chunks):
+        T = fake.shape[0]
+        if mode == "dis_loss":
+            fake = fake.detach()
+        ids.append(fake.detach().argmax(-1))
+        real = data[cs:cs + T].transpose(0, 1)                                            # [B, T]
+        fake_bt = fake.transpose(0, 1)
+        if extra_col:
+            fake_bt = torch.cat([fake_bt, fake_bt.new_zeros(*fake_bt.shape[:-1], extra_col)], -1)
+        real_1h = F.one_hot(real, V + extra_col).to(fake_bt.dtype)
+        g_loss, d_loss = adv_losses(disc_on_onehot(real_1h), disc_on_onehot(fake_bt), loss_type)
+        g_sum += g_loss.detach()
+        d_sum += d_loss.detach()
+        if mode == "dis_loss":
+            (d_loss * dis_loss_factor / share).backward()
+            if "gp" in loss_type:
+                gp = gradient_penalty(disc_on_onehot, real_1h, fake_bt, alphas[k], embed=embed, disc_on_embeds=disc_on_embeds)
+                gp_sum += gp.detach()
+                (gp * dis_loss_factor / share).backward()
+        else:
+            (g_loss * gen_loss_factor / share).backward()
+    out = {"ids": torch.cat(ids, 0)}
+    if mode == "dis_loss":
+        out["dis_loss"] = dis_loss_factor * d_sum / sample_chunks_mem
+        if "gp" in loss_type:
+            out["gp_loss"] = dis_loss_factor * gp_sum / sample_chunks_mem
+    else:
+        out["gen_loss"] = gen_loss_factor * g_sum / sample_chunks_mem
+    return out
+
+
+def seeded_state(module, seed: int, std: float = 0.15) -> Dict[str, torch.Tensor]:
+    """Deterministic, 'responsive' discriminator weights for the GAN fixtures: every floating tensor of
+    ``module.state_dict()`` is drawn from its own generator keyed by (seed, tensor name), so the reference module in
+    the build container and the drop-in module on the GPU box get identical values without shipping them."""
+    import zlib
+    sd = {}
+    for k, v in module.state_dict().items():
+        if not v.is_floating_point():
+            continue
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(k.encode()))
+        if "LayerNorm.weight" in k:
+            sd[k] = 1.0 + 0.05 * torch.randn(v.shape, generator=g)
+        elif k.endswith("bias"):
+            sd[k] = 0.02 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = std * torch.randn(v.shape, generator=g)
+    return sd
+
+
+# small BERT discriminator used by the GAN fixtures (dropout 0 so the reference run is deterministic)
+TINY_BERT = dict(architectures=["BertForMaskedLM"], model_type="bert", hidden_size=32, num_hidden_layers=2,
+                 num_attention_heads=2, intermediate_size=64, hidden_act="gelu", hidden_dropout_prob=0.0,
+                 attention_probs_dropout_prob=0.0, max_position_embeddings=64, type_vocab_size=2, initializer_range=0.02,
+                 layer_norm_eps=1e-12, pad_token_id=0)
+
+
+def relgan_d_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_rep: int = 64) -> torch.Tensor:
+    """Functional restatement of RelGAN_D.forward in eval mode (transformer_gan.py:90-119): x [B, T, V] ->
+    logits [B * num_rep].  ``sd`` holds the module's state_dict tensors."""
+    emb = (x @ sd["embeddings.weight"].t()).unsqueeze(1)                              # [B, 1, T, embed_dim]   :96-98
+    single = sd["embeddings.weight"].shape[0] // num_rep
+    pooled = []
+    for i in range(4):                                                                 # filter sizes 2..5      :100-105
+        c = F.relu(F.conv2d(emb, sd[f"convs.{i}.weight"], sd[f"convs.{i}.bias"], stride=(1, single)))
+        pooled.append(c.amax(dim=2))                                                   # max over time
+    feat = torch.cat(pooled, 1).permute(0, 2, 1).reshape(-1, 1200)                     # :106-109
+    hw = feat @ sd["highway.weight"].t() + sd["highway.bias"]                         # :110-114
+    gate = torch.sigmoid(hw)
+    feat = gate * F.relu(hw) + (1.0 - gate) * feat
+    out = feat @ sd["feature2out.weight"].t() + sd["feature2out.bias"]               # dropout is identity in eval
+    return (out @ sd["out2logits.weight"].t() + sd["out2logits.bias"]).squeeze(1)     # :116-117

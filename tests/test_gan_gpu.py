@@ -1,0 +1,116 @@
+"""GPU: the drop-in TransformerGAN (generator on the CUDA kernels, discriminator = HF BERT / RelGAN_D) against the
+golden vectors of the UNMODIFIED reference GAN step (tests/golden/gan_*.npz) and against the oracle's sampled ids."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as GU
+import txl_oracle as O
+from test_gan_golden import build_disc
+
+pytestmark = pytest.mark.gpu
+
+
+class _Vocab:
+    vec_len = 0
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
+def _cfg(shape, z, bert_dir):
+    ns = types.SimpleNamespace
+    T = int(z["dis_tgt_len"])
+    dis_type, loss_type = str(z["dis_type"]), str(z["loss_type"])
+    return ns(MODEL=ns(num_layers=shape.n_layer, num_heads=shape.n_head, units=shape.d_model, inner_size=shape.d_inner,
+                       dropout=0.0, attention_dropout=0.0, tie_embedding=True, tie_proj=False, pre_lnorm=False,
+                       same_length=shape.same_length, clamp_len=shape.clamp_len),
+              TRAIN=ns(tgt_length=T, mem_length=shape.mem_len, pad_type="model", replace_start_with_pad=False,
+                       append_note_status=False),
+              DISCRIMINATOR=ns(type=dis_type, tgt_len=T, mem_len=shape.mem_len, context_len=int(z["context_len"]),
+                               sample_chunks_mem=int(z["chunks"]), truncate_backprop=False, backprop_outside=True,
+                               gen_loss_factor=1.0, dis_loss_factor=1.0, batch_chunk=1,
+                               BERT=ns(model_path=bert_dir, loss_type=loss_type if dis_type == "bert" else "rsgan",
+                                       model_type="bert_lm", random_weights=True, freeze_layers=[]),
+                               CNN=ns(embed_dim=64, hidden_dim=64, num_rep=64, init="uniform",
+                                      loss_type=loss_type if dis_type == "cnn" else "rsgan")),
+              PPO=ns(dis_D_type="bert", dis_D_num_rep=1, clip_param=0.4))
+
+
+@pytest.mark.parametrize("name", ["gan_bert_tiny", "gan_cnn_tiny"])
+def test_gan_step_matches_reference_golden(name, tmp_path):
+    import transformer_gan as TG
+    z, shape = GU.load(name)
+    V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
+    bert_dir = str(tmp_path / "bert")
+    os.makedirs(bert_dir, exist_ok=True)
+    json.dump(dict(O.TINY_BERT, vocab_size=V + 1), open(os.path.join(bert_dir, "config.json"), "w"))
+    torch.manual_seed(0)
+    model = TG.TransformerGAN(_cfg(shape, z, bert_dir), _Vocab(V))
+    sd = {k: v.clone() for k, v in O.init_params(shape, int(z["seed"])).items()}
+    sd["crit.out_layers.0.weight"] = sd["word_emb.emb_layers.0.weight"]
+    model.generator.load_state_dict(sd, strict=False)
+    model.discriminator.load_state_dict(O.seeded_state(model.discriminator, int(z["seed"]) + 1), strict=False)
+    if hasattr(model.discriminator, "dropout"):
+        model.discriminator.dropout.p = 0.0
+    model = model.cuda().train()
+    model.generator.compute_dtype = torch.float32  # fp32 parity mode (1e-4)
+    model.temperature = float(z["temperature"])
+    data = torch.from_numpy(z["data"]).cuda()
+    U = torch.from_numpy(z["U"]).cuda()
+    alpha = torch.from_numpy(z["alpha"]).cuda()
+    chunk_of = {"k": 0}
+    model.gumbel_noise_source = lambda step, shp: U[step:step + 1]
+
+    def alpha_src(b):
+        a = alpha[chunk_of["k"] % chunks]
+        chunk_of["k"] += 1
+        return a
+    model.gp_alpha_source = alpha_src
+
+    # the oracle replays the same call on the CPU (fp64): source of the expected sampled ids
+    disc, dparams, extra, embed, on_emb = build_disc(z, shape, torch.float64)
+    Ul = [torch.from_numpy(z["U"][k:k + 1]).double() for k in range(T - ctx)]
+    al = [torch.from_numpy(z["alpha"][k]).double() for k in range(chunks)]
+    for mode in ("dis_loss", "gen_loss"):
+        model.zero_grad(set_to_none=True)
+        chunk_of["k"] = 0
+        r = model(data, None, None, mode)
+        torch.cuda.synchronize()
+        for key in ("dis_loss", "gen_loss", "gp_loss"):
+            if f"{mode}.{key}" in z.files:
+                want = float(z[f"{mode}.{key}"])
+                got = float(r[key])
+                assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (mode, key, got, want)
+        p = {k: v.double().requires_grad_(True) for k, v in O.init_params(shape, int(z["seed"])).items()}
+        ro = O.gan_step(mode, torch.from_numpy(z["data"]), p, shape, disc, extra, str(z["loss_type"]),
+                        float(z["temperature"]), Ul, al, T, ctx, chunks, embed=embed, disc_on_embeds=on_emb)
+        # sampled ids are bit-exact under the injected noise (generated positions only)
+        ids = model.last_sampled_ids.cpu()
+        want_ids = torch.cat([c for c in torch.split(ro["ids"], T // chunks)], 0)
+        gen_rows = [i for i in range(T) if i >= ctx]
+        assert torch.equal(ids, want_ids[gen_rows]), (mode, (ids != want_ids[gen_rows]).sum().item())
+        owner = model.discriminator if mode == "dis_loss" else model.generator
+        named = dict(owner.named_parameters())
+        checked = 0
+        for k in z.files:
+            pre = f"{mode}.grad."
+            if not k.startswith(pre) or k[len(pre):] == "crit.out_layers.0.weight":
+                continue
+            nm = k[len(pre):]
+            want = torch.from_numpy(z[k]).double()
+            g = named[nm].grad
+            got = g.detach().cpu().double() if g is not None else torch.zeros_like(want)
+            err = (got - want).norm().item()
+            assert err <= 2e-2 * want.norm().item() + 2e-6, (mode, nm, err, want.norm().item())
+            checked += 1
+        assert checked >= 5
+        if mode == "dis_loss":
+            assert all(prm.grad is None for prm in model.generator.parameters())

@@ -1,0 +1,226 @@
+"""Drop-in replacement of the reference's ``model/transformer_gan.py`` (GAN training step) on the libtgan_b200 kernels.
+
+``TransformerGAN(cfg, vocab)`` keeps the reference's constructor, attributes (``generator``, ``discriminator``,
+``temperature``, ``cfg``, ``vocab``, ``vec_len``, ``ntokens``) and ``forward(data, target, reset_mems, train_loss,
+mems=None, status_vec=None, update_D0=False)`` -> ``{"mle", "gen_loss", "dis_loss", "mems"[, "gp_loss"]}``
+(transformer_gan.py:123-533), including its habit of running ``backward()`` inside ``forward`` and returning detached
+sums (:487-502, :515-531).
+
+What runs where
+  * generator: every one of the ``tgt_len - context_len`` single-token sampling steps (:299-334) is the CUDA engine
+    (``MemTransformerLM.forward_generate_gumbel`` -> tgan_* kernels, fused Gumbel-softmax straight-through sampler with
+    device-side noise); the soft one-hot chain that carries the gradient through time (:308-320) is the engine's
+    soft-input path (``tgan_gemm`` embedding + ``__dinput__`` gradient).
+  * discriminator: HuggingFace ``BertForSequenceClassification`` (third-party in the reference as well,
+    transformer_gan.py:23-30 / requirements.sh:12) with eager attention so the WGAN-GP double backward
+    (:203-230) works, or the CNN ``RelGAN_D`` (discriminator.py) -- library GEMM / conv work.
+Differences from the reference, all numerically neutral:
+  * in ``"dis_loss"`` mode the sampling loop runs under ``no_grad`` (the reference builds the 123-step graph and then
+    detaches it, :346-347);
+  * Gumbel noise comes from the device-side counter RNG unless ``gumbel_noise_source`` is set (parity tests inject the
+    reference's uniform draws); the GP interpolation weights likewise honour ``gp_alpha_source``.
+The PPO variants (``dis_D``, ``"classifier"`` loss, :184-201, :351-388) are listed as "next" in SURVEY.md section 8f and
+raise ``NotImplementedError`` here.
+"""
+import torch
+import torch.nn as nn
+
+from transformers import BertConfig, BertForMaskedLM, BertForSequenceClassification
+
+from discriminator import RelGAN_D
+from mem_transformer import MemTransformerLM
+from utils.helpers import get_losses
+
+
+class TransformerGAN(nn.Module):
+    def __init__(self, cfg, vocab):
+        super().__init__()
+        self.ntokens = len(vocab)
+        self.generator = MemTransformerLM(cfg, self.ntokens, vocab.vec_len)
+        dcfg = cfg.DISCRIMINATOR
+        if "ppo" in dcfg.CNN.loss_type or "ppo" in dcfg.BERT.loss_type:
+            raise NotImplementedError("PPO discriminator variants are not part of the accelerated path yet")
+        if dcfg.type == "bert":
+            self.discriminator = self.create_bert_model(dcfg.BERT.model_path, dcfg.BERT.loss_type, dcfg.BERT.model_type,
+                                                        dcfg.BERT.random_weights)
+            self.discriminator.unfreeze_idx = self.calculate_unfreeze_idx(cfg)
+        elif dcfg.type == "cnn":
+            self.discriminator = RelGAN_D(dcfg.CNN.embed_dim, dcfg.tgt_len, dcfg.CNN.num_rep, self.ntokens, 1, cfg=cfg)
+        else:
+            self.discriminator = None
+        self.cfg = cfg
+        self.temperature = 1
+        self.vocab = vocab
+        self.vec_len = vocab.vec_len
+        # test hooks: callables returning the uniform noise of the k-th sampling step ([1, B, V]) / the GP alphas ([B])
+        self.gumbel_noise_source = None
+        self.gp_alpha_source = None
+        self.last_sampled_ids = None
+
+    # ------------------------------------------------------------------------------------------------ discriminator
+    def create_bert_model(self, model_name_or_path, loss_type, model_type=None, random_weights=False):
+        """transformer_gan.py:535-566.  Eager attention: the fused SDPA kernels have no double backward (WGAN-GP)."""
+        config = BertConfig.from_pretrained(model_name_or_path, cache_dir=None)
+        config._attn_implementation = "eager"
+        if model_type == "bert_lm":
+            model = BertForSequenceClassification(config=config)
+            if not random_weights:
+                lm = BertForMaskedLM.from_pretrained(model_name_or_path, config=config, cache_dir=None)
+                model.bert = lm.bert
+        else:
+            if random_weights:
+                raise NotImplementedError
+            model = BertForSequenceClassification.from_pretrained(model_name_or_path, config=config, cache_dir=None)
+        return model.bert if loss_type == "mmd" else model
+
+    def calculate_unfreeze_idx(self, cfg):
+        """Indices (in ``named_parameters`` order) of the discriminator tensors that train (transformer_gan.py:568-585)."""
+        frozen_layers = cfg.DISCRIMINATOR.BERT.freeze_layers
+        idx, layers = [], []
+        for i, (name, _) in enumerate(self.discriminator.named_parameters()):
+            in_layer = name.startswith("bert.encoder.layer")
+            if in_layer:
+                layers.append(name.split(".")[3])
+            frozen = (name.startswith("bert.embeddings") and not cfg.DISCRIMINATOR.BERT.random_weights) or \
+                     (in_layer and name.split(".")[3] in frozen_layers)
+            if not frozen:
+                idx.append(i)
+        assert len(layers) >= len(frozen_layers)
+        return idx
+
+    def _bert_embedding_matrix(self):
+        return self.discriminator.bert.embeddings.word_embeddings.weight
+
+    def _bert_logit(self, inputs_embeds):
+        return self.discriminator(inputs_embeds=inputs_embeds)[0][:, 0]
+
+    def calc_gradient_penalty(self, real_data, fake_data, LAMBDA=10):
+        """WGAN-GP on interpolated one-hot rows (transformer_gan.py:203-230).  real / fake: [B, T, V'] float."""
+        B = real_data.shape[0]
+        if self.gp_alpha_source is not None:
+            alpha = self.gp_alpha_source(B).to(device=real_data.device, dtype=real_data.dtype).view(B, 1, 1)
+        else:
+            alpha = torch.rand([B, 1, 1], device=real_data.device, dtype=real_data.dtype)
+        x = (alpha * real_data + (1 - alpha) * fake_data).detach().requires_grad_(True)
+        if self.cfg.DISCRIMINATOR.type == "bert":
+            # the reference re-binds ``interpolates`` to the embedded rows before differentiating (:211-216): the
+            # penalised gradient is the one w.r.t. x^ E_bert ([B, T, hidden]), not w.r.t. the one-hot interpolate
+            x = torch.einsum("ve,bcv->bce", self._bert_embedding_matrix(), x)
+            d = self._bert_logit(x)
+        else:
+            d = self.discriminator(x)
+        (grad,) = torch.autograd.grad(d, x, grad_outputs=torch.ones_like(d), create_graph=True, retain_graph=True)
+        slopes = torch.sqrt(grad.reshape(B, -1).pow(2).sum(1) + 1e-12)
+        return ((slopes - 1.0) ** 2).mean() * LAMBDA
+
+    # ------------------------------------------------------------------------------------------------ sampling
+    def _one_hot(self, ids):
+        return torch.zeros(*ids.shape, self.ntokens, dtype=torch.float32, device=ids.device).scatter_(-1, ids[..., None], 1.0)
+
+    def _sample_chunks(self, data, with_grad):
+        """Yields ``(chunk_start, chunk_end, fake_chunk [len, B, V])`` for each of the ``sample_chunks_mem`` pieces of
+        the ``DISCRIMINATOR.tgt_len`` sequence (transformer_gan.py:273-349).  The first chunk starts with the
+        ``context_len`` real tokens as one-hot rows; the gradient chain inside a chunk is the soft one-hot fed back as
+        the next input, and each chunk's first generated token restarts from a hard id."""
+        dcfg, gen = self.cfg.DISCRIMINATOR, self.generator
+        mems = None
+        if dcfg.context_len > 1:
+            with torch.no_grad():
+                _, mems = gen.forward_generate(data[:dcfg.context_len - 1], mems)
+        chunk = dcfg.tgt_len // dcfg.sample_chunks_mem
+        seq, ids, step = [], [], 0
+        for cs in range(0, dcfg.tgt_len, chunk):
+            ce = min(cs + chunk, dcfg.tgt_len)
+            for pos in range(cs, ce):
+                if pos < dcfg.context_len:
+                    seq.append(self._one_hot(data[pos]))
+                    continue
+                prev = seq[-1]
+                hard = prev.argmax(dim=-1)[None, :].detach()
+                inp = hard if (dcfg.truncate_backprop or pos == cs or not with_grad) else prev[None]
+                noise = None if self.gumbel_noise_source is None else self.gumbel_noise_source(step, (1,) + tuple(prev.shape))
+                st, mems = gen.forward_generate_gumbel(inp, self.temperature, mems, noise=noise)
+                seq.append(st[0])
+                ids.append(st[0].detach().argmax(dim=-1))
+                step += 1
+            if len(seq) == chunk + 1:  # later chunks carry the previous chunk's last token only as the seed
+                seq = seq[1:]
+            yield cs, ce, torch.stack(seq, 0)
+            seq = [seq[-1].detach()]
+        self.last_sampled_ids = torch.stack(ids, 0) if ids else None
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, data, target, reset_mems, train_loss, mems=None, status_vec=None, update_D0=False):
+        out = {"mle": None, "gen_loss": None, "dis_loss": None, "mems": None}
+        if status_vec is not None or self.cfg.TRAIN.append_note_status:
+            raise NotImplementedError("append_note_status is off in every shipped config and not accelerated")
+        if "classifier" in train_loss:
+            raise NotImplementedError("the PPO 'classifier' phase is not part of the accelerated path yet")
+        if "mle" in train_loss:
+            out["mle"], out["mems"] = self.generator(data, target, reset_mems, mems)
+        if "gen" not in train_loss and "dis" not in train_loss:
+            return out
+        dcfg, gen = self.cfg.DISCRIMINATOR, self.generator
+        dtype_cfg = dcfg.BERT if dcfg.type == "bert" else dcfg.CNN
+        if dcfg.type not in ("bert", "cnn"):
+            raise NotImplementedError(dcfg.type)
+        train_dis = "dis" in train_loss
+        train_gen = "gen" in train_loss and not train_dis
+        use_gp = train_dis and "gp" in dtype_cfg.loss_type
+        share = dcfg.batch_chunk * dcfg.sample_chunks_mem
+        cached = (gen.tgt_len, gen.mem_len)
+        gen.reset_length(1, dcfg.mem_len)
+        gen.detach_mems_grad = False
+        g_total = d_total = gp_total = 0
+        try:
+            sampler = self._sample_chunks(data, with_grad=train_gen)
+            while True:
+                if train_gen:
+                    item = next(sampler, None)
+                else:
+                    with torch.no_grad():
+                        item = next(sampler, None)
+                if item is None:
+                    break
+                cs, ce, fake = item
+                if train_dis:
+                    fake = fake.detach()
+                real = data[cs:ce].transpose(0, 1)          # [B, len] ids
+                fake_bt = fake.transpose(0, 1)              # [B, len, V]
+                if dcfg.type == "bert":
+                    # BERT's vocabulary has one extra (MASK) id: pad the sampled rows with a zero column (:396-399)
+                    fake_bt = torch.cat([fake_bt, fake_bt.new_zeros(*fake_bt.shape[:-1], 1)], -1)
+                    E = self._bert_embedding_matrix()
+                    d_real = self._bert_logit(E[real])
+                    d_fake = self._bert_logit(torch.einsum("ve,bcv->bce", E, fake_bt))
+                    real_1h = None
+                    if use_gp:
+                        real_1h = torch.zeros(*real.shape, self.ntokens + 1, device=real.device).scatter_(-1, real[..., None], 1.0)
+                else:
+                    real_1h = self._one_hot(real)
+                    d_real = self.discriminator(real_1h)
+                    d_fake = self.discriminator(fake_bt)
+                g_loss, d_loss = get_losses(d_real, d_fake, dtype_cfg.loss_type)
+                gp = self.calc_gradient_penalty(real_1h, fake_bt) if use_gp else None
+                keep = (lambda t: t.detach()) if dcfg.backprop_outside else (lambda t: t)
+                g_total = g_total + keep(g_loss)
+                d_total = d_total + keep(d_loss)
+                if gp is not None:
+                    gp_total = gp_total + keep(gp)
+                if dcfg.backprop_outside:  # the reference's name for "backward happens here, inside forward" (:487-502)
+                    if train_gen or ("gen" in train_loss and not train_dis):
+                        (g_loss.float().mean() * dcfg.gen_loss_factor / share).backward()
+                    if train_dis:
+                        (d_loss.float().mean() * dcfg.dis_loss_factor / share).backward()
+                        if gp is not None:
+                            (gp.float().mean() * dcfg.dis_loss_factor / share).backward()
+        finally:
+            gen.detach_mems_grad = True
+            gen.reset_length(*cached)
+        if train_dis:
+            out["dis_loss"] = dcfg.dis_loss_factor * d_total / dcfg.sample_chunks_mem
+            if use_gp:
+                out["gp_loss"] = dcfg.dis_loss_factor * gp_total / dcfg.sample_chunks_mem
+        else:
+            out["gen_loss"] = dcfg.gen_loss_factor * g_total / dcfg.sample_chunks_mem
+        return out
