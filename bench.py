@@ -70,28 +70,6 @@ def init_like_train_py(model, seed):
             p.data.copy_(0.01 * torch.randn(p.shape, generator=g))
 
 
-def flatten_params(model):
-    """Move every parameter into one flat fp32 buffer (views), with a matching flat gradient buffer, so the
-    gradient all-reduce, the norm clip and Adam are one kernel each."""
-    params = []
-    seen = set()
-    for p in model.parameters():
-        if id(p) not in seen:
-            seen.add(id(p))
-            params.append(p)
-    n = sum(p.numel() for p in params)
-    flat = torch.empty(n, dtype=torch.float32, device=params[0].device)
-    grad = torch.zeros_like(flat)
-    off = 0
-    for p in params:
-        k = p.numel()
-        flat[off:off + k].copy_(p.data.view(-1))
-        p.data = flat[off:off + k].view_as(p)
-        p.grad = grad[off:off + k].view_as(p)
-        off += k
-    return flat, grad
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -248,11 +226,11 @@ def main():
     model = model.to(dev).train()
     model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     model.kernel_impl = args.kernel_impl
-    flat, fgrad = flatten_params(model)
-    m_buf, v_buf = torch.zeros_like(flat), torch.zeros_like(flat)
-    gnorm = torch.zeros(1, device=dev)
+    from tgan_b200 import dp
+    fp = dp.FlatParams(model.parameters())  # one flat parameter / gradient buffer: all-reduce, clip and Adam are one call each
     lr = WORK["lr"] / world  # train.py:392 divides lr by the GPU count
-    gen = torch.Generator().manual_seed(1111 + 1000 * rank)  # train.py:224
+    opt = dp.FusedClipAdam(fp, lr, clip=WORK["clip"], world=world)
+    gen = torch.Generator().manual_seed(dp.rank_seed(1111, rank))  # train.py:224
     n_chunks = args.batch_chunk
     pin = lambda t: t.pin_memory()
     host_data = [pin(torch.randint(2, V, (Q, Bc), generator=gen)) for _ in range(4 * n_chunks)]
@@ -278,13 +256,7 @@ def main():
             l = loss.mean() / n_chunks  # train.py:891-892
             l.backward()
             total = l.detach() if total is None else total + l.detach()
-        if world > 1:
-            dist.all_reduce(fgrad)  # one all-reduce per optimizer step over NVLink; 1/world folded into grad_scale
-        gnorm.zero_()
-        L.sumsq(fgrad, fgrad.numel(), gnorm)
-        L.adam_step(flat, fgrad, m_buf, v_buf, flat.numel(), lr, 0.9, 0.999, 1e-8, 0.0, step_no[0], gnorm,
-                    WORK["clip"], 1.0 / world)
-        fgrad.zero_()
+        opt.step()  # one NCCL all-reduce of the flat gradient per optimizer step, then fused clip + Adam
         # the flat buffer changed in place: tell the engine to re-pack (parameter views share its version counter)
         model._engine._packed_version = None
         if e2e:

@@ -153,11 +153,13 @@ int tgan_convert(int dtype_src, const void* src, int64_t lds, int dtype_dst, voi
  * element (r, c) of the source goes to padded (r', c') with r' = (r / row_group) * row_group_pad + r % row_group
  * (head padding d_head -> 64), same for columns; with transpose the destination index is c' * ld_dst + r'.
  * Destinations must be pre-zeroed once (pad lanes stay zero).
- * tgan_unpack_grads does the inverse for fp32 gradients: *src_ptr[r, c] = padded[r', c'] (never transposed).  */
+ * tgan_unpack_grads does the inverse for fp32 gradients: *src_ptr[r, c] (+)= padded[r', c'] (never transposed); with
+ * `accumulate` it adds into the destination, i.e. straight into the caller's .grad tensors (train.py accumulates
+ * `batch_chunk` micro-batches before each optimizer step).                                                    */
 int tgan_pack_params(int dtype, void* packed_mat, float* packed_vec, const int64_t* desc, int n_desc,
                      int64_t max_elems, void* stream);
 int tgan_unpack_grads(const float* padded_mat, const float* padded_vec, const int64_t* desc, int n_desc,
-                      int64_t max_elems, void* stream);
+                      int64_t max_elems, int accumulate, void* stream);
 
 /* ---- optimizer side (next-row): fused grad-norm clip + Adam over flat buffers ----------------*/
 int tgan_sumsq(const float* x, int64_t n, float* out /* 1 float, accumulated */, void* stream);

@@ -426,7 +426,7 @@ __global__ void pack_kernel(T* __restrict__ mat, float* __restrict__ vec, const 
 }
 
 __global__ void unpack_kernel(const float* __restrict__ mat, const float* __restrict__ vec,
-                              const int64_t* __restrict__ desc) {
+                              const int64_t* __restrict__ desc, int accumulate) {
     const int64_t* d = desc + 12 * blockIdx.y;
     float* dst = reinterpret_cast<float*>(d[0]);
     const int64_t off = d[1], rows = d[2], cols = d[3], ld = d[4], rg = d[5], rgp = d[6], cg = d[7], cgp = d[8];
@@ -436,7 +436,8 @@ __global__ void unpack_kernel(const float* __restrict__ mat, const float* __rest
         int64_t r = e / cols, c = e % cols;
         int64_t rp = (r / rg) * rgp + r % rg, cp = (c / cg) * cgp + c % cg;
         int64_t o = off + rp * ld + cp;
-        dst[e] = is_vec ? vec[o] : mat[o];
+        const float v = is_vec ? vec[o] : mat[o];
+        dst[e] = accumulate ? dst[e] + v : v;
     }
 }
 
@@ -675,10 +676,10 @@ extern "C" int tgan_pack_params(int dtype, void* packed_mat, float* packed_vec, 
 }
 
 extern "C" int tgan_unpack_grads(const float* padded_mat, const float* padded_vec, const int64_t* desc, int n_desc,
-                                 int64_t max_elems, void* stream) {
+                                 int64_t max_elems, int accumulate, void* stream) {
     if (n_desc <= 0) return 0;
     dim3 grid(grid_for(max_elems, 256) > 64 ? 64 : grid_for(max_elems, 256), n_desc);
-    unpack_kernel<<<grid, 256, 0, ST>>>(padded_mat, padded_vec, desc);
+    unpack_kernel<<<grid, 256, 0, ST>>>(padded_mat, padded_vec, desc, accumulate);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;

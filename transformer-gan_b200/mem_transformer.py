@@ -102,6 +102,7 @@ class _TxlFunction(torch.autograd.Function):
                            n_pred=target.size(0) if mode == "mle" else None, save_for_backward=need_grad)
         model._new_mems = ectx.new_mems
         ctx.ectx, ctx.model, ctx.mode, ctx.names = ectx, model, mode, names
+        ctx.params = params
         ctx.soft_in = inp.is_floating_point()
         T, B, V = ectx.T, ectx.B, model.n_token
         if mode == "mle":
@@ -127,22 +128,29 @@ class _TxlFunction(torch.autograd.Function):
             raise RuntimeError("backward through a generator call that did not save activations")
         T, B, V = ectx.T, ectx.B, model.n_token
         gout = gout.contiguous().float()
+        # Parameter gradients are ACCUMULATED straight into ``p.grad`` by one unpack kernel (what autograd's
+        # AccumulateGrad nodes would do with 72 separate adds); the Function therefore returns None for them.
+        targets = {}
+        for n, prm in zip(ctx.names, ctx.params):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
+            targets[n] = prm.grad
         if mode == "mle":
-            grads = eng.backward(ectx, dnll=gout, need_dinput=ctx.soft_in)
+            grads = eng.backward(ectx, dnll=gout, need_dinput=ctx.soft_in, grad_targets=targets)
         else:
             g = gout.view(T * B, V)
             if mode == "gumbel":
                 dl = torch.empty_like(g)
                 L.gumbel_st_bwd(ctx.y, g, ctx.tau, dl, T * B, V)
                 g = dl
-            grads = eng.backward(ectx, dlogits32=g, need_dinput=ctx.soft_in)
+            grads = eng.backward(ectx, dlogits32=g, need_dinput=ctx.soft_in, grad_targets=targets)
         dinp = None
         if ctx.soft_in:
             d = grads["__dinput__"]
             dinp = torch.empty(ectx.Q * B, V, dtype=torch.float32, device=eng.device)
             L.convert(d, d.stride(0), dinp, V, ectx.Q * B, V, V)
             dinp = dinp.view(ectx.Q, B, V)
-        return (None, None, dinp, None, None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+        return (None, None, dinp, None, None, None, None, None, None) + (None,) * len(ctx.names)
 
 
 class MemTransformerLM(nn.Module):

@@ -489,10 +489,12 @@ class TxlEngine:
 
     # -- backward -----------------------------------------------------------------------------------------
     def backward(self, ctx: _Ctx, dnll: Optional[torch.Tensor] = None, dlogits32: Optional[torch.Tensor] = None,
-                 need_dinput: bool = False) -> Dict[str, torch.Tensor]:
+                 need_dinput: bool = False, grad_targets: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Gradients (reference layout, fp32) of sum(nll * dnll) [+ sum(logits * dlogits32)] w.r.t. every
-        generator parameter.  With need_dinput the gradient w.r.t. the soft one-hot input rows is returned
-        under the key '__dinput__' (fp32 [Q*B, VP])."""
+        generator parameter.  With ``grad_targets`` ({state_dict name: fp32 tensor}, e.g. the parameters' ``.grad``)
+        the gradients are ACCUMULATED into those tensors by one kernel (no per-tensor allocation, no autograd
+        accumulate nodes); otherwise fresh tensors are returned.  With need_dinput the gradient w.r.t. the soft
+        one-hot input rows is returned under the key '__dinput__' (fp32 [Q*B, VP])."""
         d, lay, dt = self.d, self.layout, self.dtype
         DP, NH, DIP, VP, D = d.DP, d.NH, d.DIP, d.VP, d.d_model
         Q, B, M, K, cid = ctx.Q, ctx.B, ctx.M, ctx.K, ctx.cid
@@ -611,15 +613,44 @@ class TxlEngine:
                 L.gemm(dx, self.pmat, dsoft, M=R, N=d.n_token, K=DP, ldb=eld, b_off=eoff, alpha=math.sqrt(D), impl=impl)
                 out["__dinput__"] = dsoft
         # ---- unpack to reference-layout gradients
-        grads = {}
-        rows = []
-        for (ref, name, kind, *_), urow in zip(lay.reference_map(), self._unpack_rows):
-            g = torch.empty(self._grad_shapes[ref], dtype=torch.float32, device=self.device)
-            grads[ref] = g
-            rows.append([g.data_ptr()] + urow[1:])
-        desc = torch.tensor(rows, dtype=torch.int64, device=self.device)
-        L.unpack_grads(gm, gv, desc, len(rows), self._max_elems)
+        if grad_targets is not None:
+            desc = self._unpack_desc_for(grad_targets)
+            L.unpack_grads(gm, gv, desc, desc.shape[0], self._max_elems, accumulate=True)
+            grads = {}
+        else:
+            grads = {}
+            rows = []
+            for (ref, name, kind, *_), urow in zip(lay.reference_map(), self._unpack_rows):
+                g = torch.empty(self._grad_shapes[ref], dtype=torch.float32, device=self.device)
+                grads[ref] = g
+                rows.append([g.data_ptr()] + urow[1:])
+            desc = self._stage_desc(rows)
+            L.unpack_grads(gm, gv, desc, len(rows), self._max_elems)
+            out["__desc__"] = desc  # keep the descriptor table alive until the kernel ran
         ctx.layers = None  # release activations
         out.update(grads)
-        out["__desc__"] = desc  # keep the descriptor table alive until the kernel ran
         return out
+
+    def _stage_desc(self, rows) -> torch.Tensor:
+        """Descriptor table -> device through pinned memory (an asynchronous copy: no host synchronisation)."""
+        host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+        dev = torch.empty_like(host, device=self.device)
+        dev.copy_(host, non_blocking=True)
+        self._desc_keepalive = getattr(self, "_desc_keepalive", [])[-7:] + [(host, dev)]
+        return dev
+
+    def _unpack_desc_for(self, targets: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Cached unpack table whose destinations are the given gradient tensors (rebuilt only when they move)."""
+        key = tuple(targets[ref].data_ptr() for ref, *_ in self.layout.reference_map())
+        cache = getattr(self, "_unpack_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        rows = []
+        for (ref, name, kind, *_), urow in zip(self.layout.reference_map(), self._unpack_rows):
+            t = targets[ref]
+            if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != self._grad_shapes[ref]:
+                raise L.TganError(f"gradient target for {ref} must be a contiguous fp32 tensor of the parameter's shape")
+            rows.append([t.data_ptr()] + urow[1:])
+        dev = self._stage_desc(rows)
+        self._unpack_cache = (key, dev)
+        return dev

@@ -55,7 +55,7 @@ _SIGS = {
     "tgan_colsum": [I, P, L, P, I, I, P],
     "tgan_convert": [I, P, L, I, P, L, L, I, I, P],
     "tgan_pack_params": [I, P, P, P, I, L, P],
-    "tgan_unpack_grads": [P, P, P, I, L, P],
+    "tgan_unpack_grads": [P, P, P, I, L, I, P],
     "tgan_sumsq": [P, L, P, P],
     "tgan_adam_step": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P],
 }
@@ -211,9 +211,9 @@ def pack_params(packed_mat, packed_vec, desc, n_desc, max_elems):
           desc.data_ptr(), n_desc, max_elems, _stream())
 
 
-def unpack_grads(padded_mat, padded_vec, desc, n_desc, max_elems):
+def unpack_grads(padded_mat, padded_vec, desc, n_desc, max_elems, accumulate=False):
     _call("tgan_unpack_grads", padded_mat.data_ptr(), padded_vec.data_ptr(), desc.data_ptr(), n_desc, max_elems,
-          _stream())
+          int(accumulate), _stream())
 
 
 def sumsq(x, n, out):
