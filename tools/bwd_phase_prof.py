@@ -33,8 +33,8 @@ L._lib.tgan_debug_bwd_prof.argtypes = [ctypes.c_void_p]
 L._lib.tgan_debug_bwd_prof.restype = ctypes.c_int
 rc = L._lib.tgan_debug_bwd_prof(buf)
 names = ["prologue", "g_pull", "pairA", "s_wait+ld", "ring+exp", "pairB", "dp_wait+ld", "compute", "flush_keys", "flush_dr",
-         "publish", "epilogue"]
-tot = sum(buf[:12])
+         "publish", "epilogue", "wait kdone", "wait rdone"]
+tot = sum(buf[:12])  # 12, 13 are sub-intervals of flush_keys / flush_dr
 print("rc", rc, "total clk", tot, "(warp 0 lane 0 of CTA 200; 18 tiles)")
 for n, v in zip(names, buf):
     print(f"{n:12s} {v:9d} {100.0*v/tot:5.1f}%   per tile {v/18:8.0f}")

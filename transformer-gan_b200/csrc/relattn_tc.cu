@@ -6,6 +6,8 @@
 //               32-column half w >> 2 of every 64-wide tile, so each query row is served by two threads.
 //   warp  8     one thread issues every tcgen05.mma
 //   warp  9     K / V tile loads (TMA)        warp 10  R chunks for the G product        warp 11  R chunks for dqR
+//   warp 12     dK / dV tile stores (TMA): the tiles are staged in shared memory and written by the copy engine, so the
+//               1.3 MB-strided key rows never go through the SIMT load/store pipe
 // Per 64-key tile t (TMEM columns in brackets):
 //     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO' V_t^T
 //   row threads:  P = exp2(S2 - lse2),  dS = P (keep(dP) - delta),  P~ = keep(P)   -> bf16 tiles in shared memory;
@@ -31,7 +33,7 @@ constexpr int BQ = 128;      // query rows per CTA
 constexpr int BJ = 64;       // keys per tile
 constexpr int RING_COLS = 192;
 constexpr int ROW_WARPS = 8;
-constexpr int NTHREADS = 32 * (ROW_WARPS + 4);
+constexpr int NTHREADS = 32 * (ROW_WARPS + 5);
 
 constexpr int B_OFF_QU = 0;
 constexpr int B_OFF_QV = B_OFF_QU + 16384;
@@ -47,7 +49,7 @@ constexpr int B_OFF_DRING = B_OFF_GRING + RING_COLS * BQ * 2; // bf16 [16 row gr
 constexpr int DR_GROUP = RING_COLS * 16 + 32;                 // byte stride between 8-row groups (+32: bank spread)
 constexpr int DRING_BYTES = 16 * DR_GROUP;
 constexpr int B_OFF_BAR = B_OFF_DRING + DRING_BYTES;
-constexpr int B_NUM_BARS = 24;
+constexpr int B_NUM_BARS = 26;
 constexpr int BWD_SMEM = B_OFF_BAR + B_NUM_BARS * 8 + 16 + 1024;
 static_assert(BWD_SMEM <= 232448, "shared memory budget");
 constexpr int TB_S = 0, TB_G = 64, TB_DP = 128, TB_DQK = 192, TB_DQR = 256, TB_DK = 320, TB_DV = 384, TB_DR = 448;
@@ -69,9 +71,9 @@ struct BwdParams {
 
 #ifdef TGAN_PROFILE
 __device__ long long g_bwd_prof[16];
-#define PROF_DECL long long _pt = clock64(); long long _acc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_DECL long long _pt = clock64(); long long _acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF(i) { const long long _n = clock64(); _acc[i] += _n - _pt; _pt = _n; }
-#define PROF_DUMP() if (blockIdx.x == 200 && threadIdx.x == 0) { for (int _i = 0; _i < 13; ++_i) g_bwd_prof[_i] = _acc[_i]; }
+#define PROF_DUMP() if (blockIdx.x == 200 && threadIdx.x == 0) { for (int _i = 0; _i < 16; ++_i) g_bwd_prof[_i] = _acc[_i]; }
 __device__ long long g_bwd_prof_mma[16];
 #define PROF_DUMP_MMA() if (blockIdx.x == 200) { for (int _i = 0; _i < 13; ++_i) g_bwd_prof_mma[_i] = _acc[_i]; }
 #else
@@ -91,7 +93,8 @@ __device__ __forceinline__ void pair_sync(int quarter) {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                      const __grid_constant__ CUtensorMap tmR, BwdParams p) {
+                      const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmDK,
+                      const __grid_constant__ CUtensorMap tmDV, BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     PROF_DECL
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -106,8 +109,8 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                    rg_full = v_empty + 8, rg_empty = rg_full + 16, rd_full = rg_empty + 16, rd_empty = rd_full + 8,
                    s_full = rd_empty + 8, s_empty = s_full + 8, dp_full = s_empty + 8, dp_empty = dp_full + 8,
                    g_full = dp_empty + 8, g_empty = g_full + 8, p_full = g_empty + 8, kdone = p_full + 8,
-                   dr_empty = kdone + 8, rdone = dr_empty + 8;
-    const uint32_t sTmemPtr = rdone + 8;
+                   dr_empty = kdone + 8, rdone = dr_empty + 8, ks_full = rdone + 8, ks_empty = ks_full + 8;
+    const uint32_t sTmemPtr = ks_empty + 8;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,6 +136,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         mbar_init(dp_full, 1); mbar_init(dp_empty, ROW_WARPS);
         mbar_init(g_full, 1); mbar_init(g_empty, ROW_WARPS);
         mbar_init(p_full, ROW_WARPS); mbar_init(kdone, 1); mbar_init(dr_empty, ROW_WARPS); mbar_init(rdone, 1);
+        mbar_init(ks_full, ROW_WARPS); mbar_init(ks_empty, 1);
         fence_barrier_init();
     }
     if (warp == ROW_WARPS) tmem_alloc(sTmemPtr, TM_COLS);
@@ -221,6 +225,19 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 mbar_expect_tx(rd_full, 8192);
                 tma_load_2d(sRD, &tmR, rd_full, n * HS, P0 + BJ * cc);
             }
+        }
+    } else if (warp == ROW_WARPS + 4) {
+        // =========================== dK / dV tile stores ===========================
+        if (lane == 0) {
+            for (int tt = 0; tt < nt; ++tt) {
+                mbar_wait(ks_full, tt & 1);  // all row warps have staged tile tt's dK (PT + 0) and dV (PT + 8 KB)
+                tma_store_3d(&tmDK, sPT, n * HS, b, (t_lo + tt) * BJ);
+                tma_store_3d(&tmDV, sPT + 8192, n * HS, b, (t_lo + tt) * BJ);
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(ks_empty);
+            }
+            tma_store_wait_all();
         }
     } else if (warp == ROW_WARPS) {
         // =========================== MMA issuer ===========================
@@ -353,7 +370,9 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         uint8_t* drow = gbase + B_OFF_DRING + (ii >> 3) * DR_GROUP + (ii & 7) * 2;  // ring entry (p, ii) at drow + 16 p
         // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * quarter + lane
         auto flush_dr = [&](int cc) {
+            PROF(15)
             mbar_wait(rdone, cc & 1);
+            PROF(13)
             tcgen05_fence_after();
             uint32_t v[32];
             tmem_ld32(tmem_base + TB_DR + hc + lane_off, v);
@@ -370,38 +389,41 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                                __uint_as_float(v[4 * c + 2]) * p.scale, __uint_as_float(v[4 * c + 3]) * p.scale);
             }
         };
-        // key-side results of tile tk (M = 64 layout: row r = 16 * quarter + lane, lanes 0..15)
-        auto flush_keys = [&](int tk) {
+        // key-side results of tile tk (M = 64 layout: row r = 16 * quarter + lane, lanes 0..15) -> bf16 tiles staged in
+        // the (currently free) P~ buffer, in the swizzled layout the TMA store expects; warp 12 writes them out
+        auto stage_keys = [&](int tk) {
+            PROF(15)
             mbar_wait(kdone, tk & 1);
+            PROF(12)
             tcgen05_fence_after();
             uint32_t a[32];
-            const int j = (t_lo + tk) * BJ + 16 * quarter + lane;
-            const bool wr = lane < 16 && j < p.K;
+            const int r = 16 * quarter + lane;
             tmem_ld32(tmem_base + TB_DK + hc + lane_off, a);
             tmem_ld_wait();
-            if (wr) {
-                bf16* dst = p.dk + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
+            if (lane < 16) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float f[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * p.scale;
-                    store8(dst + 8 * c, f);
+                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + sw128_off(r, 4 * half + c)), f);
                 }
             }
             tmem_ld32(tmem_base + TB_DV + hc + lane_off, a);
             tmem_ld_wait();
-            if (wr) {
-                bf16* dst = p.dv + ((int64_t)j * p.B + b) * p.lddkv + n * HS + hc;
+            if (lane < 16) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float f[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
-                    store8(dst + 8 * c, f);
+                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + 8192 + sw128_off(r, 4 * half + c)), f);
                 }
             }
             tcgen05_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ks_full);
         };
 #pragma unroll 1
         for (int tt = 0; tt < nt; ++tt) {
@@ -476,6 +498,9 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(dp_empty);
             PROF(6)
+            // the previous tile's dK / dV leave through the P~ buffer (free until this tile publishes) and the copy engine
+            if (tt > 0) stage_keys(tt - 1);
+            PROF(8)
             // 4. P~ = keep(P), dS = P (keep(dP) - delta), packed to bf16 pairs in registers
             uint32_t ptw[16], dsw[16];
             {
@@ -497,14 +522,12 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     dsw[c] = *reinterpret_cast<uint32_t*>(&d);
                 }
             }
-            // 5. drain the previous tile: its dK / dV (frees the P~ / dS buffers) and its dR chunk (frees the ring
-            //    third that this tile's scatter is about to reuse).  Those MMAs ran while this tile was being computed.
+            // 5. drain the previous tile's dR chunk (frees the ring third that this tile's scatter is about to reuse)
             PROF(7)
             if (tt > 0) {
-                flush_keys(tt - 1);
-                PROF(8)
                 flush_dr(tt - 1);
                 PROF(9)
+                mbar_wait(ks_empty, (tt - 1) & 1);  // the TMA store has finished reading the P~ buffer
             }
             if (tt + 2 >= nt) {
                 // chunk tt+2 is one of the two tail chunks whose upper positions are never written: clear this thread's
@@ -536,7 +559,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             if (lane == 0) mbar_arrive(p_full);
             PROF(10)
         }
-        flush_keys(nt - 1);
+        stage_keys(nt - 1);
         for (int cc = nt - 1; cc < nc; ++cc) flush_dr(cc);
         // dq = (dqK + dqR) / sqrt(d); du / dvb = column sums over the query rows
         {
@@ -605,6 +628,11 @@ int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v
     if (rc) return rc;
     rc = tc::make_tmap_2d(&tmR, r, (uint64_t)K, (uint64_t)N * HS, (uint64_t)ldr, BJ, HS);
     if (rc) return rc;
+    CUtensorMap tmDK, tmDV;
+    rc = tc::make_tmap_3d(&tmDK, dk, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)lddkv, (uint64_t)B * lddkv, HS, 1, BJ);
+    if (rc) return rc;
+    rc = tc::make_tmap_3d(&tmDV, dv, (uint64_t)N * HS, (uint64_t)B, (uint64_t)K, (uint64_t)lddkv, (uint64_t)B * lddkv, HS, 1, BJ);
+    if (rc) return rc;
     BwdParams p;
     p.q = (const bf16*)q; p.ldq = ldq; p.out = (const bf16*)out; p.dout = (const bf16*)dout; p.ldo = ldo; p.lse = lse;
     p.u = u; p.vb = vb; p.reset = reset; p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddkv = lddkv;
@@ -620,7 +648,7 @@ int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v
         attr_set = true;
     }
     TGAN_CUDA_OK(cudaMemset2DAsync(dr, lddr * sizeof(float), 0, (size_t)N * HS * sizeof(float), K, st));
-    relattn_bwd_tc_kernel<<<B * N, NTHREADS, BWD_SMEM, st>>>(tmK, tmV, tmR, p);
+    relattn_bwd_tc_kernel<<<B * N, NTHREADS, BWD_SMEM, st>>>(tmK, tmV, tmR, tmDK, tmDV, p);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
