@@ -113,43 +113,78 @@ __global__ void pos_emb_kernel(const float* __restrict__ inv_freq, T* __restrict
 
 // ------------------------------------------------------------------------------------------------------------
 // LayerNorm forward (warp per row; z fp32 -> y T)                   mem_transformer.py:58, 255
+// Each lane owns the 4-column groups lane*4 + 128*u: the row is read ONCE with 16-byte loads, kept in registers for
+// the mean / variance / normalise passes, and written with 8- (bf16) or 16-byte (fp32) stores.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
+__device__ __forceinline__ void load4(const float* p, float* o) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float* o) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+    o[0] = f0.x; o[1] = f0.y; o[2] = f1.x; o[3] = f1.y;
+}
+__device__ __forceinline__ void store4(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float* v) {
+    uint2 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]);
+    h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
+template <typename T, int MAXU>
 __global__ void ln_fwd_kernel(const float* __restrict__ z, int64_t ldz, T* __restrict__ y, int64_t ldy,
                               const float* __restrict__ gamma, const float* __restrict__ beta,
                               float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, int DP) {
     int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* zr = z + (int64_t)row * ldz;
+    float v[MAXU][4];
     float s = 0.f;
-    for (int c = lane * 4; c < D; c += 128) {
-        float4 v = *reinterpret_cast<const float4*>(zr + c);
-        s += v.x + (c + 1 < D ? v.y : 0.f) + (c + 2 < D ? v.z : 0.f) + (c + 3 < D ? v.w : 0.f);
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+        const int c = lane * 4 + 128 * u;
+        if (c < DP) {
+            load4(zr + c, v[u]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { v[u][t] = c + t < D ? v[u][t] : 0.f; s += v[u][t]; }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[u][t] = 0.f;
+        }
     }
-    float mu = warp_sum(s) / D;
+    const float mu = warp_sum(s) / D;
     float q = 0.f;
-    for (int c = lane * 4; c < D; c += 128) {
-        float4 v = *reinterpret_cast<const float4*>(zr + c);
-        float a = v.x - mu, b = v.y - mu, cc = v.z - mu, d = v.w - mu;
-        q += a * a + (c + 1 < D ? b * b : 0.f) + (c + 2 < D ? cc * cc : 0.f) + (c + 3 < D ? d * d : 0.f);
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+        const int c = lane * 4 + 128 * u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const float d = c + t < D ? v[u][t] - mu : 0.f; q += d * d; }
     }
-    float rs = rsqrtf(warp_sum(q) / D + 1e-5f);
+    const float rs = rsqrtf(warp_sum(q) / D + 1e-5f);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
     T* yr = y + (int64_t)row * ldy;
-    for (int c0 = lane * 8; c0 < DP; c0 += 256) {
-        float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            int c = c0 + t;
-            o[t] = c < D ? (zr[c] - mu) * rs * gamma[c] + beta[c] : 0.f;
+    for (int u = 0; u < MAXU; ++u) {
+        const int c = lane * 4 + 128 * u;
+        if (c < DP) {
+            float g[4], bt[4], o[4];
+            load4(gamma + c, g); load4(beta + c, bt);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] = c + t < D ? (v[u][t] - mu) * rs * g[t] + bt[t] : 0.f;
+            store4(yr + c, o);
         }
-        store8(yr + c0, o);
     }
 }
 
-// LayerNorm backward.  One warp per row; dgamma/dbeta partials are reduced per block in shared memory and
-// added to global memory with one atomic per column per block.
-template <typename T, int MAXC>
+// LayerNorm backward.  One warp per row (same column ownership as the forward); dgamma/dbeta partials are reduced
+// per block in shared memory and added to global memory with one atomic per column per block.
+template <typename T, int MAXU>
 __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const float* __restrict__ z, int64_t ldz,
                               const float* __restrict__ gamma, const float* __restrict__ mean,
                               const float* __restrict__ rstd, T* __restrict__ dz, int64_t lddz,
@@ -162,65 +197,77 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const floa
     for (int c = threadIdx.x; c < 2 * DP; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float pg[MAXC], pb[MAXC];  // per-lane partials for columns lane*8 + 256*u + t
+    const uint32_t key = dropout_key(seed, site);
+    float pg[MAXU][4], pb[MAXU][4], gm[MAXU][4];
 #pragma unroll
-    for (int t = 0; t < MAXC; ++t) pg[t] = pb[t] = 0.f;
+    for (int u = 0; u < MAXU; ++u) {
+        const int c = lane * 4 + 128 * u;
+        if (c < DP) load4(gamma + c, gm[u]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { pg[u][t] = pb[u][t] = 0.f; if (c >= DP) gm[u][t] = 0.f; }
+    }
     const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
     for (int row = r_begin + warp; row < r_end; row += WPB) {
         const T* dyr = dy + (int64_t)row * lddy;
         const float* zr = z + (int64_t)row * ldz;
         const float mu = mean[row], rs = rstd[row];
-        float g[MAXC], xh[MAXC];
+        float g[MAXU][4], xh[MAXU][4];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int u = 0; u < MAXC / 8; ++u) {
-            int c0 = lane * 8 + 256 * u;
-            if (c0 < DP) {
-                float d8[8];
-                load8(dyr + c0, d8);
+        for (int u = 0; u < MAXU; ++u) {
+            const int c = lane * 4 + 128 * u;
+            if (c < DP) {
+                float d4[4], z4[4];
+                load4(dyr + c, d4);
+                load4(zr + c, z4);
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    int c = c0 + t;
-                    float x = c < D ? (zr[c] - mu) * rs : 0.f;
-                    float dv = c < D ? d8[t] : 0.f;
-                    pg[u * 8 + t] += dv * x;
-                    pb[u * 8 + t] += dv;
-                    float gg = c < D ? dv * gamma[c] : 0.f;
-                    g[u * 8 + t] = gg; xh[u * 8 + t] = x;
+                for (int t = 0; t < 4; ++t) {
+                    const bool ok = c + t < D;
+                    const float x = ok ? (z4[t] - mu) * rs : 0.f;
+                    const float dv = ok ? d4[t] : 0.f;
+                    pg[u][t] += dv * x;
+                    pb[u][t] += dv;
+                    const float gg = dv * gm[u][t];
+                    g[u][t] = gg; xh[u][t] = x;
                     s1 += gg; s2 += gg * x;
                 }
             } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) { g[u * 8 + t] = 0.f; xh[u * 8 + t] = 0.f; }
+                for (int t = 0; t < 4; ++t) { g[u][t] = 0.f; xh[u][t] = 0.f; }
             }
         }
         s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
 #pragma unroll
-        for (int u = 0; u < MAXC / 8; ++u) {
-            int c0 = lane * 8 + 256 * u;
-            if (c0 < DP) {
-                float o[8], od[8];
-                uint32_t keep = (thresh && dzd) ? dropout_keep8(seed, site, (uint64_t)row * lddd + c0, thresh) : 0xffu;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    int c = c0 + t;
-                    float v = c < D ? rs * (g[u * 8 + t] - s1 - xh[u * 8 + t] * s2) : 0.f;
-                    o[t] = v;
-                    od[t] = ((keep >> t) & 1) ? v * drop_scale : 0.f;
+        for (int u = 0; u < MAXU; ++u) {
+            const int c = lane * 4 + 128 * u;
+            if (c < DP) {
+                float o[4], od[4];
+                uint32_t keep = 0xfu;
+                if (thresh && dzd) {
+                    const uint64_t e0 = (uint64_t)row * lddd + c;  // multiple of 4: two hash pairs
+                    const uint32_t h0 = dropout_hash_pair(key, e0 >> 1), h1 = dropout_hash_pair(key, (e0 >> 1) + 1);
+                    keep = (uint32_t)((h0 & 0xffffu) >= thresh) | ((uint32_t)((h0 >> 16) >= thresh) << 1) |
+                           ((uint32_t)((h1 & 0xffffu) >= thresh) << 2) | ((uint32_t)((h1 >> 16) >= thresh) << 3);
                 }
-                store8(dz + (int64_t)row * lddz + c0, o);
-                if (dzd) store8(dzd + (int64_t)row * lddd + c0, od);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float val = c + t < D ? rs * (g[u][t] - s1 - xh[u][t] * s2) : 0.f;
+                    o[t] = val;
+                    od[t] = ((keep >> t) & 1) ? val * drop_scale : 0.f;
+                }
+                store4(dz + (int64_t)row * lddz + c, o);
+                if (dzd) store4(dzd + (int64_t)row * lddd + c, od);
             }
         }
     }
 #pragma unroll
-    for (int u = 0; u < MAXC / 8; ++u) {
-        int c0 = lane * 8 + 256 * u;
-        if (c0 < DP) {
+    for (int u = 0; u < MAXU; ++u) {
+        const int c = lane * 4 + 128 * u;
+        if (c < DP) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                atomicAdd(&s_dg[c0 + t], pg[u * 8 + t]);
-                atomicAdd(&s_db[c0 + t], pb[u * 8 + t]);
+            for (int t = 0; t < 4; ++t) {
+                atomicAdd(&s_dg[c + t], pg[u][t]);
+                atomicAdd(&s_db[c + t], pb[u][t]);
             }
         }
     }
@@ -548,8 +595,15 @@ extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int6
                            const float* beta, float* mean, float* rstd, int rows, int D, int DP, void* stream) {
     if (rows <= 0) return 0;
     TGAN_CHECK_ARG(DP % 8 == 0 && ldz % 4 == 0 && ldy % 8 == 0 && D <= DP, "tgan_ln_fwd: alignment");
-    DISPATCH_T(dtype, (ln_fwd_kernel<T><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
-                                                                                   mean, rstd, rows, D, DP)));
+    TGAN_CHECK_ARG(DP <= 1024 && (((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)z) & 15) == 0 && ((uintptr_t)y & 7) == 0,
+                   "tgan_ln_fwd: DP <= 1024, 16-byte aligned z / gamma / beta");
+    if (DP <= 512) {
+        DISPATCH_T(dtype, (ln_fwd_kernel<T, 4><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
+                                                                                          mean, rstd, rows, D, DP)));
+    } else {
+        DISPATCH_T(dtype, (ln_fwd_kernel<T, 8><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
+                                                                                          mean, rstd, rows, D, DP)));
+    }
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
@@ -560,8 +614,9 @@ extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float*
                            float* dgamma, float* dbeta, int rows, int D, int DP, float drop_p, uint64_t seed,
                            uint64_t site, void* stream) {
     if (rows <= 0) return 0;
-    TGAN_CHECK_ARG(DP % 8 == 0 && DP <= 1024 && lddy % 8 == 0 && lddz % 8 == 0 && (!dz_drop || lddd % 8 == 0),
-                   "tgan_ln_bwd: DP <= 1024, multiples of 8");
+    TGAN_CHECK_ARG(DP % 8 == 0 && DP <= 1024 && lddy % 8 == 0 && lddz % 8 == 0 && (!dz_drop || lddd % 8 == 0) &&
+                       ldz % 4 == 0 && (((uintptr_t)gamma | (uintptr_t)z) & 15) == 0,
+                   "tgan_ln_bwd: DP <= 1024, multiples of 8, 16-byte aligned z / gamma");
     uint32_t th = (drop_p > 0.f && dz_drop) ? dropout_thresh(drop_p) : 0u;
     float ds = (drop_p > 0.f && dz_drop) ? 1.f / (1.f - drop_p) : 1.f;
     int blocks = min(ceil_div(rows, WPB), 148 * 4);
@@ -569,11 +624,11 @@ extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float*
     blocks = ceil_div(rows, rpb);
     size_t smem = 2 * DP * sizeof(float);
     if (DP <= 512) {
-        DISPATCH_T(dtype, (ln_bwd_kernel<T, 16><<<blocks, WPB * 32, smem, ST>>>(
+        DISPATCH_T(dtype, (ln_bwd_kernel<T, 4><<<blocks, WPB * 32, smem, ST>>>(
                               (const T*)dy, lddy, z, ldz, gamma, mean, rstd, (T*)dz, lddz, (T*)dz_drop, lddd, dgamma,
                               dbeta, rows, D, DP, rpb, ds, th, seed, site)));
     } else {
-        DISPATCH_T(dtype, (ln_bwd_kernel<T, 32><<<blocks, WPB * 32, smem, ST>>>(
+        DISPATCH_T(dtype, (ln_bwd_kernel<T, 8><<<blocks, WPB * 32, smem, ST>>>(
                               (const T*)dy, lddy, z, ldz, gamma, mean, rstd, (T*)dz, lddz, (T*)dz_drop, lddd, dgamma,
                               dbeta, rows, D, DP, rpb, ds, th, seed, site)));
     }
