@@ -1,13 +1,13 @@
 // tcgen05 relative-position attention BACKWARD for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 // Reference: autograd of mem_transformer.py:201-244 (+ _rel_shift :133-147, mask :495-547); SURVEY.md section 9.
 //
-// One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.  Twelve warps:
-//   warps 0..7  "row" warps: thread = (query row = TMEM lane, column half h): warp w owns lane quarter w & 3 and the
-//               32-column half w >> 2 of every 64-wide tile, so each query row is served by two threads.
-//   warp  8     one thread issues every tcgen05.mma
-//   warp  9     K / V tile loads (TMA)        warp 10  R chunks for the G product        warp 11  R chunks for dqR
-//   warp 12     dK / dV tile stores (TMA): the tiles are staged in shared memory and written by the copy engine, so the
-//               1.3 MB-strided key rows never go through the SIMT load/store pipe
+// One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.  4*SPLIT + 5 warps:
+//   row warps   (4*SPLIT of them) thread = (query row = TMEM lane, column slice): warp w owns lane quarter w & 3 and
+//               the CW = 64/SPLIT-column slice w >> 2 of every 64-wide tile, so each query row is served by SPLIT
+//               threads (SPLIT = 4: 16 row warps -- the row work is latency-bound, more resident warps hide it).
+//   then one warp each: tcgen05.mma issuer; K / V tile loads (TMA); R chunks for the G product; R chunks for dqR;
+//               dK / dV tile stores (TMA): the tiles are staged in shared memory and written by the copy engine, so
+//               the 1.3 MB-strided key rows never go through the SIMT load/store pipe
 // Per 64-key tile t (TMEM columns in brackets):
 //     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO' V_t^T
 //   row threads:  P = exp2(S2 - lse2),  dS = P (keep(dP) - delta),  P~ = keep(P)   -> bf16 tiles in shared memory;
@@ -32,8 +32,14 @@ constexpr int HS = TGAN_HS;  // 64
 constexpr int BQ = 128;      // query rows per CTA
 constexpr int BJ = 64;       // keys per tile
 constexpr int RING_COLS = 192;
-constexpr int ROW_WARPS = 8;
+#ifndef TGAN_BWD_SPLIT
+#define TGAN_BWD_SPLIT 4
+#endif
+constexpr int SPLIT = TGAN_BWD_SPLIT;   // threads per query row (2 or 4): each owns CW columns of every 64-wide tile
+constexpr int CW = BJ / SPLIT;
+constexpr int ROW_WARPS = 4 * SPLIT;
 constexpr int NTHREADS = 32 * (ROW_WARPS + 5);
+static_assert(SPLIT == 2 || SPLIT == 4, "row split");
 
 constexpr int B_OFF_QU = 0;
 constexpr int B_OFF_QV = B_OFF_QU + 16384;
@@ -86,9 +92,14 @@ __device__ long long g_bwd_prof_mma[16];
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// the two warps serving one lane quarter (w and w + 4) meet on named barrier 1 + quarter
+// the SPLIT warps serving one lane quarter (w, w + 4, ...) meet on named barrier 1 + quarter
 __device__ __forceinline__ void pair_sync(int quarter) {
-    asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(quarter + 1), "n"(32 * SPLIT) : "memory");
+}
+// CW consecutive fp32 TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t* r) {
+    if constexpr (CW == 32) tmem_ld32(taddr, r);
+    else tmem_ld16(taddr, r);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -142,9 +153,11 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     if (warp == ROW_WARPS) tmem_alloc(sTmemPtr, TM_COLS);
 
     // row-thread identity
-    const int quarter = warp & 3, half = (warp >> 2) & 1;
+    const int quarter = warp & 3, part = (warp >> 2) & (SPLIT - 1);
     const int ii = 32 * quarter + lane;
     float delta = 0.f, lse2 = 0.f;
+    // row ii's SPLIT partial sums of delta meet inside the row's own 128 bytes of the (still unused) P~ tile
+    float* delta_x = reinterpret_cast<float*>(gbase + B_OFF_PT + (ii >> 3) * 1024 + (ii & 7) * 128);
     if (warp < ROW_WARPS) {
         const bool live = ii < rows_here;
         const int64_t row = (int64_t)ii * p.B + b;
@@ -152,12 +165,13 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const bf16* orow = p.out + row * p.ldo + n * HS;
         const bf16* grow = p.dout + row * p.ldo + n * HS;
 #pragma unroll
-        for (int c = 0; c < HS / 8; ++c) {
+        for (int cc = 0; cc < HS / 8 / SPLIT; ++cc) {  // this thread stages (and sums delta over) its CW columns of the row
+            const int c = part * (HS / 8 / SPLIT) + cc;
             float o[8], g[8];
             if (live) { load8(orow + 8 * c, o); load8(grow + 8 * c, g); }
 #pragma unroll
             for (int t = 0; t < 8; ++t) delta += live ? g[t] * o[t] : 0.f;
-            if ((c >> 2) == half) {  // this thread stages its half of the row
+            {
                 float x[8], a[8], bb[8], uu[8], vv[8];
                 if (live) load8(qrow + 8 * c, x);
                 load8(p.u + n * HS + 8 * c, uu);
@@ -173,6 +187,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 store8(reinterpret_cast<bf16*>(gbase + B_OFF_DO + sw128_off(ii, c)), g);
             }
         }
+        delta_x[part] = delta;
         lse2 = live ? p.lse[(int64_t)bn * p.Q + ii] * 1.4426950408889634f : 0.f;
         // zero the dS ring
         for (int o = threadIdx.x * 16; o < DRING_BYTES; o += 32 * ROW_WARPS * 16)
@@ -192,6 +207,11 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
+    if (warp < ROW_WARPS) {
+        delta = 0.f;
+#pragma unroll
+        for (int t = 0; t < SPLIT; ++t) delta += delta_x[t];
+    }
     PROF(0)
 
     if (warp == ROW_WARPS + 1) {
@@ -363,7 +383,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         // =========================== row warps ===========================
         const bool live = ii < rows_here;
         const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
-        const int hc = 32 * half;  // first column of this thread's half
+        const int hc = CW * part;  // first column of this thread's slice
         const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + ii));
         const uint32_t th_hi = p.drop_thresh << 16;
         int consumed = 0;
@@ -374,8 +394,8 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             mbar_wait(rdone, cc & 1);
             PROF(13)
             tcgen05_fence_after();
-            uint32_t v[32];
-            tmem_ld32(tmem_base + TB_DR + hc + lane_off, v);
+            uint32_t v[CW];
+            tmem_ld_cw(tmem_base + TB_DR + hc + lane_off, v);
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -384,7 +404,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             if (lane < 16 && pr >= 0 && pr < p.K) {
                 float* dst = p.dr + (int64_t)pr * p.lddr + n * HS + hc;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                for (int c = 0; c < CW / 4; ++c)
                     red_add_v4(dst + 4 * c, __uint_as_float(v[4 * c]) * p.scale, __uint_as_float(v[4 * c + 1]) * p.scale,
                                __uint_as_float(v[4 * c + 2]) * p.scale, __uint_as_float(v[4 * c + 3]) * p.scale);
             }
@@ -396,28 +416,28 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             mbar_wait(kdone, tk & 1);
             PROF(12)
             tcgen05_fence_after();
-            uint32_t a[32];
+            uint32_t a[CW];
             const int r = 16 * quarter + lane;
-            tmem_ld32(tmem_base + TB_DK + hc + lane_off, a);
+            tmem_ld_cw(tmem_base + TB_DK + hc + lane_off, a);
             tmem_ld_wait();
             if (lane < 16) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < CW / 8; ++c) {
                     float f[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * p.scale;
-                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + sw128_off(r, 4 * half + c)), f);
+                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + sw128_off(r, (CW / 8) * part + c)), f);
                 }
             }
-            tmem_ld32(tmem_base + TB_DV + hc + lane_off, a);
+            tmem_ld_cw(tmem_base + TB_DV + hc + lane_off, a);
             tmem_ld_wait();
             if (lane < 16) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < CW / 8; ++c) {
                     float f[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
-                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + 8192 + sw128_off(r, 4 * half + c)), f);
+                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + 8192 + sw128_off(r, (CW / 8) * part + c)), f);
                 }
             }
             tcgen05_fence_before();
@@ -427,20 +447,20 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         };
 #pragma unroll 1
         for (int tt = 0; tt < nt; ++tt) {
-            // 1. new G chunks (tile tt reads chunks tt .. tt+2): this thread converts its 32-column half.  The ring third
+            // 1. new G chunks (tile tt reads chunks tt .. tt+2): this thread converts its CW-column slice.  The ring third
             //    being overwritten was last read in tile tt-1, which both threads of the row finished before pair sync B.
             while (consumed <= tt + 2 && consumed < nc) {
                 mbar_wait(g_full, consumed & 1);
                 tcgen05_fence_after();
-                uint32_t g[32];
-                tmem_ld32(tmem_base + TB_G + hc + lane_off, g);
+                uint32_t g[CW];
+                tmem_ld_cw(tmem_base + TB_G + hc + lane_off, g);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(g_empty);
                 __half* dst = gring + ((consumed % 3) * BJ + hc) * BQ + ii;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
+                for (int c = 0; c < CW; ++c) dst[c * BQ] = __float2half_rn(__uint_as_float(g[c]));
                 ++consumed;
             }
             PROF(1)
@@ -452,12 +472,12 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             const __half* g0 = gring + start * BQ + ii;
             const __half* g1 = g0 - RING_COLS * BQ;
             // 2. P = exp2((S + G) * scale * log2e - lse2)
-            float pr[32];
+            float pr[CW];
             {
                 mbar_wait(s_full, tt & 1);
                 tcgen05_fence_after();
-                uint32_t sr[32];
-                tmem_ld32(tmem_base + TB_S + hc + lane_off, sr);
+                uint32_t sr[CW];
+                tmem_ld_cw(tmem_base + TB_S + hc + lane_off, sr);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
@@ -467,7 +487,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                                       (!reset_b || p.M <= j0);
                 if (interior) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
+                    for (int jj = 0; jj < CW; ++jj) {
                         const float gv = __half2float((jj < wrap ? g0 : g1)[jj * BQ]);
                         pr[jj] = fast_exp2(fmaf(__uint_as_float(sr[jj]) + gv, p.scale_log2, -lse2));
                     }
@@ -478,7 +498,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     if (reset_b) lim_lo = max(lim_lo, p.M - j0 - hc);
                     lim_hi = min(lim_hi, p.K - 1 - j0 - hc);
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
+                    for (int jj = 0; jj < CW; ++jj) {
                         const float gv = __half2float((jj < wrap ? g0 : g1)[jj * BQ]);
                         const float e = fast_exp2(fmaf(__uint_as_float(sr[jj]) + gv, p.scale_log2, -lse2));
                         pr[jj] = (jj >= lim_lo && jj <= lim_hi) ? e : 0.f;
@@ -491,8 +511,8 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             // 3. dP
             mbar_wait(dp_full, tt & 1);
             tcgen05_fence_after();
-            uint32_t dpr[32];
-            tmem_ld32(tmem_base + TB_DP + hc + lane_off, dpr);
+            uint32_t dpr[CW];
+            tmem_ld_cw(tmem_base + TB_DP + hc + lane_off, dpr);
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -502,11 +522,11 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             if (tt > 0) stage_keys(tt - 1);
             PROF(8)
             // 4. P~ = keep(P), dS = P (keep(dP) - delta), packed to bf16 pairs in registers
-            uint32_t ptw[16], dsw[16];
+            uint32_t ptw[CW / 2], dsw[CW / 2];
             {
                 const uint32_t rk_tile = rowkey + (uint32_t)((j0 + hc) >> 1) * 0x85EBCA77u;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < CW / 2; ++c) {
                     float p0 = pr[2 * c], p1 = pr[2 * c + 1];
                     float dp0 = __uint_as_float(dpr[2 * c]), dp1 = __uint_as_float(dpr[2 * c + 1]);
                     float pt0 = p0, pt1 = p1;
@@ -534,7 +554,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 // half of the ring third before anyone scatters into it
                 uint8_t* z = drow + (((tt + 2) % 3) * BJ + hc) * 16;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) *reinterpret_cast<uint16_t*>(z + 16 * c) = 0;
+                for (int c = 0; c < CW; ++c) *reinterpret_cast<uint16_t*>(z + 16 * c) = 0;
                 pair_sync(quarter);
             }
             // 6. publish: P~ and dS tiles (swizzled K-major) + inverse-shift scatter of dS into the ring
@@ -542,14 +562,14 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 uint8_t* d0 = drow + start * 16;
                 uint8_t* d1 = d0 - RING_COLS * 16;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, 4 * half + c)) =
+                for (int c = 0; c < CW / 8; ++c) {
+                    *reinterpret_cast<uint4*>(gbase + B_OFF_PT + sw128_off(ii, (CW / 8) * part + c)) =
                         make_uint4(ptw[4 * c], ptw[4 * c + 1], ptw[4 * c + 2], ptw[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(gbase + B_OFF_DS + sw128_off(ii, 4 * half + c)) =
+                    *reinterpret_cast<uint4*>(gbase + B_OFF_DS + sw128_off(ii, (CW / 8) * part + c)) =
                         make_uint4(dsw[4 * c], dsw[4 * c + 1], dsw[4 * c + 2], dsw[4 * c + 3]);
                 }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < CW / 2; ++c) {
                     *reinterpret_cast<uint16_t*>((2 * c < wrap ? d0 : d1) + 32 * c) = (uint16_t)(dsw[c] & 0xffffu);
                     *reinterpret_cast<uint16_t*>((2 * c + 1 < wrap ? d0 : d1) + 32 * c + 16) = (uint16_t)(dsw[c] >> 16);
                 }
@@ -563,15 +583,15 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         for (int cc = nt - 1; cc < nc; ++cc) flush_dr(cc);
         // dq = (dqK + dqR) / sqrt(d); du / dvb = column sums over the query rows
         {
-            uint32_t a[32], c2[32];
-            tmem_ld32(tmem_base + TB_DQK + hc + lane_off, a);
-            tmem_ld32(tmem_base + TB_DQR + hc + lane_off, c2);
+            uint32_t a[CW], c2[CW];
+            tmem_ld_cw(tmem_base + TB_DQK + hc + lane_off, a);
+            tmem_ld_cw(tmem_base + TB_DQR + hc + lane_off, c2);
             tmem_ld_wait();
             tcgen05_fence_before();
             if (live) {
                 bf16* dst = p.dq + ((int64_t)ii * p.B + b) * p.ldq + n * HS + hc;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < CW / 8; ++c) {
                     float f[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) f[t] = (__uint_as_float(a[8 * c + t]) + __uint_as_float(c2[8 * c + t])) * p.scale;
@@ -580,13 +600,15 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             }
             float su = 0.f, sv = 0.f;
 #pragma unroll
-            for (int d = 0; d < 32; ++d) {
+            for (int d = 0; d < CW; ++d) {
                 const float tk = warp_sum(live ? __uint_as_float(a[d]) : 0.f);
                 const float tr = warp_sum(live ? __uint_as_float(c2[d]) : 0.f);
                 if (d == lane) { su = tk; sv = tr; }
             }
-            atomicAdd(&p.du[n * HS + hc + lane], su * p.scale);
-            atomicAdd(&p.dvb[n * HS + hc + lane], sv * p.scale);
+            if (lane < CW) {
+                atomicAdd(&p.du[n * HS + hc + lane], su * p.scale);
+                atomicAdd(&p.dvb[n * HS + hc + lane], sv * p.scale);
+            }
         }
         PROF(11)
         PROF_DUMP()
