@@ -4,12 +4,18 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128-byte swizzle) into a STAGES-deep shared-memory ring
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) per 16-wide k slice, commits the
 //               stage back to the producer (tcgen05.commit -> mbarrier) and the finished tile to the epilogue
-//   warps 2..5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM, 2 x BN columns),
-//               transpose 32x32 blocks through shared memory so global accesses are row-contiguous, apply
-//               alpha / bias / ReLU / ReLU-mask / dropout / residual / accumulate, store bf16 or fp32.
+//   warps 2..9  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM, 2 x BN columns), apply
+//               alpha / bias / ReLU / ReLU-mask / dropout / residual with the flag set fixed at COMPILE time for the
+//               combinations the layer stack uses (a run-time-flag epilogue is branch- and I-cache-bound: 5300 vs
+//               500 clocks per tile), stage [32 rows][128 bytes] boxes in swizzled shared memory and let the copy
+//               engine write them (TMA store; TMA reduce-add for gradient accumulation and split-K partial sums).
+//               Operands the copy engine cannot address (unaligned rows, bf16 accumulation) take a direct path.
 // Operand layouts: K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); both are read by TMA with
 // the same 64 x 64-element swizzled boxes and described to the tensor core through the UMMA descriptors.
 // Used for every dense contraction of the path: QKV / R / O projections, FFN, logits, and all dgrad / wgrad.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace tc {
@@ -40,6 +46,26 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
     if (r != CUDA_SUCCESS) {
         tgan_set_error("cuTensorMapEncodeTiled(2d) failed: %d (rows %llu cols %llu ld %llu)", (int)r,
                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+        return 2;
+    }
+    return 0;
+}
+
+int make_tmap_2d_dt(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols, int is_f32) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { tgan_set_error("cuTensorMapEncodeTiled entry point not available"); return 2; }
+    const uint64_t esz = is_f32 ? 4 : 2;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * esz};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        tgan_set_error("cuTensorMapEncodeTiled(2d, %s) failed: %d (rows %llu cols %llu ld %llu)", is_f32 ? "f32" : "bf16",
+                       (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
         return 2;
     }
     return 0;
@@ -84,11 +110,26 @@ constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int EPI_ATOMIC = 1 << 20;   // internal: split-K partial sums are added with red.global.add (fp32 C)
 constexpr int EPI_VEC = 1 << 21;      // internal: C / aux rows are 16-byte aligned -> 8-wide vector accesses
 constexpr int EPI_BIAS_VEC = 1 << 22; // internal: bias pointer is 16-byte aligned
+constexpr int EPI_TMA = 1 << 23;      // internal: C leaves through shared memory + TMA store (reduce-add for ACCUM / split-K)
+constexpr int EPI_ALPHA = 1 << 24;    // internal: alpha != 1
+constexpr int STAGE_BYTES = 32 * 128; // one epilogue warp's staging box: 32 rows x 128 bytes, 128-byte swizzle
+
+#ifdef TGAN_PROFILE
+__device__ long long g_gemm_prof[32];
+#define GPROF_DECL long long _pt = clock64(); long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define GPROF(i) { const long long _n = clock64(); _acc[i] += _n - _pt; _pt = _n; }
+#define GPROF_DUMP(base) if (blockIdx.x == 1 && lane == 0) { for (int _i = 0; _i < 8; ++_i) g_gemm_prof[(base) + _i] = _acc[_i]; }
+#else
+#define GPROF_DECL
+#define GPROF(i)
+#define GPROF_DUMP(base)
+#endif
 
 template <int BN> struct Cfg {
     static constexpr int STAGES = BN == 256 ? 4 : 6;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + EPI_WARPS * STAGE_BYTES + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, const float* v) {
@@ -96,8 +137,70 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, const float* v) {
                  : "memory");
 }
 
-// Epilogue of one accumulator row segment: 32 consecutive columns [col0, col0+32) of row `row`, owned by one thread
-// (thread = TMEM lane = output row, so every global access is a row-contiguous 16/32-byte vector).
+// Final values (before ACCUM) of the 8 consecutive columns col .. col+7 of output row `row`; nv <= 8 of them exist.
+// thread = TMEM lane = output row, so aux / bias accesses are row-contiguous 16/32-byte vectors.
+__device__ __forceinline__ void epi_values8(float* v, const uint32_t* regs, int64_t row, int col, int nv, int64_t ldc,
+                                            const EpiParams& ep) {
+    const int flags = ep.flags;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(regs[t]) * ep.alpha;
+    if ((flags & EPI_VEC) && nv == 8) {
+        if (flags & TGAN_EPI_BIAS) {
+            float b[8];
+            if (flags & EPI_BIAS_VEC) load8(ep.bias + col, b);
+            else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) b[t] = __ldg(ep.bias + col + t);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] += b[t];
+        }
+        if (flags & TGAN_EPI_RELU) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+        }
+        float a[8];
+        if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX)) {
+            if (ep.aux_is_f32) load8((const float*)ep.aux + row * ep.ldaux + col, a);
+            else load8((const bf16*)ep.aux + row * ep.ldaux + col, a);
+        }
+        if (flags & TGAN_EPI_MASK_POS) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = a[t] > 0.f ? v[t] : 0.f;
+        }
+        if (flags & TGAN_EPI_DROPOUT) {
+            const uint32_t keep = dropout_keep8_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * ep.drop_scale : 0.f;
+        }
+        if (flags & TGAN_EPI_ADD_AUX) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] += a[t];
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            float x = 0.f;
+            if (t < nv) {
+                x = v[t];
+                if (flags & TGAN_EPI_BIAS) x += __ldg(ep.bias + col + t);
+                if (flags & TGAN_EPI_RELU) x = fmaxf(x, 0.f);
+                float a = 0.f;
+                if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX))
+                    a = ep.aux_is_f32 ? ((const float*)ep.aux)[row * ep.ldaux + col + t]
+                                      : to_f(((const bf16*)ep.aux)[row * ep.ldaux + col + t]);
+                if (flags & TGAN_EPI_MASK_POS) x = a > 0.f ? x : 0.f;
+                if (flags & TGAN_EPI_DROPOUT)
+                    x = dropout_keep_k(ep.drop_key, (uint64_t)row * ldc + col + t, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
+                if (flags & TGAN_EPI_ADD_AUX) x += a;
+            }
+            v[t] = x;
+        }
+    }
+}
+
+// Direct-to-global sink of one 32-column accumulator segment (operands that the copy engine cannot address:
+// unaligned C rows, bf16 accumulation).  Each thread writes its own row.
 template <typename TC>
 __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int col0, int N, TC* __restrict__ C,
                                           int64_t ldc, const EpiParams& ep) {
@@ -106,43 +209,11 @@ __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int
     for (int g = 0; g < 4; ++g) {
         const int col = col0 + 8 * g;
         if (col >= N) break;
+        const int nv = min(8, N - col);
         float v[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(regs[8 * g + t]) * ep.alpha;
+        epi_values8(v, regs + 8 * g, row, col, nv, ldc, ep);
         TC* cp = C + row * ldc + col;
-        if ((flags & EPI_VEC) && col + 8 <= N) {
-            if (flags & TGAN_EPI_BIAS) {
-                float b[8];
-                if (flags & EPI_BIAS_VEC) load8(ep.bias + col, b);
-                else {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) b[t] = __ldg(ep.bias + col + t);
-                }
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v[t] += b[t];
-            }
-            if (flags & TGAN_EPI_RELU) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
-            }
-            float a[8];
-            if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX)) {
-                if (ep.aux_is_f32) load8((const float*)ep.aux + row * ep.ldaux + col, a);
-                else load8((const bf16*)ep.aux + row * ep.ldaux + col, a);
-            }
-            if (flags & TGAN_EPI_MASK_POS) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v[t] = a[t] > 0.f ? v[t] : 0.f;
-            }
-            if (flags & TGAN_EPI_DROPOUT) {
-                const uint32_t keep = dropout_keep8_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * ep.drop_scale : 0.f;
-            }
-            if (flags & TGAN_EPI_ADD_AUX) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v[t] += a[t];
-            }
+        if ((flags & EPI_VEC) && nv == 8) {
             if (flags & EPI_ATOMIC) {
                 red_add_f32x4((float*)cp, v);
                 red_add_f32x4((float*)cp + 4, v + 4);
@@ -156,21 +227,10 @@ __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int
                 store8(cp, v);
             }
         } else {
-            const int nv = min(8, N - col);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 if (t < nv) {
                     float x = v[t];
-                    if (flags & TGAN_EPI_BIAS) x += __ldg(ep.bias + col + t);
-                    if (flags & TGAN_EPI_RELU) x = fmaxf(x, 0.f);
-                    float a = 0.f;
-                    if (flags & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX))
-                        a = ep.aux_is_f32 ? ((const float*)ep.aux)[row * ep.ldaux + col + t]
-                                          : to_f(((const bf16*)ep.aux)[row * ep.ldaux + col + t]);
-                    if (flags & TGAN_EPI_MASK_POS) x = a > 0.f ? x : 0.f;
-                    if (flags & TGAN_EPI_DROPOUT)
-                        x = dropout_keep_k(ep.drop_key, (uint64_t)row * ldc + col + t, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
-                    if (flags & TGAN_EPI_ADD_AUX) x += a;
                     if (flags & EPI_ATOMIC) atomicAdd((float*)(cp + t), x);
                     else {
                         if (flags & TGAN_EPI_ACCUM) x += to_f(cp[t]);
@@ -178,6 +238,69 @@ __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int
                     }
                 }
             }
+        }
+    }
+}
+
+// Compile-time epilogue (EPI = the public flag bits that apply + EPI_ALPHA): vector-aligned operands, N % 8 == 0, bf16
+// aux.  The hot shapes of the layer stack all take this path; no per-flag branches, no scalar tail.
+template <int EPI>
+__device__ __forceinline__ void epi_values8_ct(float* v, const uint32_t* regs, int64_t row, int col, int64_t ldc,
+                                               const EpiParams& ep) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = (EPI & EPI_ALPHA) ? __uint_as_float(regs[t]) * ep.alpha : __uint_as_float(regs[t]);
+    if constexpr ((EPI & TGAN_EPI_BIAS) != 0) {
+        float b[8];
+        load8(ep.bias + col, b);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] += b[t];
+    }
+    if constexpr ((EPI & TGAN_EPI_RELU) != 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+    }
+    float a[8];
+    if constexpr ((EPI & (TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX)) != 0) load8((const bf16*)ep.aux + row * ep.ldaux + col, a);
+    if constexpr ((EPI & TGAN_EPI_MASK_POS) != 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = a[t] > 0.f ? v[t] : 0.f;
+    }
+    if constexpr ((EPI & TGAN_EPI_DROPOUT) != 0) {
+        const uint32_t keep = dropout_keep8_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * ep.drop_scale : 0.f;
+    }
+    if constexpr ((EPI & TGAN_EPI_ADD_AUX) != 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] += a[t];
+    }
+}
+
+// Shared-memory sink: the 32-column segment of row r (0..31 inside this warp's staging tile) goes into the
+// 128-byte-swizzled [32 rows][128 bytes] box that the TMA store / reduce reads.  seg = index of the 32-column
+// segment inside the box (bf16: 0 or 1, fp32: 0).
+template <typename TC, int EPI>
+__device__ __forceinline__ void epi_row32_smem(const uint32_t* regs, int64_t row, int r, int col0, int seg, int N,
+                                               uint8_t* stage, int64_t ldc, const EpiParams& ep) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int col = col0 + 8 * g;
+        float v[8];
+        if constexpr (EPI >= 0) {
+            epi_values8_ct<EPI>(v, regs + 8 * g, row, col, ldc, ep);  // N % 8 == 0: a started segment is whole groups
+        } else {
+            const int nv = max(0, min(8, N - col));
+            if (nv > 0) epi_values8(v, regs + 8 * g, row, col, nv, ldc, ep);
+            else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = 0.f;
+            }
+        }
+        if constexpr (sizeof(TC) == 2) {
+            store8(reinterpret_cast<bf16*>(stage + sw128_off(r, 4 * seg + g)), v);
+        } else {
+            *reinterpret_cast<float4*>(stage + sw128_off(r, 2 * g)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(stage + sw128_off(r, 2 * g + 1)) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
 }
@@ -197,16 +320,19 @@ __device__ __forceinline__ Work get_work(int w, int num_tiles, int tiles_n, int 
     return r;
 }
 
-template <int BN, bool A_MN, bool B_MN, typename TC>
+// EPI >= 0: compile-time epilogue (see epi_values8_ct; always the TMA sink); EPI = -1: run-time flags, either sink
+template <int BN, bool A_MN, bool B_MN, typename TC, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TC* __restrict__ C,
-               int64_t ldc, int M, int N, int K, int splits, int kb_per_split, EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, TC* __restrict__ C, int64_t ldc, int M, int N, int K, int splits,
+               int kb_per_split, EpiParams ep) {
     constexpr int STAGES = Cfg<BN>::STAGES;
     constexpr int B_BYTES = Cfg<BN>::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = base, sB = base + STAGES * A_BYTES;
-    const uint32_t sBar = sB + STAGES * B_BYTES;
+    const uint32_t sStage = sB + STAGES * B_BYTES;  // 1024-byte aligned: EPI_WARPS staging boxes
+    const uint32_t sBar = sStage + EPI_WARPS * STAGE_BYTES;
     const uint32_t full0 = sBar, empty0 = sBar + 8 * STAGES, tfull0 = sBar + 16 * STAGES, tempty0 = tfull0 + 16;
     const uint32_t sTmemPtr = tempty0 + 16;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -223,7 +349,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        if (EPI >= 0 || (ep.flags & EPI_TMA)) tma_prefetch_desc(&tmC);
+    }
     if (warp == 1) tmem_alloc(sTmemPtr, 2 * BN);
     tcgen05_fence_before();
     __syncthreads();
@@ -233,11 +362,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            GPROF_DECL
             int s = 0; uint32_t ph = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
                 for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+                    GPROF(0)
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    GPROF(1)
                     const uint32_t fb = full0 + 8 * s;
                     mbar_expect_tx(fb, A_BYTES + B_BYTES);
                     const uint32_t a_dst = sA + s * A_BYTES, b_dst = sB + s * B_BYTES;
@@ -254,6 +386,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
+            GPROF(0)
+            GPROF_DUMP(0)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -264,14 +398,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t db0 = B_MN ? umma_smem_desc(sB, 8192, 1024) : umma_smem_desc(sB, 16, 1024);
         constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4, b_kstep = (B_MN ? 2048 : 32) >> 4;
         int s = 0; uint32_t ph = 0; int it = 0;
+        GPROF_DECL
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
             const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
             const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+            GPROF(0)
             mbar_wait(tempty0 + 8 * as, aph ^ 1);
+            GPROF(1)
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + as * BN;
             for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+                GPROF(0)
                 mbar_wait(full0 + 8 * s, ph);
+                GPROF(2)
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint64_t da = da0 + (uint64_t)((s * A_BYTES) >> 4), db = db0 + (uint64_t)((s * B_BYTES) >> 4);
@@ -285,29 +424,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
+        GPROF(0)
+        GPROF_DUMP(8)
     } else {
         // ===================== epilogue warps =====================
-        // warp w may only touch TMEM lanes 32*(w%4) .. +31; the two warps sharing a lane quarter split the columns
+        // warp w may only touch TMEM lanes 32*(w%4) .. +31; the two warps sharing a lane quarter split the columns.
+        // TMA path: each warp stages a [32 rows][128 bytes] box in shared memory (swizzled) and lets the copy engine
+        // write (or reduce-add) full 128-byte lines; the direct path stores row-strided 16-byte vectors itself.
         const int eq = warp & 3, eh = (warp - 2) >> 2;
+        constexpr int BOXC = 128 / (int)sizeof(TC);  // columns per staging box (bf16: 64, fp32: 32)
+        const bool use_tma = EPI >= 0 || (ep.flags & EPI_TMA) != 0;
+        const bool reduce = (ep.flags & (EPI_ATOMIC | TGAN_EPI_ACCUM)) != 0;
+        uint8_t* stage = gen_base + (sStage - base) + (warp - 2) * STAGE_BYTES;
+        const uint32_t stage_u32 = sStage + (warp - 2) * STAGE_BYTES;
+        bool pending = false;  // a bulk store issued by this warp may still be reading the staging box
         int it = 0;
+        GPROF_DECL
         for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
             const Work wk = get_work<BN>(w, num_tiles, tiles_n, nk, kb_per_split);
             const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+            GPROF(0)
             mbar_wait(tfull0 + 8 * as, aph);
+            GPROF(1)
             tcgen05_fence_after();
-            const int64_t row = wk.m0 + 32 * eq + lane;
+            const int row0 = wk.m0 + 32 * eq;
+            const int64_t row = row0 + lane;
+            if (use_tma) {
 #pragma unroll 1
-            for (int c0 = eh * (BN / 2); c0 < (eh + 1) * (BN / 2); c0 += 32) {
-                if (wk.n0 + c0 >= N) break;  // warp-uniform
-                uint32_t regs[32];
-                tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * eq) << 16), regs);
-                tmem_ld_wait();
-                if (row < M) epi_row32<TC>(regs, row, wk.n0 + c0, N, C, ldc, ep);
+                for (int b0 = eh * (BN / 2); b0 < (eh + 1) * (BN / 2); b0 += BOXC) {
+                    if (wk.n0 + b0 >= N) break;  // warp-uniform
+#pragma unroll
+                    for (int seg = 0; seg < BOXC / 32; ++seg) {
+                        const int c0 = b0 + 32 * seg;
+                        if (wk.n0 + c0 >= N) break;  // warp-uniform; the rest of the box is clipped by the tensor map
+                        uint32_t regs[32];
+                        GPROF(0)
+                        tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * eq) << 16), regs);
+                        tmem_ld_wait();
+                        GPROF(2)
+                        if (seg == 0 && pending) {
+                            if (lane == 0) tma_store_wait_read();
+                            __syncwarp();
+                            pending = false;
+                        }
+                        GPROF(3)
+                        if (row < M) epi_row32_smem<TC, EPI>(regs, row, lane, wk.n0 + c0, seg, N, stage, ldc, ep);
+                        GPROF(4)
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (reduce) tma_reduce_add_2d(&tmC, stage_u32, wk.n0 + b0, row0);
+                        else tma_store_2d(&tmC, stage_u32, wk.n0 + b0, row0);
+                        tma_store_commit();
+                    }
+                    pending = true;
+                    GPROF(5)
+                }
+            } else if constexpr (EPI < 0) {
+#pragma unroll 1
+                for (int c0 = eh * (BN / 2); c0 < (eh + 1) * (BN / 2); c0 += 32) {
+                    if (wk.n0 + c0 >= N) break;  // warp-uniform
+                    uint32_t regs[32];
+                    GPROF(0)
+                    tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * eq) << 16), regs);
+                    tmem_ld_wait();
+                    GPROF(2)
+                    if (row < M) epi_row32<TC>(regs, row, wk.n0 + c0, N, C, ldc, ep);
+                    GPROF(4)
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         }
+        if (pending && lane == 0) tma_store_wait_all();
+        GPROF(0)
+        if (warp == 2) { GPROF_DUMP(16) }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -317,10 +510,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, typename TC>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M, int N, int K, int splits,
-              const EpiParams& ep, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC>;
+template <int BN, bool A_MN, bool B_MN, typename TC, int EPI>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, void* C, int64_t ldc, int M, int N,
+              int K, int splits, const EpiParams& ep, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         TGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
@@ -331,24 +524,49 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t l
     splits = ceil_div(nk, kb_per_split);  // no empty split
     const int work = ceil_div(M, BM) * ceil_div(N, BN) * splits;
     const int grid = work < sm_count() ? work : sm_count();
-    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, (TC*)C, ldc, M, N, K, splits, kb_per_split, ep);
+    kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM, st>>>(tmA, tmB, tmC, (TC*)C, ldc, M, N, K, splits, kb_per_split, ep);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
 }
 
+#define TGAN_LAUNCH_ARGS tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st
+// epi_ct: the compile-time epilogue key, or -1.  The fused epilogues of the layer stack only occur with the
+// nn.Linear layout (A and B K-major); every layout has the plain (0) variant for projections / weight gradients.
 template <int BN, typename TC>
-int launch_layout(int transA, int transB, const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, int M,
-                  int N, int K, int splits, const EpiParams& ep, cudaStream_t st) {
+int launch_layout(int transA, int transB, int epi_ct, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                  void* C, int64_t ldc, int M, int N, int K, int splits, const EpiParams& ep, cudaStream_t st) {
+    constexpr int B_ = TGAN_EPI_BIAS, R_ = TGAN_EPI_RELU, MP = TGAN_EPI_MASK_POS, AX = TGAN_EPI_ADD_AUX, DR = TGAN_EPI_DROPOUT;
     // transA = 1 -> A stored [K, M] -> MN-major A;  transB = 0 -> B stored [K, N] -> MN-major B
-    if (!transA && transB) return launch_tc<BN, false, false, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
-    if (!transA && !transB) return launch_tc<BN, false, true, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
-    if (transA && transB) return launch_tc<BN, true, false, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
-    return launch_tc<BN, true, true, TC>(tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    if (!transA && transB) {
+        switch (epi_ct) {
+            case 0: return launch_tc<BN, false, false, TC, 0>(TGAN_LAUNCH_ARGS);
+            case B_: return launch_tc<BN, false, false, TC, B_>(TGAN_LAUNCH_ARGS);
+            case B_ | R_: return launch_tc<BN, false, false, TC, B_ | R_>(TGAN_LAUNCH_ARGS);
+            case B_ | R_ | DR: return launch_tc<BN, false, false, TC, B_ | R_ | DR>(TGAN_LAUNCH_ARGS);
+            case AX: return launch_tc<BN, false, false, TC, AX>(TGAN_LAUNCH_ARGS);
+            case AX | DR: return launch_tc<BN, false, false, TC, AX | DR>(TGAN_LAUNCH_ARGS);
+            case B_ | AX: return launch_tc<BN, false, false, TC, B_ | AX>(TGAN_LAUNCH_ARGS);
+            case B_ | AX | DR: return launch_tc<BN, false, false, TC, B_ | AX | DR>(TGAN_LAUNCH_ARGS);
+            case MP: return launch_tc<BN, false, false, TC, MP>(TGAN_LAUNCH_ARGS);
+            case MP | EPI_ALPHA: return launch_tc<BN, false, false, TC, MP | EPI_ALPHA>(TGAN_LAUNCH_ARGS);
+            default: return launch_tc<BN, false, false, TC, -1>(TGAN_LAUNCH_ARGS);
+        }
+    }
+    if (!transA && !transB)
+        return epi_ct == 0 ? launch_tc<BN, false, true, TC, 0>(TGAN_LAUNCH_ARGS) : launch_tc<BN, false, true, TC, -1>(TGAN_LAUNCH_ARGS);
+    if (transA && transB)
+        return epi_ct == 0 ? launch_tc<BN, true, false, TC, 0>(TGAN_LAUNCH_ARGS) : launch_tc<BN, true, false, TC, -1>(TGAN_LAUNCH_ARGS);
+    return epi_ct == 0 ? launch_tc<BN, true, true, TC, 0>(TGAN_LAUNCH_ARGS) : launch_tc<BN, true, true, TC, -1>(TGAN_LAUNCH_ARGS);
 }
 }  // namespace
 
 extern "C" int tgan_has_tcgen05(void) { return 1; }
+#ifdef TGAN_PROFILE
+extern "C" int tgan_debug_gemm_prof(long long* host32) {
+    return (int)cudaMemcpyFromSymbol(host32, g_gemm_prof, sizeof(long long) * 32);
+}
+#endif
 
 int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
                  int64_t ldb, void* C, int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int flags,
@@ -406,10 +624,27 @@ int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const
             ep.flags = (ep.flags & ~TGAN_EPI_ACCUM) | EPI_ATOMIC;
         }
     }
-    if (dtype_c == TGAN_F32) {
-        if (BN == 256) return launch_layout<256, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
-        return launch_layout<128, float>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    // C leaves through shared memory + TMA whenever the copy engine can address it: 16-byte aligned rows, and
+    // accumulation only into fp32 (reduce-add)
+    CUtensorMap tmC;
+    memset(&tmC, 0, sizeof(tmC));
+    const bool accum = (ep.flags & (TGAN_EPI_ACCUM | EPI_ATOMIC)) != 0;
+    if (vec && ((int64_t)N * esz_c) % 16 == 0 && !(accum && dtype_c != TGAN_F32) && !getenv("TGAN_GEMM_NO_TMA_EPI")) {
+        rc = tc::make_tmap_2d_dt(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, dtype_c == TGAN_F32 ? 32 : 64,
+                                 dtype_c == TGAN_F32);
+        if (rc) return rc;
+        ep.flags |= EPI_TMA;
     }
-    if (BN == 256) return launch_layout<256, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
-    return launch_layout<128, bf16>(transA, transB, tmA, tmB, C, ldc, M, N, K, splits, ep, st);
+    // compile-time epilogue variant: whole 8-column groups, aligned bias, bf16 aux
+    int epi_ct = -1;
+    if ((ep.flags & EPI_TMA) && N % 8 == 0 && !ep.aux_is_f32 && (!(ep.flags & TGAN_EPI_BIAS) || (ep.flags & EPI_BIAS_VEC)) &&
+        !getenv("TGAN_GEMM_NO_CT_EPI"))
+        epi_ct = (ep.flags & (TGAN_EPI_BIAS | TGAN_EPI_RELU | TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX | TGAN_EPI_DROPOUT)) |
+                 (alpha != 1.0f ? EPI_ALPHA : 0);
+    if (dtype_c == TGAN_F32) {
+        if (BN == 256) return launch_layout<256, float>(transA, transB, epi_ct, tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st);
+        return launch_layout<128, float>(transA, transB, epi_ct, tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st);
+    }
+    if (BN == 256) return launch_layout<256, bf16>(transA, transB, epi_ct, tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st);
+    return launch_layout<128, bf16>(transA, transB, epi_ct, tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st);
 }

@@ -74,6 +74,17 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                  "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+// element-wise global += shared (atomic at the L2; the element type comes from the tensor map)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING shared memory (the source may be reused)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -215,6 +226,9 @@ EncodeTiledFn get_encode_fn();
 // 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols]; 128-byte swizzle
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                  uint32_t box_cols);
+// same, bf16 or fp32 elements (GEMM output maps)
+int make_tmap_2d_dt(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols, int is_f32);
 // 3-D bf16 tensor: dim0 (contiguous) x dim1 (stride1 elements) x dim2 (stride2 elements)
 int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                  uint64_t stride2, uint32_t b0, uint32_t b1, uint32_t b2);
