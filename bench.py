@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from the host instead of replaying "
+                    "the captured forward / backward CUDA graphs of each ring phase")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--warm-segments", type=int, default=None,
                     help="untimed steps before timing (default: enough to fill the recurrence memory, >= --warmup)")
@@ -202,6 +204,7 @@ def workload_config(args, world):
                         "d_inner 1000, vocab 310, tgt_len 128, mem_len 1024, dropout 0.1), synthetic MAESTRO-vocab tokens",
             "global_batch": args.global_batch, "seq_len": WORK["tgt_len"], "mem_len": WORK["mem_len"],
             "batch_chunk": args.batch_chunk, "parallelism": f"dp{world}",
+            "launch": "host launches" if args.no_graphs else "CUDA graphs (one forward + one backward graph per ring phase)",
             "l2": "per-step working set (activations + recurrence memory, several GB) is far larger than the 126 MB L2"}
 
 
@@ -230,6 +233,7 @@ def main():
     model = model.to(dev).train()
     model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     model.kernel_impl = args.kernel_impl
+    model.use_cuda_graphs = not args.no_graphs
     from tgan_b200 import dp
     fp = dp.FlatParams(model.parameters())  # one flat parameter / gradient buffer: all-reduce, clip and Adam are one call each
     lr = WORK["lr"] / world  # train.py:392 divides lr by the GPU count
@@ -287,7 +291,10 @@ def main():
         return ms.item(), L.launch_count() - l0
 
     # warm the recurrence memory to its steady-state length (M = mem_len) before timing: 8 segments
-    warm_segments = args.warm_segments if args.warm_segments is not None else max(args.warmup, WORK["mem_len"] // Q)
+    # ... then one more pass over every ring phase so that each phase's forward / backward graph is captured
+    fill = WORK["mem_len"] // Q
+    phases = 0 if args.no_graphs else (WORK["mem_len"] + Q) // Q
+    warm_segments = args.warm_segments if args.warm_segments is not None else max(args.warmup, fill) + phases + 1
     for _ in range(warm_segments):
         train_step(False)
     sampler = ClockSampler(local)

@@ -52,6 +52,16 @@ int tgan_has_tcgen05(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 unsigned long long tgan_launch_count(void);
 
+/* ---- device-side step counter ---------------------------------------------------------------------------
+ * Every stochastic kernel (dropout sites, Gumbel noise) derives its mask from (seed, site, element).  A replayed
+ * CUDA graph repeats (seed, site), so the trainer registers ONE device uint32 here and bumps it once per optimizer
+ * step on the stream (e.g. as the first node of the captured step); the kernels fold its current value into the
+ * mask key.  The forward and backward of one step see the same value and regenerate identical masks.
+ * dev_u32 = NULL switches the fold off (default).  Host-synchronous; call it outside stream capture.
+ * Replaces the implicit global-RNG state advance behind nn.Dropout / torch.rand (mem_transformer.py:37,39,229,248,
+ * 557,573,610). */
+int tgan_set_step_counter(const void* dev_u32);
+
 /* ---- dense contractions ------------------------------------------------------------------------------
  * C[M,N] = epi( sum_k opA(A)[m,k] * opB(B)[k,n] ),  row-major.
  *   transA = 0: A is [M,K] (lda >= K);  transA = 1: A is [K,M] (lda >= M)

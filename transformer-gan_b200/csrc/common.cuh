@@ -123,8 +123,32 @@ __host__ __device__ __forceinline__ bool dropout_keep_k(uint32_t key, uint64_t e
     const uint32_t h = dropout_hash_pair(key, e >> 1);
     return ((e & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh16;  // thresh16 = p * 2^16
 }
+// ---- device-side step counter --------------------------------------------------------------------------------
+// A replayed CUDA graph repeats its kernel arguments, so (seed, site) alone would repeat the dropout masks every
+// step.  tgan_set_step_counter() registers one device uint32 that the trainer bumps once per optimizer step
+// (on the stream, e.g. as the first node of the captured step); every mask key folds its current value in.  The
+// forward and the backward of one step read the same value, so they regenerate identical masks.  NULL = off.
+// (one copy of the pointer per translation unit: the library is built without relocatable device code)
+static __device__ const uint32_t* d_tgan_step_ctr = nullptr;
+__device__ __forceinline__ uint32_t step_fold(uint32_t key) {
+    const uint32_t* c = d_tgan_step_ctr;
+    return c ? mix32(key ^ (__ldg(c) * 0x9E3779B1u)) : key;
+}
+__device__ __forceinline__ uint64_t step_fold_site(uint64_t site) {
+    const uint32_t* c = d_tgan_step_ctr;
+    return c ? site ^ ((uint64_t)__ldg(c) << 40) : site;
+}
+static inline int tgan_set_step_ctr_local(const void* dev_ptr) {
+    return (int)cudaMemcpyToSymbol(d_tgan_step_ctr, &dev_ptr, sizeof(dev_ptr));
+}
+int tgan_set_step_ctr_gemm_simt(const void*);
+int tgan_set_step_ctr_gemm_tc(const void*);
+int tgan_set_step_ctr_relattn_simt(const void*);
+int tgan_set_step_ctr_relattn_fwd_tc(const void*);
+int tgan_set_step_ctr_relattn_bwd_tc(const void*);
+
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t site, uint64_t e, uint32_t thresh16) {
-    return dropout_keep_k(dropout_key(seed, site), e, thresh16);
+    return dropout_keep_k(step_fold(dropout_key(seed, site)), e, thresh16);
 }
 // keep bits for the 8 consecutive elements e0 .. e0+7
 __host__ __device__ __forceinline__ uint32_t dropout_keep8_k(uint32_t key, uint64_t e0, uint32_t thresh16) {
@@ -143,7 +167,7 @@ __host__ __device__ __forceinline__ uint32_t dropout_keep8_k(uint32_t key, uint6
     return m;
 }
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t site, uint64_t e0, uint32_t thresh16) {
-    return dropout_keep8_k(dropout_key(seed, site), e0, thresh16);
+    return dropout_keep8_k(step_fold(dropout_key(seed, site)), e0, thresh16);
 }
 // attention-probability dropout: one hash yields the keep decisions of a pair of adjacent keys (16 bits each);
 // the per-row key is hashed once per query row.  Shared by the SIMT and the tcgen05 attention kernels so that

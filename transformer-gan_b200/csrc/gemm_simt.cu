@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(int M, int N, int K, cons
                                         : to_f(((const TA*)ep.aux)[(int64_t)gm * ep.ldaux + gn]);
                 if (flags & TGAN_EPI_MASK_POS) v = a > 0.f ? v : 0.f;
                 if (flags & TGAN_EPI_DROPOUT)
-                    v = dropout_keep_k(ep.drop_key, (uint64_t)gm * ldc + gn, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
+                    v = dropout_keep_k(step_fold(ep.drop_key), (uint64_t)gm * ldc + gn, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
                 if (flags & TGAN_EPI_ADD_AUX) v += a;
             } else if (flags & TGAN_EPI_DROPOUT) {
-                v = dropout_keep_k(ep.drop_key, (uint64_t)gm * ldc + gn, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
+                v = dropout_keep_k(step_fold(ep.drop_key), (uint64_t)gm * ldc + gn, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
             }
             TC* cp = C + (int64_t)gm * ldc + gn;
             if (flags & TGAN_EPI_ACCUM) v += to_f(*cp);
@@ -164,3 +164,5 @@ extern "C" int tgan_gemm(int dtype_ab, int dtype_c, int transA, int transB, int 
     return tgan_gemm_simt(dtype_ab, dtype_c, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux,
                           epi_flags, alpha, drop_p, seed, site, st);
 }
+
+int tgan_set_step_ctr_gemm_simt(const void* p) { return tgan_set_step_ctr_local(p); }

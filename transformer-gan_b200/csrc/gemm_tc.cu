@@ -140,7 +140,7 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, const float* v) {
 // Final values (before ACCUM) of the 8 consecutive columns col .. col+7 of output row `row`; nv <= 8 of them exist.
 // thread = TMEM lane = output row, so aux / bias accesses are row-contiguous 16/32-byte vectors.
 __device__ __forceinline__ void epi_values8(float* v, const uint32_t* regs, int64_t row, int col, int nv, int64_t ldc,
-                                            const EpiParams& ep) {
+                                            const EpiParams& ep, uint32_t dkey) {
     const int flags = ep.flags;
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(regs[t]) * ep.alpha;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void epi_values8(float* v, const uint32_t* regs, int6
             for (int t = 0; t < 8; ++t) v[t] = a[t] > 0.f ? v[t] : 0.f;
         }
         if (flags & TGAN_EPI_DROPOUT) {
-            const uint32_t keep = dropout_keep8_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh);
+            const uint32_t keep = dropout_keep8_k(dkey, (uint64_t)row * ldc + col, ep.drop_thresh);
 #pragma unroll
             for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * ep.drop_scale : 0.f;
         }
@@ -191,7 +191,7 @@ __device__ __forceinline__ void epi_values8(float* v, const uint32_t* regs, int6
                                       : to_f(((const bf16*)ep.aux)[row * ep.ldaux + col + t]);
                 if (flags & TGAN_EPI_MASK_POS) x = a > 0.f ? x : 0.f;
                 if (flags & TGAN_EPI_DROPOUT)
-                    x = dropout_keep_k(ep.drop_key, (uint64_t)row * ldc + col + t, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
+                    x = dropout_keep_k(dkey, (uint64_t)row * ldc + col + t, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
                 if (flags & TGAN_EPI_ADD_AUX) x += a;
             }
             v[t] = x;
@@ -203,7 +203,7 @@ __device__ __forceinline__ void epi_values8(float* v, const uint32_t* regs, int6
 // unaligned C rows, bf16 accumulation).  Each thread writes its own row.
 template <typename TC>
 __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int col0, int N, TC* __restrict__ C,
-                                          int64_t ldc, const EpiParams& ep) {
+                                          int64_t ldc, const EpiParams& ep, uint32_t dkey) {
     const int flags = ep.flags;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -211,7 +211,7 @@ __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int
         if (col >= N) break;
         const int nv = min(8, N - col);
         float v[8];
-        epi_values8(v, regs + 8 * g, row, col, nv, ldc, ep);
+        epi_values8(v, regs + 8 * g, row, col, nv, ldc, ep, dkey);
         TC* cp = C + row * ldc + col;
         if ((flags & EPI_VEC) && nv == 8) {
             if (flags & EPI_ATOMIC) {
@@ -246,7 +246,7 @@ __device__ __forceinline__ void epi_row32(const uint32_t* regs, int64_t row, int
 // aux.  The hot shapes of the layer stack all take this path; no per-flag branches, no scalar tail.
 template <int EPI>
 __device__ __forceinline__ void epi_values8_ct(float* v, const uint32_t* regs, int64_t row, int col, int64_t ldc,
-                                               const EpiParams& ep) {
+                                               const EpiParams& ep, uint32_t dkey) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] = (EPI & EPI_ALPHA) ? __uint_as_float(regs[t]) * ep.alpha : __uint_as_float(regs[t]);
     if constexpr ((EPI & TGAN_EPI_BIAS) != 0) {
@@ -266,7 +266,7 @@ __device__ __forceinline__ void epi_values8_ct(float* v, const uint32_t* regs, i
         for (int t = 0; t < 8; ++t) v[t] = a[t] > 0.f ? v[t] : 0.f;
     }
     if constexpr ((EPI & TGAN_EPI_DROPOUT) != 0) {
-        const uint32_t keep = dropout_keep8_k(ep.drop_key, (uint64_t)row * ldc + col, ep.drop_thresh);
+        const uint32_t keep = dropout_keep8_k(dkey, (uint64_t)row * ldc + col, ep.drop_thresh);
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = ((keep >> t) & 1) ? v[t] * ep.drop_scale : 0.f;
     }
@@ -281,16 +281,16 @@ __device__ __forceinline__ void epi_values8_ct(float* v, const uint32_t* regs, i
 // segment inside the box (bf16: 0 or 1, fp32: 0).
 template <typename TC, int EPI>
 __device__ __forceinline__ void epi_row32_smem(const uint32_t* regs, int64_t row, int r, int col0, int seg, int N,
-                                               uint8_t* stage, int64_t ldc, const EpiParams& ep) {
+                                               uint8_t* stage, int64_t ldc, const EpiParams& ep, uint32_t dkey) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const int col = col0 + 8 * g;
         float v[8];
         if constexpr (EPI >= 0) {
-            epi_values8_ct<EPI>(v, regs + 8 * g, row, col, ldc, ep);  // N % 8 == 0: a started segment is whole groups
+            epi_values8_ct<EPI>(v, regs + 8 * g, row, col, ldc, ep, dkey);  // N % 8 == 0: a started segment is whole groups
         } else {
             const int nv = max(0, min(8, N - col));
-            if (nv > 0) epi_values8(v, regs + 8 * g, row, col, nv, ldc, ep);
+            if (nv > 0) epi_values8(v, regs + 8 * g, row, col, nv, ldc, ep, dkey);
             else {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) v[t] = 0.f;
@@ -433,6 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // write (or reduce-add) full 128-byte lines; the direct path stores row-strided 16-byte vectors itself.
         const int eq = warp & 3, eh = (warp - 2) >> 2;
         constexpr int BOXC = 128 / (int)sizeof(TC);  // columns per staging box (bf16: 64, fp32: 32)
+        const uint32_t dkey = step_fold(ep.drop_key);
         const bool use_tma = EPI >= 0 || (ep.flags & EPI_TMA) != 0;
         const bool reduce = (ep.flags & (EPI_ATOMIC | TGAN_EPI_ACCUM)) != 0;
         uint8_t* stage = gen_base + (sStage - base) + (warp - 2) * STAGE_BYTES;
@@ -468,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             pending = false;
                         }
                         GPROF(3)
-                        if (row < M) epi_row32_smem<TC, EPI>(regs, row, lane, wk.n0 + c0, seg, N, stage, ldc, ep);
+                        if (row < M) epi_row32_smem<TC, EPI>(regs, row, lane, wk.n0 + c0, seg, N, stage, ldc, ep, dkey);
                         GPROF(4)
                     }
                     fence_proxy_async_smem();
@@ -490,7 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld32(tmem_base + as * BN + c0 + ((uint32_t)(32 * eq) << 16), regs);
                     tmem_ld_wait();
                     GPROF(2)
-                    if (row < M) epi_row32<TC>(regs, row, wk.n0 + c0, N, C, ldc, ep);
+                    if (row < M) epi_row32<TC>(regs, row, wk.n0 + c0, N, C, ldc, ep, dkey);
                     GPROF(4)
                 }
             }
@@ -562,6 +563,7 @@ int launch_layout(int transA, int transB, int epi_ct, const CUtensorMap& tmA, co
 }  // namespace
 
 extern "C" int tgan_has_tcgen05(void) { return 1; }
+int tgan_set_step_ctr_gemm_tc(const void* p) { return tgan_set_step_ctr_local(p); }
 #ifdef TGAN_PROFILE
 extern "C" int tgan_debug_gemm_prof(long long* host32) {
     return (int)cudaMemcpyFromSymbol(host32, g_gemm_prof, sizeof(long long) * 32);

@@ -224,7 +224,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const bool live = ii < rows_here;
         const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
         float m_ref = -INFINITY, l = 0.f;
-        const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + i));
+        const uint32_t rowkey = attn_drop_rowkey(step_fold(p.drop_key), (uint32_t)(bn * p.Q + i));
         const float c_log2 = p.scale_log2;
         // thread-private ring row: ring[col * BQ + ii]
         auto pull = [&](int cc) {
@@ -382,6 +382,8 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     }
 }
 }  // namespace
+
+int tgan_set_step_ctr_relattn_fwd_tc(const void* p) { return tgan_set_step_ctr_local(p); }
 
 int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out, int64_t ldo,

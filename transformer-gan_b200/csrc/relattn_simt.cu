@@ -61,7 +61,7 @@ __device__ __forceinline__ bool attn_masked(int i, int j, int b_reset, const Att
 
 __device__ __forceinline__ bool drop_keep_ij(const AttnArgs& a, int bn, int i, int j) {
     if (!a.thresh) return true;
-    return attn_drop_keep(attn_drop_rowkey(a.key, (uint32_t)(bn * a.Q + i)), j, a.thresh);
+    return attn_drop_keep(attn_drop_rowkey(step_fold(a.key), (uint32_t)(bn * a.Q + i)), j, a.thresh);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -424,3 +424,5 @@ int tgan_relattn_bwd_simt(int dtype, const void* q, int64_t ldq, const void* k, 
     return bwd_launch<bf16>(q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq, dk, dv, lddkv,
                             dr, lddr, du, dvb, a, st);
 }
+
+int tgan_set_step_ctr_relattn_simt(const void* p) { return tgan_set_step_ctr_local(p); }

@@ -384,7 +384,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const bool live = ii < rows_here;
         const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
         const int hc = CW * part;  // first column of this thread's slice
-        const uint32_t rowkey = attn_drop_rowkey(p.drop_key, (uint32_t)(bn * p.Q + ii));
+        const uint32_t rowkey = attn_drop_rowkey(step_fold(p.drop_key), (uint32_t)(bn * p.Q + ii));
         const uint32_t th_hi = p.drop_thresh << 16;
         int consumed = 0;
         uint8_t* drow = gbase + B_OFF_DRING + (ii >> 3) * DR_GROUP + (ii & 7) * 2;  // ring entry (p, ii) at drow + 16 p
@@ -628,6 +628,8 @@ extern "C" int tgan_debug_bwd_prof(long long* host16) {
     return (int)cudaMemcpyFromSymbol(host16, g_bwd_prof, sizeof(long long) * 16);
 }
 #endif
+
+int tgan_set_step_ctr_relattn_bwd_tc(const void* p) { return tgan_set_step_ctr_local(p); }
 
 int tgan_relattn_bwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, const void* out,

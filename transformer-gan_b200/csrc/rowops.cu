@@ -22,6 +22,13 @@ void tgan_set_error(const char* fmt, ...) {
 extern "C" const char* tgan_last_error(void) { return g_err; }
 extern "C" int tgan_version(void) { return 100; }
 extern "C" unsigned long long tgan_launch_count(void) { return g_tgan_launches; }
+extern "C" int tgan_set_step_counter(const void* dev_u32) {
+    int rc = tgan_set_step_ctr_local(dev_u32);
+    rc |= tgan_set_step_ctr_gemm_simt(dev_u32) | tgan_set_step_ctr_gemm_tc(dev_u32) | tgan_set_step_ctr_relattn_simt(dev_u32) |
+          tgan_set_step_ctr_relattn_fwd_tc(dev_u32) | tgan_set_step_ctr_relattn_bwd_tc(dev_u32);
+    if (rc) { tgan_set_error("tgan_set_step_counter: cudaMemcpyToSymbol failed"); return 2; }
+    return 0;
+}
 
 #define DISPATCH_T(dtype, ...)                                  \
     do {                                                        \
@@ -68,7 +75,7 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __res
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    const uint32_t key = dropout_key(seed, site);
+    const uint32_t key = step_fold(dropout_key(seed, site));
     const int c = c0 + 2 * lane;
     for (int row = r0 + warp; row < r1; row += nwarps) {
         const int v = (int)ids[row];
@@ -197,7 +204,7 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const floa
     for (int c = threadIdx.x; c < 2 * DP; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t key = dropout_key(seed, site);
+    const uint32_t key = step_fold(dropout_key(seed, site));
     float pg[MAXU][4], pb[MAXU][4], gm[MAXU][4];
 #pragma unroll
     for (int u = 0; u < MAXU; ++u) {
@@ -357,7 +364,7 @@ __global__ void gumbel_fwd_kernel(const float* __restrict__ logits, int64_t ldl,
         if (U) u = U[(int64_t)row * ldu + c];
         else {
             uint64_t e = (uint64_t)row * V + c;
-            Philox4 r = philox4x32_10(seed, site, e >> 2);
+            Philox4 r = philox4x32_10(seed, step_fold_site(site), e >> 2);
             uint32_t bits = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
             u = (bits >> 8) * (1.0f / 16777216.0f);  // [0, 1) like torch.rand
         }

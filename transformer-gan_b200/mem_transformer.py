@@ -153,6 +153,60 @@ class _TxlFunction(torch.autograd.Function):
         return (None, None, dinp, None, None, None, None, None, None) + (None,) * len(ctx.names)
 
 
+class _GraphEntry:
+    """One captured MLE segment: forward graph, backward graph, their static inputs and outputs."""
+    fwd = bwd = ectx = None
+    n_fwd = n_bwd = 0
+    grad_ptrs = None
+
+
+class _TxlGraphFunction(torch.autograd.Function):
+    """MLE forward / backward as two CUDA-graph replays (``MemTransformerLM.use_cuda_graphs``).
+
+    A training segment is ~180 kernel launches of fixed shape; at small per-GPU batches (data parallel at 4-8 GPUs) the
+    host cannot enqueue them as fast as the GPU retires them.  The engine calls for one (ring phase, shape) key are
+    captured once and replayed; inputs are copied into static buffers, parameter gradients are accumulated into the
+    ``.grad`` tensors that existed at capture (re-captured if they move), and the dropout masks advance through the
+    device step counter (tgan_set_step_counter) that the forward graph bumps as its first node."""
+
+    @staticmethod
+    def forward(ctx, model, entry, names, *params):
+        entry.fwd.replay()
+        L.note_graph_replay(entry.n_fwd)
+        ctx.model, ctx.entry, ctx.names, ctx.params = model, entry, names, params
+        e = entry.ectx
+        return e.nll.view(e.T, e.B).clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        model, entry = ctx.model, ctx.entry
+        eng = model._get_engine()
+        targets = {}
+        for n, prm in zip(ctx.names, ctx.params):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
+            targets[n] = prm.grad
+        ptrs = tuple(t.data_ptr() for t in targets.values())
+        entry.dnll.copy_(gout.reshape(-1))
+        if entry.bwd is None or entry.grad_ptrs != ptrs:
+            if entry.ectx.layers is None:
+                raise RuntimeError("the gradient tensors moved after the backward graph was captured; keep .grad "
+                                   "allocated (zero it in place) when use_cuda_graphs is on")
+            eng._unpack_desc_for(targets)  # descriptor table staged outside the capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g, pool=eng.graph_pool()):
+                eng.backward(entry.ectx, dnll=entry.dnll, grad_targets=targets)
+            entry.bwd, entry.n_bwd, entry.grad_ptrs = g, L.launch_count() - n0, ptrs
+            # eng.backward dropped the activations: their pool blocks may now be reused by the next key's capture
+            # (graphs that share the pool are replayed strictly one after the other)
+        entry.bwd.replay()
+        L.note_graph_replay(entry.n_bwd)
+        model._graph_pending = None
+        return (None, None, None) + (None,) * len(ctx.names)
+
+
 class MemTransformerLM(nn.Module):
     def __init__(self, cfg, n_token, vec_len):
         n_layer, n_head, d_model = cfg.MODEL.num_layers, cfg.MODEL.num_heads, cfg.MODEL.units
@@ -193,6 +247,11 @@ class MemTransformerLM(nn.Module):
         self.kernel_impl = L.IMPL_AUTO
         self._engine = None
         self._new_mems = None
+        # replay each steady-state MLE segment (forward, backward) as CUDA graphs instead of ~180 launches; see
+        # _TxlGraphFunction.  Off by default: it pins the input / gradient buffers of the captured shapes.
+        self.use_cuda_graphs = False
+        self._graphs = {}
+        self._graph_pending = None
 
     # ---- reference API ---------------------------------------------------------------------------------
     def reset_length(self, tgt_len, mem_len):
@@ -220,10 +279,53 @@ class MemTransformerLM(nn.Module):
         e.bind_params(_param_dict(self))
         return e
 
+    def _graph_entry(self, eng, data, target, reset_mems, ring):
+        """The captured forward for this (ring phase, shape) key; captured on first use."""
+        B, Q, T = data.shape[1], data.shape[0], target.shape[0]
+        key = (ring.slabs.data_ptr(), ring.start, ring.length, Q, B, T, self.mem_len, self.same_length, self.training,
+               eng.d.dropout, eng.d.dropatt, eng._param_key)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = _GraphEntry()
+            entry.ids, entry.tgt = data.clone(), target.clone()
+            entry.reset = torch.zeros(B, dtype=torch.uint8, device=data.device)
+            entry.dnll = torch.zeros(T * B, dtype=torch.float32, device=data.device)
+            ctr = L.step_counter(data.device)
+            eng._packed_version = None  # the parameter re-pack must be part of the graph
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g, pool=eng.graph_pool()):
+                ctr.add_(1)
+                entry.ectx = eng.forward(entry.ids, entry.reset, ring, mem_len=self.mem_len, same_length=self.same_length,
+                                         training=self.training, target=entry.tgt, n_pred=T, save_for_backward=True)
+            eng._packed_version = None
+            entry.fwd, entry.n_fwd = g, L.launch_count() - n0
+            nm = entry.ectx.new_mems
+            entry.new_mems = None if nm is None else (nm.start, nm.length)
+            self._graphs[key] = entry
+        entry.ids.copy_(data)
+        entry.tgt.copy_(target)
+        if reset_mems is None:
+            entry.reset.zero_()
+        else:
+            entry.reset.copy_(reset_mems)
+        return entry
+
     def _run(self, mode, data, target, reset_mems, mems, temperature=None, noise=None):
         eng = self._get_engine()
         names = [r for r, *_ in eng.layout.reference_map()]
         pd = _param_dict(self)
+        if (self.use_cuda_graphs and mode == "mle" and isinstance(mems, RingMems) and self.mem_len > 0
+                and mems.length == self.mem_len and mems.bsz == data.shape[1] and torch.is_grad_enabled()
+                and self._graph_pending is None and data.dim() == 2):
+            ring = eng._prepare_ring(mems, data.shape[1], data.shape[0], self.mem_len)
+            if ring is mems:  # steady state: the ring is reused in place, only (start, length) move
+                entry = self._graph_entry(eng, data, target, reset_mems, ring)
+                self._graph_pending = entry
+                out = _TxlGraphFunction.apply(self, entry, names, *[pd[n] for n in names])
+                start, length = entry.new_mems
+                return out, RingMems(ring.slabs, start, length, self.d_model)
         out = _TxlFunction.apply(self, mode, data, target, reset_mems, mems, temperature, noise, names,
                                  *[pd[n] for n in names])
         return out, self._new_mems

@@ -293,6 +293,12 @@ class TxlEngine:
         return self.gvec.data_ptr() + 4 * self.layout.vec[name][0]
 
     # -- helpers ------------------------------------------------------------------------------------------
+    def graph_pool(self):
+        """One private memory pool shared by every captured segment (they are replayed strictly one after another)."""
+        if getattr(self, "_graph_pool", None) is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        return self._graph_pool
+
     def _site(self, call_id: int, local: int) -> int:
         return call_id * 256 + local
 

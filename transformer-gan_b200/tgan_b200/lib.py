@@ -58,6 +58,7 @@ _SIGS = {
     "tgan_unpack_grads": [P, P, P, I, L, I, P],
     "tgan_sumsq": [P, L, P, P],
     "tgan_adam_step": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P],
+    "tgan_set_step_counter": [P],
 }
 EXPORTS = ["tgan_last_error", "tgan_version", "tgan_has_tcgen05", "tgan_launch_count"] + list(_SIGS)
 for _name, _sig in _SIGS.items():
@@ -74,8 +75,33 @@ def has_tcgen05() -> bool:
     return bool(_lib.tgan_has_tcgen05())
 
 
+_replayed = 0
+_step_counters = {}
+
+
 def launch_count() -> int:
-    return int(_lib.tgan_launch_count())
+    """Kernels of this library enqueued so far: direct launches plus the kernel nodes of every graph replay."""
+    return int(_lib.tgan_launch_count()) + _replayed
+
+
+def note_graph_replay(n_kernels: int) -> None:
+    global _replayed
+    _replayed += n_kernels
+
+
+def step_counter(device) -> torch.Tensor:
+    """The process-wide device step counter (int32 [1]) registered with tgan_set_step_counter; created on first use."""
+    key = torch.device(device).index or 0
+    if key not in _step_counters:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        set_step_counter(t)
+        _step_counters[key] = t
+    return _step_counters[key]
+
+
+def set_step_counter(counter) -> None:
+    """Register (or, with None, clear) the device uint32/int32 step counter folded into every dropout / noise key."""
+    _call("tgan_set_step_counter", None if counter is None else counter.data_ptr())
 
 
 def _ptr(t):
