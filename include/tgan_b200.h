@@ -139,13 +139,15 @@ int tgan_ce_bwd(int dtype, const float* logits, int64_t ldl, const int64_t* targ
 /* ---- Gumbel-softmax straight-through: mem_transformer.py:609-628 ----------------------------------------
  * g = -log(-log(U+1e-20)+1e-20); y = softmax((logits+g)/tau); ids = argmax y;
  * st = (onehot(ids) - y) + y evaluated in fp32 exactly as the reference does.  U fp32 [rows, ldu] (injected
- * noise) or NULL -> Philox(seed, site).  y (fp32 [rows, ldy]) is saved for the backward.                   */
-int tgan_gumbel_st_fwd(const float* logits, int64_t ldl, const float* U, int64_t ldu, float tau, float* y,
-                       int64_t ldy, float* st, int64_t lds, int64_t* ids, int rows, int V, uint64_t seed,
+ * noise) or NULL -> Philox(seed, site).  y (fp32 [rows, ldy]) is saved for the backward.
+ * tau_dev (optional, DEVICE float): read instead of `tau` -- the annealed temperature (helpers.py:62-82) changes every
+ * step, and a kernel argument would be frozen into a captured CUDA graph.                                    */
+int tgan_gumbel_st_fwd(const float* logits, int64_t ldl, const float* U, int64_t ldu, float tau, const float* tau_dev,
+                       float* y, int64_t ldy, float* st, int64_t lds, int64_t* ids, int rows, int V, uint64_t seed,
                        uint64_t site, void* stream);
 /* dlogits = (1/tau) * y * (dst - <y, dst>)  -> fp32 [rows, ldd] */
-int tgan_gumbel_st_bwd(const float* y, int64_t ldy, const float* dst, int64_t lds, float tau, float* dlogits,
-                       int64_t ldd, int rows, int V, void* stream);
+int tgan_gumbel_st_bwd(const float* y, int64_t ldy, const float* dst, int64_t lds, float tau, const float* tau_dev,
+                       float* dlogits, int64_t ldd, int rows, int V, void* stream);
 
 /* ---- small reductions / converts -------------------------------------------------------------------------*/
 /* out[n] += sum_m x[m,n]   (bias gradients) */

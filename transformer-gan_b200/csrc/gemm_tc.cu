@@ -579,12 +579,15 @@ int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const
         tgan_set_error("tgan_gemm: tcgen05 path needs 16-byte aligned operands and leading dimensions that are multiples of 8");
         return -1;
     }
-    if (!force && (M < 64 || 2.0 * M * N * K < 3.0e7)) {
+    // Even a 32-row decode GEMM belongs here: one 128-row MMA tile per 128/256 output columns finishes in a few
+    // microseconds, while the FFMA kernel needs ~100 us for the same rows (few CTAs, serial K loop).
+    if (!force && 2.0 * M * N * K < 1.0e6) {
         tgan_set_error("tgan_gemm: problem too small for the tcgen05 path");
         return -1;
     }
     const int waste256 = ceil_div(N, 256) * 256 - N, waste128 = ceil_div(N, 128) * 128 - N;
-    const int BN = (waste256 <= waste128) ? 256 : 128;
+    int BN = (waste256 <= waste128) ? 256 : 128;
+    if (ceil_div(M, BM) * ceil_div(N, 256) * 2 <= sm_count()) BN = 128;  // few tiles: narrower ones fill more SMs
     CUtensorMap tmA, tmB;
     int rc;
     if (!transA) rc = tc::make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);

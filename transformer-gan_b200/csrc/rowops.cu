@@ -349,11 +349,12 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, int64_t ldl, con
 // Gumbel-softmax straight-through (warp per row)                    mem_transformer.py:609-628
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gumbel_fwd_kernel(const float* __restrict__ logits, int64_t ldl, const float* __restrict__ U,
-                                  int64_t ldu, float tau, float* __restrict__ y, int64_t ldy,
-                                  float* __restrict__ st, int64_t lds, int64_t* __restrict__ ids, int rows, int V,
-                                  uint64_t seed, uint64_t site) {
+                                  int64_t ldu, float tau, const float* __restrict__ tau_dev, float* __restrict__ y,
+                                  int64_t ldy, float* __restrict__ st, int64_t lds, int64_t* __restrict__ ids, int rows,
+                                  int V, uint64_t seed, uint64_t site) {
     int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
+    if (tau_dev) tau = __ldg(tau_dev);
     const float* l = logits + (int64_t)row * ldl;
     float* yr = y + (int64_t)row * ldy;
     // pass 1: perturbed, tempered logits (kept in y), running max / first argmax
@@ -410,9 +411,11 @@ __global__ void gumbel_fwd_kernel(const float* __restrict__ logits, int64_t ldl,
 }
 
 __global__ void gumbel_bwd_kernel(const float* __restrict__ y, int64_t ldy, const float* __restrict__ dst,
-                                  int64_t lds, float tau, float* __restrict__ dl, int64_t ldd, int rows, int V) {
+                                  int64_t lds, float tau, const float* __restrict__ tau_dev, float* __restrict__ dl,
+                                  int64_t ldd, int rows, int V) {
     int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
+    if (tau_dev) tau = __ldg(tau_dev);
     const float* yr = y + (int64_t)row * ldy;
     const float* dr = dst + (int64_t)row * lds;
     float dot = 0.f;
@@ -678,22 +681,22 @@ extern "C" int tgan_ce_bwd(int dtype, const float* logits, int64_t ldl, const in
     return 0;
 }
 
-extern "C" int tgan_gumbel_st_fwd(const float* logits, int64_t ldl, const float* U, int64_t ldu, float tau, float* y,
-                                  int64_t ldy, float* st, int64_t lds, int64_t* ids, int rows, int V, uint64_t seed,
-                                  uint64_t site, void* stream) {
+extern "C" int tgan_gumbel_st_fwd(const float* logits, int64_t ldl, const float* U, int64_t ldu, float tau,
+                                  const float* tau_dev, float* y, int64_t ldy, float* st, int64_t lds, int64_t* ids,
+                                  int rows, int V, uint64_t seed, uint64_t site, void* stream) {
     if (rows <= 0) return 0;
-    TGAN_CHECK_ARG(y != nullptr && tau > 0.f, "tgan_gumbel_st_fwd: y buffer and tau > 0 required");
-    gumbel_fwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(logits, ldl, U, ldu, tau, y, ldy, st, lds, ids, rows,
-                                                                 V, seed, site);
+    TGAN_CHECK_ARG(y != nullptr && (tau_dev != nullptr || tau > 0.f), "tgan_gumbel_st_fwd: y buffer and tau > 0 required");
+    gumbel_fwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(logits, ldl, U, ldu, tau, tau_dev, y, ldy, st, lds, ids,
+                                                                 rows, V, seed, site);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
 }
 
 extern "C" int tgan_gumbel_st_bwd(const float* y, int64_t ldy, const float* dst, int64_t lds, float tau,
-                                  float* dlogits, int64_t ldd, int rows, int V, void* stream) {
+                                  const float* tau_dev, float* dlogits, int64_t ldd, int rows, int V, void* stream) {
     if (rows <= 0) return 0;
-    gumbel_bwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(y, ldy, dst, lds, tau, dlogits, ldd, rows, V);
+    gumbel_bwd_kernel<<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(y, ldy, dst, lds, tau, tau_dev, dlogits, ldd, rows, V);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;

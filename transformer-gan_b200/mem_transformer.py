@@ -115,9 +115,9 @@ class _TxlFunction(torch.autograd.Function):
         y = torch.empty(T * B, V, dtype=torch.float32, device=eng.device)
         U = None if noise is None else noise.reshape(T * B, V).to(device=eng.device, dtype=torch.float32).contiguous()
         eng.calls += 1
-        L.gumbel_st_fwd(ectx.logits, U, float(temperature), y, logits, None, T * B, V, seed=eng.seed,
-                        site=eng._site(eng.calls, 3))
-        ctx.y, ctx.tau = y, float(temperature)
+        tau = temperature if isinstance(temperature, torch.Tensor) else float(temperature)  # tensor: read on the device
+        L.gumbel_st_fwd(ectx.logits, U, tau, y, logits, None, T * B, V, seed=eng.seed, site=eng._site(eng.calls, 3))
+        ctx.y, ctx.tau = y, tau
         return logits.view(T, B, V)
 
     @staticmethod
@@ -172,6 +172,7 @@ class _TxlGraphFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, entry, names, *params):
         entry.fwd.replay()
+        model._get_engine().pack_epoch += 1  # the graph re-packed the parameters: cached K/V projections are stale
         L.note_graph_replay(entry.n_fwd)
         ctx.model, ctx.entry, ctx.names, ctx.params = model, entry, names, params
         e = entry.ectx
@@ -325,7 +326,7 @@ class MemTransformerLM(nn.Module):
                 self._graph_pending = entry
                 out = _TxlGraphFunction.apply(self, entry, names, *[pd[n] for n in names])
                 start, length = entry.new_mems
-                return out, RingMems(ring.slabs, start, length, self.d_model)
+                return out, RingMems(ring.slabs, start, length, self.d_model, kv=ring.kv)
         out = _TxlFunction.apply(self, mode, data, target, reset_mems, mems, temperature, noise, names,
                                  *[pd[n] for n in names])
         return out, self._new_mems

@@ -69,11 +69,15 @@ class RingMems:
     The reference returns a fresh ``[n_layer+1, M, B, d_model]`` fp32 tensor per call; ``materialize()``
     produces exactly that tensor (for tests, checkpoints and the generate.py self-check)."""
 
-    def __init__(self, slabs: torch.Tensor, start: int, length: int, d_model: int):
+    def __init__(self, slabs: torch.Tensor, start: int, length: int, d_model: int, kv: Optional[dict] = None):
         self.slabs = slabs
         self.start = start
         self.length = length
         self.d_model = d_model
+        # projected-K/V cache of the ring rows (decode-sized calls only, see TxlEngine.forward): shared by every
+        # RingMems window over the same slabs.  {"buf": [n_layer, capacity, B, 2*N*64], "lo", "hi": cached physical
+        # rows, "tag": parameter-pack epoch the rows were projected with}
+        self.kv = kv if kv is not None else {"buf": None, "lo": 0, "hi": 0, "tag": -1}
 
     @property
     def capacity(self) -> int:
@@ -231,6 +235,8 @@ class TxlEngine:
         self._packed_version = None
         self._pack_desc = None
         self._es = 2 if dtype == torch.bfloat16 else 4
+        self.pack_epoch = 0        # bumped whenever the packed parameter copies are rewritten
+        self.kv_cache_max_q = 8    # calls with at most this many new rows keep / reuse the projected-K/V cache
 
     # -- parameters ---------------------------------------------------------------------------------------
     def bind_params(self, params: Dict[str, torch.Tensor]):
@@ -281,6 +287,7 @@ class TxlEngine:
             return
         L.pack_params(self.pmat, self.pvec, self._pack_desc, self._pack_desc.shape[0], self._max_elems)
         self._packed_version = ver
+        self.pack_epoch += 1
 
     def _m(self, name):  # (tensor, element offset, ld)
         off, rows, ld = self.layout.mat[name]
@@ -306,7 +313,8 @@ class TxlEngine:
         return torch.empty(*shape, dtype=dtype or self.dtype, device=self.device)
 
     def new_ring(self, B: int, Q: int, mem_len: int) -> RingMems:
-        cap = mem_len + Q
+        # decode-sized segments get a longer ring: the window then slides mem_len steps before a re-layout is due
+        cap = mem_len + Q if Q > self.kv_cache_max_q else 2 * mem_len + Q
         slabs = torch.zeros(self.d.n_layer + 1, cap, B, self.d.DP, dtype=self.dtype, device=self.device)
         return RingMems(slabs, 0, 0, self.d.d_model)
 
@@ -412,26 +420,46 @@ class TxlEngine:
         ctx.pe = pe
         scale = 1.0 / math.sqrt(d.d_head)
         ctx.layers = []
+        # Projected-K/V cache (the reference re-projects every memory row at each of the 123 sampling
+        # steps / every generated token, mem_transformer.py:166-170).  For decode-sized calls the K/V rows live in a
+        # buffer that mirrors the ring; rows projected by an earlier call with the same packed parameters are reused
+        # and only the new rows go through the GEMM.  Same values up to nothing: the rows are bit-identical.
+        use_cache = Q <= self.kv_cache_max_q and mem_len > 0 and len(ctx.x_segs) == 1
+        kv_from = 0
+        if use_cache:
+            st, s0 = ring.kv, ctx.x_segs[0][0]
+            if st["buf"] is None or st["buf"].shape[1:3] != (C, B) or st["buf"].dtype != dt:
+                st["buf"] = torch.empty(d.n_layer, C, B, 2 * NH, dtype=dt, device=self.device)
+                st["tag"] = -1
+            cached = M > 0 and st["tag"] == self.pack_epoch and st["lo"] <= s0 and st["hi"] == w
+            kv_from = w if cached else s0  # first physical row that still has to be projected
         for l in range(d.n_layer):
             p = f"l{l}."
             sv = _Ctx()
             woff, wld = self._m(p + "Wqkv")
             q = self._buf(R, NH)
-            kv = self._buf(KR, 2 * NH)
             r = self._buf(K, NH)
             x_base = l * slab_elems
             L.gemm(slabs, self.pmat, q, M=R, N=NH, K=DP, lda=DP, ldb=wld, a_off=cur_off[l], b_off=woff, impl=self.impl)
-            row = 0
-            for pos, n in ctx.x_segs:
-                L.gemm(slabs, self.pmat, kv, M=n * B, N=2 * NH, K=DP, lda=DP, ldb=wld, a_off=x_base + pos * B * DP,
-                       b_off=woff + NH * wld, c_off=row * B * 2 * NH, impl=self.impl)
-                row += n
+            if use_cache:
+                kv, kv_off = ring.kv["buf"], (l * C + ctx.x_segs[0][0]) * B * 2 * NH
+                L.gemm(slabs, self.pmat, kv, M=(w + Q - kv_from) * B, N=2 * NH, K=DP, lda=DP, ldb=wld, ldc=2 * NH,
+                       a_off=x_base + kv_from * B * DP, b_off=woff + NH * wld, c_off=(l * C + kv_from) * B * 2 * NH,
+                       impl=self.impl)
+            else:
+                kv, kv_off = self._buf(KR, 2 * NH), 0
+                row = 0
+                for pos, n in ctx.x_segs:
+                    L.gemm(slabs, self.pmat, kv, M=n * B, N=2 * NH, K=DP, lda=DP, ldb=wld, a_off=x_base + pos * B * DP,
+                           b_off=woff + NH * wld, c_off=row * B * 2 * NH, impl=self.impl)
+                    row += n
             roff, rld = self._m(p + "Wr")
             L.gemm(pe, self.pmat, r, M=K, N=NH, K=DP, ldb=rld, b_off=roff, impl=self.impl)
             att = self._buf(R, NH)
             lse = self._buf(B * d.n_head * Q, dtype=torch.float32)
             L.relattn_fwd(q, kv, kv, 2 * NH, r, self._v("u"), self._v("vb"), reset_u8, att, lse, B, d.n_head, Q, M, msl,
-                          same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=self.impl, v_off=NH)
+                          same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=self.impl, k_off=kv_off,
+                          v_off=kv_off + NH)
             # O projection + dropout + residual (fp32) -> LN
             ooff, old = self._m(p + "Wo")
             z1 = self._buf(R, DP, dtype=torch.float32)
@@ -456,10 +484,14 @@ class TxlEngine:
             L.ln_fwd(z2, slabs, self._v(p + "ln2_g"), self._v(p + "ln2_b"), mean2, rstd2, R, D, DP,
                      y_off=cur_off[l + 1])
             if save_for_backward:
-                sv.q, sv.kv, sv.r, sv.att, sv.lse = q, kv, r, att, lse
+                sv.q, sv.kv, sv.kv_off, sv.r, sv.att, sv.lse = q, kv, kv_off, r, att, lse
                 sv.z1, sv.a, sv.mean1, sv.rstd1 = z1, a, mean1, rstd1
                 sv.h, sv.z2, sv.mean2, sv.rstd2 = h, z2, mean2, rstd2
                 ctx.layers.append(sv)
+        if use_cache:
+            st = ring.kv
+            st["lo"] = st["lo"] if kv_from == w and M > 0 else ctx.x_segs[0][0]
+            st["hi"], st["tag"] = w + Q, self.pack_epoch
         # 3. final dropout, logits, NLL
         T = Q if n_pred is None else n_pred
         ctx.T = T
@@ -488,7 +520,7 @@ class TxlEngine:
         if mem_len > 0:
             new_len = min(M + Q, mem_len)
             new_start = (ring.start + M + Q - new_len) % C
-            ctx.new_mems = RingMems(ring.slabs, new_start, new_len, D)
+            ctx.new_mems = RingMems(ring.slabs, new_start, new_len, D, kv=ring.kv)
         else:
             ctx.new_mems = None
         return ctx
@@ -581,7 +613,7 @@ class TxlEngine:
             L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
                           sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
                           ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,
-                          v_off=NH, dv_off=NH)
+                          k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
             if dt == torch.float32:
                 dr = dr32
             else:

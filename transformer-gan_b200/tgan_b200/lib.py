@@ -50,8 +50,8 @@ _SIGS = {
                          F, F, U, U, I, P],
     "tgan_ce_fwd": [P, L, P, P, P, I, I, P],
     "tgan_ce_bwd": [I, P, L, P, P, P, P, L, I, I, I, P],
-    "tgan_gumbel_st_fwd": [P, L, P, L, F, P, L, P, L, P, I, I, U, U, P],
-    "tgan_gumbel_st_bwd": [P, L, P, L, F, P, L, I, I, P],
+    "tgan_gumbel_st_fwd": [P, L, P, L, F, P, P, L, P, L, P, I, I, U, U, P],
+    "tgan_gumbel_st_bwd": [P, L, P, L, F, P, P, L, I, I, P],
     "tgan_colsum": [I, P, L, P, I, I, P],
     "tgan_convert": [I, P, L, I, P, L, L, I, I, P],
     "tgan_pack_params": [I, P, P, P, I, L, P],
@@ -211,14 +211,21 @@ def ce_bwd(logits, target, lse, dnll, dlogits, rows, V, VP):
           _ptr(lse), _ptr(dnll), dlogits.data_ptr(), dlogits.stride(0), rows, V, VP, _stream())
 
 
+def _tau(tau):
+    """temperature as (by-value float, device pointer): a 1-element CUDA tensor is read on the device (graph-safe)"""
+    return (1.0, tau.data_ptr()) if isinstance(tau, torch.Tensor) else (float(tau), None)
+
+
 def gumbel_st_fwd(logits, U, tau, y, st, ids, rows, V, seed=0, site=0):
+    tv, tp = _tau(tau)
     _call("tgan_gumbel_st_fwd", logits.data_ptr(), logits.stride(0), _ptr(U), 0 if U is None else U.stride(0),
-          tau, y.data_ptr(), y.stride(0), _ptr(st), 0 if st is None else st.stride(0), _ptr(ids), rows, V, seed,
+          tv, tp, y.data_ptr(), y.stride(0), _ptr(st), 0 if st is None else st.stride(0), _ptr(ids), rows, V, seed,
           site, _stream())
 
 
 def gumbel_st_bwd(y, dst, tau, dlogits, rows, V):
-    _call("tgan_gumbel_st_bwd", y.data_ptr(), y.stride(0), dst.data_ptr(), dst.stride(0), tau, dlogits.data_ptr(),
+    tv, tp = _tau(tau)
+    _call("tgan_gumbel_st_bwd", y.data_ptr(), y.stride(0), dst.data_ptr(), dst.stride(0), tv, tp, dlogits.data_ptr(),
           dlogits.stride(0), rows, V, _stream())
 
 

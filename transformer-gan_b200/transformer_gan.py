@@ -32,6 +32,10 @@ from mem_transformer import MemTransformerLM
 from utils.helpers import get_losses
 
 
+def gen_is_bf16(gen) -> bool:
+    return getattr(gen, "compute_dtype", torch.float32) == torch.bfloat16
+
+
 class TransformerGAN(nn.Module):
     def __init__(self, cfg, vocab):
         super().__init__()
@@ -56,6 +60,10 @@ class TransformerGAN(nn.Module):
         self.gumbel_noise_source = None
         self.gp_alpha_source = None
         self.last_sampled_ids = None
+        # replay the adversarial phase of forward() as one CUDA graph per (phase, batch shape); see _gan_phase_graphed
+        self.use_cuda_graphs = False
+        self._gan_graphs, self._gan_warm = {}, set()
+        self.disc_tf32 = True  # TF32 tensor-core GEMMs for the discriminator when the generator computes in bf16
 
     # ------------------------------------------------------------------------------------------------ discriminator
     def create_bert_model(self, model_name_or_path, loss_type, model_type=None, random_weights=False):
@@ -92,7 +100,15 @@ class TransformerGAN(nn.Module):
         return self.discriminator.bert.embeddings.word_embeddings.weight
 
     def _bert_logit(self, inputs_embeds):
-        return self.discriminator(inputs_embeds=inputs_embeds)[0][:, 0]
+        """Logit column 0 of BertForSequenceClassification(inputs_embeds=...) (transformer_gan.py:403-416), calling the
+        sub-modules directly: with no padding the all-ones attention mask HuggingFace builds adds exactly 0.0 to every
+        score, and its construction (a host scalar copied to the device) cannot be captured in a CUDA graph."""
+        m = self.discriminator
+        bert = m.bert
+        h = bert.embeddings(inputs_embeds=inputs_embeds)
+        h = bert.encoder(h, attention_mask=None)
+        h = h[0] if isinstance(h, (tuple, list)) else h.last_hidden_state
+        return m.classifier(m.dropout(bert.pooler(h)))[:, 0]
 
     def calc_gradient_penalty(self, real_data, fake_data, LAMBDA=10):
         """WGAN-GP on interpolated one-hot rows (transformer_gan.py:203-230).  real / fake: [B, T, V'] float."""
@@ -160,6 +176,86 @@ class TransformerGAN(nn.Module):
             out["mle"], out["mems"] = self.generator(data, target, reset_mems, mems)
         if "gen" not in train_loss and "dis" not in train_loss:
             return out
+        # In bf16 mode the discriminator's GEMMs (HuggingFace BERT / RelGAN_D: library code, fp32 tensors) run on the
+        # tensor cores as TF32 -- more mantissa than the generator's own bf16 operands; fp32 mode keeps them exact.
+        tf32 = self.disc_tf32 and gen_is_bf16(self.generator)
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32 or prev_tf32
+        try:
+            if (self.use_cuda_graphs and data.is_cuda and self.gumbel_noise_source is None and self.gp_alpha_source is None
+                    and self.cfg.DISCRIMINATOR.backprop_outside):
+                out.update(self._gan_phase_graphed(data, train_loss))
+            else:
+                out.update(self._gan_phase(data, train_loss))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        return out
+
+    # ------------------------------------------------------------------------------------------------ CUDA graphs
+    def _grad_tensors(self):
+        """Every tensor the GAN phase accumulates gradients into (created as zeros if missing): their addresses are
+        part of a captured graph."""
+        ts = []
+        for m in (self.generator, self.discriminator):
+            for p in m.parameters():
+                if p.requires_grad:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    ts.append(p.grad)
+        return ts
+
+    def _gan_phase_graphed(self, data, train_loss):
+        """The whole adversarial phase -- context pass, the 123-step Gumbel sampling chain, discriminator forward /
+        backward [/ gradient penalty], generator backward through the chain -- as ONE CUDA-graph replay.  The phase is
+        ~7 000 (dis) / ~23 000 (gen) launches of tiny kernels whose shapes depend only on (phase, batch): the host
+        cannot enqueue them as fast as the GPU retires them.  The first call of a key runs eagerly (lazy
+        initialisation), the second is captured, later ones are replayed.  The annealed temperature is read from a
+        device scalar, the noise / dropout streams advance through the device step counter."""
+        from tgan_b200 import lib as L
+        gen = self.generator
+        eng = gen._get_engine()
+        key = (train_loss, tuple(data.shape), gen.training, self.discriminator.training, eng._param_key)
+        if key not in self._gan_graphs:
+            if key not in self._gan_warm:
+                self._gan_warm.add(key)
+                return self._gan_phase(data, train_loss)
+            grads = self._grad_tensors()
+            names = [r for r, *_ in eng.layout.reference_map()]
+            pd = dict(gen.named_parameters())
+            pd.setdefault("crit.out_layers.0.weight", gen.crit.out_layers[0].weight)
+            eng._unpack_desc_for({n: pd[n].grad for n in names})  # descriptor table staged outside the capture
+            entry = type("GanGraph", (), {})()
+            entry.data, entry.tau = data.clone(), torch.ones(1, dtype=torch.float32, device=data.device)
+            entry.grad_ptrs = tuple(t.data_ptr() for t in grads)
+            ctr = L.step_counter(data.device)
+            eng._packed_version = None  # the parameter re-pack must be part of the graph
+            saved_tau, self.temperature = self.temperature, entry.tau
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            try:
+                with torch.cuda.graph(g, pool=eng.graph_pool()):
+                    ctr.add_(1)
+                    entry.out = self._gan_phase(entry.data, train_loss)
+            finally:
+                self.temperature = saved_tau
+                eng._packed_version = None
+            entry.graph, entry.n = g, L.launch_count() - n0
+            self._gan_graphs[key] = entry
+        entry = self._gan_graphs[key]
+        if tuple(t.data_ptr() for t in self._grad_tensors()) != entry.grad_ptrs:
+            del self._gan_graphs[key]  # the gradient buffers moved (zero_grad(set_to_none=True)): capture again
+            return self._gan_phase_graphed(data, train_loss)
+        entry.data.copy_(data)
+        entry.tau.fill_(float(self.temperature))
+        entry.graph.replay()
+        L.note_graph_replay(entry.n)
+        eng.pack_epoch += 1
+        return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in entry.out.items()}
+
+    def _gan_phase(self, data, train_loss):
+        """Adversarial part of ``forward`` (transformer_gan.py:273-533): returns the dis / gen / gp entries of the dict."""
+        out = {}
         dcfg, gen = self.cfg.DISCRIMINATOR, self.generator
         dtype_cfg = dcfg.BERT if dcfg.type == "bert" else dcfg.CNN
         if dcfg.type not in ("bert", "cnn"):
