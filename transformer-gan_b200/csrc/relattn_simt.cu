@@ -204,6 +204,88 @@ relattn_bwd_rows_simt(const T* __restrict__ q, int64_t ldq, const T* __restrict_
     }
 }
 
+// backward pass 2 for decode-sized calls (Q <= SMALLQ): one THREAD per key row.  The warp-per-key kernel below spreads
+// the query rows over the lanes and pays 128 warp reductions per key whatever Q is -- at Q = 1 (every Gumbel sampling
+// step of the GAN phase) that is ~1500 instructions per key for 200 FMAs of work.  Here lane = key: the (q + bias) /
+// dout rows sit in shared memory, each thread streams its own k / v / r rows (full 128-byte lines), keeps its
+// dS / P~ column in shared memory and writes dk / dv with 16-byte stores.  No cross-lane traffic at all.
+constexpr int SMALLQ = 16;
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+relattn_bwd_keys_smallq(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v,
+                        int64_t ldkv, const T* __restrict__ r, int64_t ldr, const float* __restrict__ u,
+                        const float* __restrict__ vb, const uint8_t* __restrict__ reset,
+                        const T* __restrict__ dout, int64_t ldo, const float* __restrict__ lse,
+                        const float* __restrict__ delta, T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv,
+                        AttnArgs a) {
+    __shared__ float s_qu[SMALLQ][HS], s_qv[SMALLQ][HS], s_do[SMALLQ][HS], s_L[SMALLQ], s_dl[SMALLQ];
+    __shared__ float s_ds[SMALLQ][WARPS * 32], s_pw[SMALLQ][WARPS * 32];
+    const int bn = blockIdx.y, b = bn / a.N, n = bn % a.N;
+    for (int idx = threadIdx.x; idx < a.Q * HS; idx += blockDim.x) {
+        const int i = idx / HS, d = idx % HS;
+        const int64_t row = (int64_t)i * a.B + b;
+        const float x = to_f(q[row * ldq + n * HS + d]);
+        s_qu[i][d] = x + u[n * HS + d];
+        s_qv[i][d] = x + vb[n * HS + d];
+        s_do[i][d] = to_f(dout[row * ldo + n * HS + d]);
+    }
+    for (int i = threadIdx.x; i < a.Q; i += blockDim.x) {
+        s_L[i] = lse[(int64_t)bn * a.Q + i];
+        s_dl[i] = delta[(int64_t)bn * a.Q + i];
+    }
+    __syncthreads();
+    const int j = blockIdx.x * (WARPS * 32) + threadIdx.x;
+    if (j >= a.K) return;
+    const int64_t krow = (int64_t)j * a.B + b;
+    const T* kr = k + krow * ldkv + n * HS;
+    const T* vr = v + krow * ldkv + n * HS;
+    int ilo = max(0, j - a.M), ihi = a.Q - 1;
+    if (a.same_length) ihi = min(ihi, j + a.msl - 1);
+    if (reset && reset[b] && j < a.M) ihi = -1;
+    // phase 1: dS and the dropped probability of every (query, this key) pair -> thread-private shared-memory columns
+    for (int i = ilo; i <= ihi; ++i) {
+        const T* rr = r + (int64_t)(j + a.Q - 1 - i) * ldr + n * HS;
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < HS / 8; ++c) {
+            float kk[8], yy[8], vv[8];
+            load8(kr + 8 * c, kk);
+            load8(rr + 8 * c, yy);
+            load8(vr + 8 * c, vv);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int d = 8 * c + t;
+                s = fmaf(s_qu[i][d], kk[t], fmaf(s_qv[i][d], yy[t], s));
+                dp = fmaf(s_do[i][d], vv[t], dp);
+            }
+        }
+        const float pr = expf(s * a.scale - s_L[i]);
+        const bool keep = drop_keep_ij(a, bn, i, j);
+        dp = keep ? dp * a.drop_scale : 0.f;
+        s_pw[i][threadIdx.x] = keep ? pr * a.drop_scale : 0.f;
+        s_ds[i][threadIdx.x] = pr * (dp - s_dl[i]) * a.scale;
+    }
+    // phase 2: dk_j = sum_i dS_ij (q_i + u), dv_j = sum_i P~_ij dout_i, eight columns at a time
+    T* dkr = dk + krow * lddkv + n * HS;
+    T* dvr = dv + krow * lddkv + n * HS;
+#pragma unroll
+    for (int c = 0; c < HS / 8; ++c) {
+        float ak[8], av[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { ak[t] = 0.f; av[t] = 0.f; }
+        for (int i = ilo; i <= ihi; ++i) {
+            const float ds = s_ds[i][threadIdx.x], pw = s_pw[i][threadIdx.x];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                ak[t] = fmaf(ds, s_qu[i][8 * c + t], ak[t]);
+                av[t] = fmaf(pw, s_do[i][8 * c + t], av[t]);
+            }
+        }
+        store8(dkr + 8 * c, ak);
+        store8(dvr + 8 * c, av);
+    }
+}
+
 // backward pass 2: per key row -> dk, dv
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -396,10 +478,19 @@ static int bwd_launch(const void* q, int64_t ldq, const void* k, const void* v, 
                                                          delta, (T*)dq, du, dvb, a);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
-    dim3 g2(ceil_div(a.K, WARPS), a.B * a.N);
-    relattn_bwd_keys_simt<T><<<g2, WARPS * 32, 0, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)r,
-                                                         ldr, u, vb, reset, (const T*)dout, ldo, lse, delta, (T*)dk,
-                                                         (T*)dv, lddkv, a);
+    const bool vec_ok = ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)dk | (uintptr_t)dv) & 31) == 0) &&
+                        ldkv % 8 == 0 && ldr % 8 == 0 && lddkv % 8 == 0;
+    if (a.Q <= SMALLQ && vec_ok) {
+        dim3 g2(ceil_div(a.K, WARPS * 32), a.B * a.N);
+        relattn_bwd_keys_smallq<T><<<g2, WARPS * 32, 0, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv,
+                                                               (const T*)r, ldr, u, vb, reset, (const T*)dout, ldo, lse,
+                                                               delta, (T*)dk, (T*)dv, lddkv, a);
+    } else {
+        dim3 g2(ceil_div(a.K, WARPS), a.B * a.N);
+        relattn_bwd_keys_simt<T><<<g2, WARPS * 32, 0, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)r,
+                                                             ldr, u, vb, reset, (const T*)dout, ldo, lse, delta, (T*)dk,
+                                                             (T*)dv, lddkv, a);
+    }
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     dim3 g3(ceil_div(a.K, WARPS), a.N);
