@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the GAN-phase and generation side measurements")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "the captured forward / backward CUDA graphs of each ring phase")
     ap.add_argument("--cpu-batch", type=int, default=4)
@@ -209,6 +210,83 @@ def workload_config(args, world):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Side measurements of the other hot-path configurations: reported next to the headline, not part of it
+# ---------------------------------------------------------------------------------------------------------
+def time_calls(fn, reps):
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def gan_phase_extra(dev, B, mle_ms, graphs):
+    """experiment_spanbert.yml adversarial phase (transformer_gan.py:232-533): one "dis_loss" and one "gen_loss" call on
+    a [128, B] batch -- 123 Gumbel sampling steps, BERT 5x768 discriminator (seeded random weights), WGAN-GP -- and the
+    tokens/s of the 5-step cycle train.py runs (dis_loss_freq = gen_loss_freq = 5)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gan_bench as G
+    from tgan_b200 import lib as L
+    model = G.build(dev)
+    model.temperature = 1.0
+    model.use_cuda_graphs = graphs
+    data = torch.randint(2, WORK["n_token"], (128, B), generator=torch.Generator().manual_seed(7)).to(dev)
+    res = {"batch": B, "sampling_steps": 123, "discriminator": "BERT 5x768 (HuggingFace, TF32), wgan-gp",
+           "launch": "one CUDA graph per phase" if graphs else "host launches"}
+    for phase in ("dis_loss", "gen_loss"):
+        def call():
+            model.zero_grad(set_to_none=False)
+            float(model(data, None, None, phase)[phase])
+        for _ in range(2 if graphs else 1):  # eager (lazy initialisation), then the capturing call
+            call()
+        n0 = L.launch_count()
+        res[phase + "_ms"] = time_calls(call, 2)
+        res[phase + "_launches"] = (L.launch_count() - n0) // 2
+    toks = 5 * WORK["tgt_len"] * B
+    res["cycle_tokens_per_s"] = toks / ((5 * mle_ms + res["dis_loss_ms"] + res["gen_loss_ms"]) / 1e3)
+    res["cycle"] = "5 MLE steps + 1 discriminator update + 1 generator update (train.py:924-1090)"
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def generate_extra(model, dev, B=128, mem_len=4146, steps=48):
+    """inference_unconditional.yml decode step (generate.py:132-226 -> forward_generate, mem_transformer.py:578-600):
+    one new token per sequence against a full memory of 4146 positions, K/V projections served from the cache."""
+    V = WORK["n_token"]
+    g = torch.Generator().manual_seed(3)
+    was_training, cached = model.training, (model.tgt_len, model.mem_len)
+    graphs, model.use_cuda_graphs = model.use_cuda_graphs, False
+    model.eval()
+    try:
+        with torch.no_grad():
+            mems = None
+            model.reset_length(128, mem_len)
+            for _ in range((mem_len + 127) // 128):  # fill the memory with 128-token segments
+                _, mems = model.forward_generate(torch.randint(2, V, (128, B), generator=g).to(dev), mems)
+            model.reset_length(1, mem_len)
+            tok = torch.randint(2, V, (1, B), generator=g).to(dev)
+            state = {"mems": mems}
+
+            def step():
+                logits, state["mems"] = model.forward_generate(tok, state["mems"])
+                return logits
+            for _ in range(3):
+                step()
+            ms = time_calls(lambda: [step() for _ in range(steps)], 2) / steps
+    finally:
+        model.reset_length(*cached)
+        model.train(was_training)
+        model.use_cuda_graphs = graphs
+    return {"batch": B, "mem_len": mem_len, "ms_per_step": ms, "tokens_per_s": B / (ms / 1e3),
+            "note": "logits only (sampling / top-k is the caller's, generate.py:228-304); host-launched"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -335,6 +413,17 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if pk else "fallback 1.59 PFLOP/s",
                 "us_per_launch": t * 1e6}
         del A, W, C
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras and args.dtype == "bf16":
+        extras = {}
+        try:
+            extras["generate"] = generate_extra(model, dev)
+        except Exception as e:  # noqa: BLE001  (side measurement: never lose the headline line)
+            extras["generate"] = {"error": repr(e)[:200]}
+        try:
+            extras["gan_phase"] = gan_phase_extra(dev, args.global_batch, ms_dev / args.steps, not args.no_graphs)
+        except Exception as e:  # noqa: BLE001
+            extras["gan_phase"] = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.cpu_batch)
@@ -352,7 +441,7 @@ def main():
             "gpu_launches": launches,
             "step_tensor_frac_of_sustained_peak": step_flops / (ms_dev / args.steps / 1e3) / world /
                                                   (pk.get("bf16_tflops_sustained", 1400.0) * 1e12),
-            "roofline": roof, "cpu_baseline": cpu}))
+            "roofline": roof, "cpu_baseline": cpu, "extras": extras}))
     if world > 1:
         dist.destroy_process_group()
 
