@@ -465,36 +465,66 @@ __global__ void convert_kernel(const TS* __restrict__ src, int64_t lds, TD* __re
 // ------------------------------------------------------------------------------------------------------------
 // parameter packing / gradient unpacking (descriptor table, one launch)
 // ------------------------------------------------------------------------------------------------------------
+// block = 32 x 8 threads; 32-bit index arithmetic (every tensor of the model has < 2^31 elements); rows are walked by
+// thread rows so both sides of the copy are coalesced, transposed destinations go through a 32 x 32 shared-memory tile
 template <typename T>
-__global__ void pack_kernel(T* __restrict__ mat, float* __restrict__ vec, const int64_t* __restrict__ desc) {
+__global__ void __launch_bounds__(256) pack_kernel(T* __restrict__ mat, float* __restrict__ vec,
+                                                   const int64_t* __restrict__ desc) {
     const int64_t* d = desc + 12 * blockIdx.y;
-    const float* src = reinterpret_cast<const float*>(d[0]);
-    const int64_t dst_off = d[1], rows = d[2], cols = d[3], ld = d[4], rg = d[5], rgp = d[6], cg = d[7], cgp = d[8];
+    const float* __restrict__ src = reinterpret_cast<const float*>(d[0]);
+    const int64_t dst_off = d[1], ld = d[4];
+    const int rows = (int)d[2], cols = (int)d[3], rg = (int)d[5], rgp = (int)d[6], cg = (int)d[7], cgp = (int)d[8];
     const bool tr = d[9] != 0, is_vec = d[10] != 0;
-    const int64_t total = rows * cols;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = e / cols, c = e % cols;
-        int64_t rp = (r / rg) * rgp + r % rg, cp = (c / cg) * cgp + c % cg;
-        int64_t o = dst_off + (tr ? cp * ld + rp : rp * ld + cp);
-        float v = src[e];
-        if (is_vec) vec[o] = v;
-        else mat[o] = from_f<T>(v);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (!tr) {
+        for (int r = blockIdx.x * 8 + ty; r < rows; r += gridDim.x * 8) {
+            const int64_t o = dst_off + (int64_t)((r / rg) * rgp + r % rg) * ld;
+            const float* sr = src + (int64_t)r * cols;
+            for (int c = tx; c < cols; c += 32) {
+                const int cp = (c / cg) * cgp + c % cg;
+                if (is_vec) vec[o + cp] = sr[c];
+                else mat[o + cp] = from_f<T>(sr[c]);
+            }
+        }
+        return;
+    }
+    __shared__ float tile[32][33];
+    const int tiles_c = (cols + 31) >> 5, tiles = ((rows + 31) >> 5) * tiles_c;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int r0 = (t / tiles_c) << 5, c0 = (t % tiles_c) << 5;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k, c = c0 + tx;
+            tile[ty + 8 * k][tx] = (r < rows && c < cols) ? src[(int64_t)r * cols + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k, r = r0 + tx;
+            if (r < rows && c < cols) {
+                const int cp = (c / cg) * cgp + c % cg, rp = (r / rg) * rgp + r % rg;
+                mat[dst_off + (int64_t)cp * ld + rp] = from_f<T>(tile[tx][ty + 8 * k]);
+            }
+        }
+        __syncthreads();
     }
 }
 
-__global__ void unpack_kernel(const float* __restrict__ mat, const float* __restrict__ vec,
-                              const int64_t* __restrict__ desc, int accumulate) {
+__global__ void __launch_bounds__(256) unpack_kernel(const float* __restrict__ mat, const float* __restrict__ vec,
+                                                     const int64_t* __restrict__ desc, int accumulate) {
     const int64_t* d = desc + 12 * blockIdx.y;
-    float* dst = reinterpret_cast<float*>(d[0]);
-    const int64_t off = d[1], rows = d[2], cols = d[3], ld = d[4], rg = d[5], rgp = d[6], cg = d[7], cgp = d[8];
-    const bool is_vec = d[10] != 0;
-    const int64_t total = rows * cols;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = e / cols, c = e % cols;
-        int64_t rp = (r / rg) * rgp + r % rg, cp = (c / cg) * cgp + c % cg;
-        int64_t o = off + rp * ld + cp;
-        const float v = is_vec ? vec[o] : mat[o];
-        dst[e] = accumulate ? dst[e] + v : v;
+    float* __restrict__ dst = reinterpret_cast<float*>(d[0]);
+    const int64_t off = d[1], ld = d[4];
+    const int rows = (int)d[2], cols = (int)d[3], rg = (int)d[5], rgp = (int)d[6], cg = (int)d[7], cgp = (int)d[8];
+    const float* __restrict__ srcp = d[10] != 0 ? vec : mat;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = blockIdx.x * 8 + ty; r < rows; r += gridDim.x * 8) {
+        const float* sr = srcp + off + (int64_t)((r / rg) * rgp + r % rg) * ld;
+        float* dr = dst + (int64_t)r * cols;
+        for (int c = tx; c < cols; c += 32) {
+            const float v = sr[(c / cg) * cgp + c % cg];
+            dr[c] = accumulate ? dr[c] + v : v;
+        }
     }
 }
 
