@@ -126,6 +126,91 @@ relattn_fwd_simt(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Forward for decode-sized calls (Q <= DECODE_Q): one CTA per (query row, sequence, head), its DECODE_WARPS warps split
+// the keys in 32-key chunks ("flash decoding").  Score phase: lane = key (each lane streams its own 128-byte k / r
+// rows); value phase: lane = two head dims (the chunk's probabilities are broadcast with shuffles and every v row is
+// one coalesced 128-byte warp load), so a lane carries 2 accumulators instead of 64 and nothing is reduced across
+// lanes at the end.  The warps' partial (max, sum, out) triples meet in shared memory.
+// The generic kernel above runs ONE warp per (row, sequence, head): at Q = 1 that is 13 % occupancy and a 64-way
+// warp reduction per row -- the decode step then sits ~7x above the time the K/V cache stream needs.
+constexpr int DECODE_Q = 8, DECODE_WARPS = 8;
+__device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load2(const bf16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T>
+__global__ void __launch_bounds__(DECODE_WARPS * 32)
+relattn_fwd_decode(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v,
+                   int64_t ldkv, const T* __restrict__ r, int64_t ldr, const float* __restrict__ u,
+                   const float* __restrict__ vb, const uint8_t* __restrict__ reset, T* __restrict__ out, int64_t ldo,
+                   float* __restrict__ lse, AttnArgs a) {
+    __shared__ float s_qu[HS], s_qv[HS];
+    __shared__ float s_m[DECODE_WARPS], s_l[DECODE_WARPS], s_o[DECODE_WARPS][HS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x;
+    const int bn = blockIdx.y, b = bn / a.N, n = bn % a.N;
+    const int64_t row = (int64_t)i * a.B + b;
+    for (int d = threadIdx.x; d < HS; d += blockDim.x) {
+        const float qd = to_f(q[row * ldq + n * HS + d]);
+        s_qu[d] = qd + u[n * HS + d];
+        s_qv[d] = qd + vb[n * HS + d];
+    }
+    __syncthreads();
+    int jlo = 0, jhi = min(a.K - 1, i + a.M);
+    if (a.same_length) jlo = max(0, i - a.msl + 1);
+    if (reset && reset[b]) jlo = max(jlo, a.M);
+    float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;  // m: warp-uniform running max; l: this lane's share of the sum
+    for (int j0 = jlo + 32 * warp; j0 <= jhi; j0 += 32 * DECODE_WARPS) {
+        const int j = j0 + lane;
+        float s = -INFINITY;
+        if (j <= jhi) {
+            const T* kr = k + ((int64_t)j * a.B + b) * ldkv + n * HS;
+            const T* rr = r + (int64_t)(j + a.Q - 1 - i) * ldr + n * HS;
+            s = dot_row2(s_qu, kr, s_qv, rr) * a.scale;
+        }
+        const float mn = fmaxf(m, warp_max(s));  // finite: the chunk holds at least key j0
+        const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+        const float pe = (j <= jhi) ? expf(s - mn) : 0.f;
+        l = l * corr + pe;
+        const float pw = (j <= jhi && drop_keep_ij(a, bn, i, j)) ? pe * a.drop_scale : 0.f;
+        acc0 *= corr; acc1 *= corr;
+        m = mn;
+        const int nk = min(32, jhi - j0 + 1);
+        const T* vbase = v + ((int64_t)j0 * a.B + b) * ldkv + n * HS + 2 * lane;
+#pragma unroll 8
+        for (int jj = 0; jj < nk; ++jj) {
+            const float pj = __shfl_sync(0xffffffffu, pw, jj);
+            const T* vr = vbase + (int64_t)jj * a.B * ldkv;
+            const float2 vv = load2(vr);
+            acc0 = fmaf(pj, vv.x, acc0);
+            acc1 = fmaf(pj, vv.y, acc1);
+        }
+    }
+    const float lw = warp_sum(l);
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = lw; }
+    s_o[warp][2 * lane] = acc0;
+    s_o[warp][2 * lane + 1] = acc1;
+    __syncthreads();
+    if (warp == 0) {
+        float m_all = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < DECODE_WARPS; ++w) m_all = fmaxf(m_all, s_m[w]);
+        float l_all = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < DECODE_WARPS; ++w) {
+            const float f = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - m_all);
+            l_all = fmaf(s_l[w], f, l_all);
+            o0 = fmaf(s_o[w][2 * lane], f, o0);
+            o1 = fmaf(s_o[w][2 * lane + 1], f, o1);
+        }
+        const float inv = l_all > 0.f ? 1.f / l_all : 0.f;
+        out[row * ldo + n * HS + 2 * lane] = from_f<T>(o0 * inv);
+        out[row * ldo + n * HS + 2 * lane + 1] = from_f<T>(o1 * inv);
+        if (lane == 0) lse[(int64_t)bn * a.Q + i] = l_all > 0.f ? m_all + logf(l_all) : -INFINITY;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // backward pass 1: per query row -> dq, delta, du, dvb
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -452,6 +537,21 @@ int tgan_relattn_fwd_simt(int dtype, const void* q, int64_t ldq, const void* k, 
                           int64_t ldo, float* lse, int B, int N, int Q, int M, int msl, int same_length, float scale,
                           float drop_p, uint64_t seed, uint64_t site, cudaStream_t st) {
     AttnArgs a = make_args(B, N, Q, M, msl, same_length, scale, drop_p, seed, site);
+    const bool vec_ok = ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)r) & 31) == 0) && ldkv % 8 == 0 && ldr % 8 == 0;
+    if (Q <= DECODE_Q && vec_ok) {
+        dim3 gd(Q, B * N);
+        if (dtype == TGAN_F32)
+            relattn_fwd_decode<float><<<gd, DECODE_WARPS * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v,
+                                                                         ldkv, (const float*)r, ldr, u, vb, reset,
+                                                                         (float*)out, ldo, lse, a);
+        else
+            relattn_fwd_decode<bf16><<<gd, DECODE_WARPS * 32, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v,
+                                                                        ldkv, (const bf16*)r, ldr, u, vb, reset,
+                                                                        (bf16*)out, ldo, lse, a);
+        TGAN_COUNT_LAUNCH();
+        TGAN_LAUNCH_OK();
+        return 0;
+    }
     dim3 grid(ceil_div(Q, WARPS), B * N);
     if (dtype == TGAN_F32)
         relattn_fwd_simt<float><<<grid, WARPS * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v,
