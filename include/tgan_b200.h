@@ -94,10 +94,12 @@ int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t ld, int kle
 int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
                 const float* beta, float* mean, float* rstd, int rows, int D, int DP, void* stream);
 /* dz = LN'(dy) ; dz_drop (optional) = dropmask(seed, site)(dz) / (1-p) -- the gradient entering the dropout
- * that precedes the residual add; dgamma / dbeta (fp32 [D]) are accumulated (+=).                         */
+ * that precedes the residual add; dgamma / dbeta (fp32 [D]) are accumulated (+=).  dsum (optional, fp32 [D],
+ * accumulated): column sums of dz_drop (of dz when dz_drop is NULL) = the bias gradient of the Linear whose output
+ * feeds this LayerNorm (CoreNet.3.bias, mem_transformer.py:38) -- saves a separate pass over the rows.      */
 int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float* z, int64_t ldz, const float* gamma,
                 const float* mean, const float* rstd, void* dz, int64_t lddz, void* dz_drop, int64_t lddd,
-                float* dgamma, float* dbeta, int rows, int D, int DP, float drop_p, uint64_t seed,
+                float* dgamma, float* dbeta, float* dsum, int rows, int D, int DP, float drop_p, uint64_t seed,
                 uint64_t site, void* stream);
 
 /* ---- stateless dropout (Philox4x32-10 keyed by seed/site/element): nn.Dropout sites of :37,39,248,557,573 -

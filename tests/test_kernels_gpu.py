@@ -133,7 +133,10 @@ def test_layernorm_fwd_bwd(dtype):
     dy = _rand(rows, DP, dtype=dtype, seed=4)
     dz, dzd = torch.empty_like(dy), torch.empty_like(dy)
     dg, db = torch.zeros(DP, device="cuda"), torch.zeros(DP, device="cuda")
-    L.ln_bwd(dy, z, gamma, mean, rstd, dz, dzd, dg, db, rows, D, DP, 0.2, 3, 9)
+    dsum = torch.zeros(DP, device="cuda")
+    L.ln_bwd(dy, z, gamma, mean, rstd, dz, dzd, dg, db, rows, D, DP, 0.2, 3, 9, dsum=dsum)
+    # fused bias gradient: column sums of the dropped gradient (fp32 sums of the values before the bf16 store)
+    assert (dsum[:D] - dzd[:, :D].float().sum(0)).abs().max() < (1e-4 if dtype == torch.float32 else 0.15)
     gref = gamma[:D].double().clone().requires_grad_(True)
     bref = beta[:D].double().clone().requires_grad_(True)
     out = torch.nn.functional.layer_norm(zr, (D,), gref, bref)

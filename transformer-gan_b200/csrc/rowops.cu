@@ -196,22 +196,23 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const floa
                               const float* __restrict__ gamma, const float* __restrict__ mean,
                               const float* __restrict__ rstd, T* __restrict__ dz, int64_t lddz,
                               T* __restrict__ dzd, int64_t lddd, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta, int rows, int D, int DP, int rows_per_block,
-                              float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
-    extern __shared__ float sm[];  // [2][DP]
+                              float* __restrict__ dbeta, float* __restrict__ dsum, int rows, int D, int DP,
+                              int rows_per_block, float drop_scale, uint32_t thresh, uint64_t seed, uint64_t site) {
+    extern __shared__ float sm[];  // [3][DP]
     float* s_dg = sm;
     float* s_db = sm + DP;
-    for (int c = threadIdx.x; c < 2 * DP; c += blockDim.x) sm[c] = 0.f;
+    float* s_dd = sm + 2 * DP;
+    for (int c = threadIdx.x; c < 3 * DP; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t key = step_fold(dropout_key(seed, site));
-    float pg[MAXU][4], pb[MAXU][4], gm[MAXU][4];
+    float pg[MAXU][4], pb[MAXU][4], pd[MAXU][4], gm[MAXU][4];
 #pragma unroll
     for (int u = 0; u < MAXU; ++u) {
         const int c = lane * 4 + 128 * u;
         if (c < DP) load4(gamma + c, gm[u]);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { pg[u][t] = pb[u][t] = 0.f; if (c >= DP) gm[u][t] = 0.f; }
+        for (int t = 0; t < 4; ++t) { pg[u][t] = pb[u][t] = pd[u][t] = 0.f; if (c >= DP) gm[u][t] = 0.f; }
     }
     const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
     for (int row = r_begin + warp; row < r_end; row += WPB) {
@@ -261,6 +262,7 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const floa
                     const float val = c + t < D ? rs * (g[u][t] - s1 - xh[u][t] * s2) : 0.f;
                     o[t] = val;
                     od[t] = ((keep >> t) & 1) ? val * drop_scale : 0.f;
+                    pd[u][t] += dzd ? od[t] : val;
                 }
                 store4(dz + (int64_t)row * lddz + c, o);
                 if (dzd) store4(dzd + (int64_t)row * lddd + c, od);
@@ -275,6 +277,7 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const floa
             for (int t = 0; t < 4; ++t) {
                 atomicAdd(&s_dg[c + t], pg[u][t]);
                 atomicAdd(&s_db[c + t], pb[u][t]);
+                if (dsum) atomicAdd(&s_dd[c + t], pd[u][t]);
             }
         }
     }
@@ -282,6 +285,7 @@ __global__ void ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const floa
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
         atomicAdd(&dgamma[c], s_dg[c]);
         atomicAdd(&dbeta[c], s_db[c]);
+        if (dsum) atomicAdd(&dsum[c], s_dd[c]);
     }
 }
 
@@ -651,8 +655,8 @@ extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int6
 
 extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float* z, int64_t ldz, const float* gamma,
                            const float* mean, const float* rstd, void* dz, int64_t lddz, void* dz_drop, int64_t lddd,
-                           float* dgamma, float* dbeta, int rows, int D, int DP, float drop_p, uint64_t seed,
-                           uint64_t site, void* stream) {
+                           float* dgamma, float* dbeta, float* dsum, int rows, int D, int DP, float drop_p,
+                           uint64_t seed, uint64_t site, void* stream) {
     if (rows <= 0) return 0;
     TGAN_CHECK_ARG(DP % 8 == 0 && DP <= 1024 && lddy % 8 == 0 && lddz % 8 == 0 && (!dz_drop || lddd % 8 == 0) &&
                        ldz % 4 == 0 && (((uintptr_t)gamma | (uintptr_t)z) & 15) == 0,
@@ -662,15 +666,15 @@ extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float*
     int blocks = min(ceil_div(rows, WPB), 148 * 4);
     int rpb = ceil_div(rows, blocks);
     blocks = ceil_div(rows, rpb);
-    size_t smem = 2 * DP * sizeof(float);
+    size_t smem = 3 * DP * sizeof(float);
     if (DP <= 512) {
         DISPATCH_T(dtype, (ln_bwd_kernel<T, 4><<<blocks, WPB * 32, smem, ST>>>(
                               (const T*)dy, lddy, z, ldz, gamma, mean, rstd, (T*)dz, lddz, (T*)dz_drop, lddd, dgamma,
-                              dbeta, rows, D, DP, rpb, ds, th, seed, site)));
+                              dbeta, dsum, rows, D, DP, rpb, ds, th, seed, site)));
     } else {
         DISPATCH_T(dtype, (ln_bwd_kernel<T, 8><<<blocks, WPB * 32, smem, ST>>>(
                               (const T*)dy, lddy, z, ldz, gamma, mean, rstd, (T*)dz, lddz, (T*)dz_drop, lddd, dgamma,
-                              dbeta, rows, D, DP, rpb, ds, th, seed, site)));
+                              dbeta, dsum, rows, D, DP, rpb, ds, th, seed, site)));
     }
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();

@@ -582,9 +582,9 @@ class TxlEngine:
             # LN2 backward
             dz2, dz2d = self._buf(R, DP), (self._buf(R, DP) if p_drop > 0 else None)
             L.ln_bwd(dx, sv.z2, self._v(p + "ln2_g"), sv.mean2, sv.rstd2, dz2, dz2d, self._gv(p + "ln2_g"),
-                     self._gv(p + "ln2_b"), R, D, DP, p_drop, seed, self._site(cid, 11 + 4 * l))
+                     self._gv(p + "ln2_b"), R, D, DP, p_drop, seed, self._site(cid, 11 + 4 * l),
+                     dsum=self._gv(p + "b2"))  # db2 = column sums of the gradient entering W2's output dropout
             g2 = dz2d if dz2d is not None else dz2
-            L.colsum(g2, gv, R, D, ld=DP, out_off=lay.vec[p + "b2"][0])
             wgrad(p + "W2", g2, sv.h, R, DP, DIP, ldy=DP, ldx=DIP)
             w2toff, w2tld = self._m(p + "W2.T")
             dh = self._buf(R, DIP)

@@ -43,7 +43,7 @@ _SIGS = {
     "tgan_embed_bwd": [I, P, P, L, P, L, I, I, I, F, F, U, U, P],
     "tgan_pos_emb": [I, P, P, L, I, I, I, I, F, U, U, P],
     "tgan_ln_fwd": [I, P, L, P, L, P, P, P, P, I, I, I, P],
-    "tgan_ln_bwd": [I, P, L, P, L, P, P, P, P, L, P, L, P, P, I, I, I, F, U, U, P],
+    "tgan_ln_bwd": [I, P, L, P, L, P, P, P, P, L, P, L, P, P, P, I, I, I, F, U, U, P],
     "tgan_dropout": [I, P, L, P, L, I, I, F, U, U, P],
     "tgan_relattn_fwd": [I, P, L, P, P, L, P, L, P, P, P, P, L, P, I, I, I, I, I, I, F, F, U, U, I, P],
     "tgan_relattn_bwd": [I, P, L, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P, P, L, P, L, P, P, I, I, I, I, I, I,
@@ -169,10 +169,10 @@ def ln_fwd(z, y, gamma, beta, mean, rstd, rows, D, DP, y_off=0):
           DP, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), rows, D, DP, _stream())
 
 
-def ln_bwd(dy, z, gamma, mean, rstd, dz, dz_drop, dgamma, dbeta, rows, D, DP, drop_p, seed, site, dy_off=0):
+def ln_bwd(dy, z, gamma, mean, rstd, dz, dz_drop, dgamma, dbeta, rows, D, DP, drop_p, seed, site, dy_off=0, dsum=None):
     _call("tgan_ln_bwd", dtype_code(dz.dtype), dy.data_ptr() + dy_off * dy.element_size(), DP, z.data_ptr(),
           z.stride(0), _ptr(gamma), _ptr(mean), _ptr(rstd), dz.data_ptr(), dz.stride(0),
-          _ptr(dz_drop), DP, _ptr(dgamma), _ptr(dbeta), rows, D, DP, drop_p, seed, site, _stream())
+          _ptr(dz_drop), DP, _ptr(dgamma), _ptr(dbeta), _ptr(dsum), rows, D, DP, drop_p, seed, site, _stream())
 
 
 def dropout(src, dst, rows, cols, lds, ldd, p, seed, site, src_off=0, dst_off=0):
