@@ -103,6 +103,32 @@ def test_gemm_tc_large_k_accumulation_and_persistence():
     assert (C.float() - ref).abs().max().item() < 0.3
 
 
+@pytest.mark.parametrize("cdtype", [torch.bfloat16, torch.float32])
+def test_gemm_tc_cta_pair_kernel(cdtype):
+    """Shapes with >= 74 output tiles of 256 x 256 take the 2-CTA (cta_group::2) kernel: plain, fused FFN and residual
+    epilogues, ragged M / N edges, dropout mask identical to the SIMT kernel's."""
+    L = _lib()
+    M, N, K = 4100, 1288, 520
+    A, B = _rand(M, K, dtype=torch.bfloat16, seed=3, scale=0.5), _rand(N, K, dtype=torch.bfloat16, seed=4, scale=0.5)
+    bias, aux = _rand(N, seed=5), _rand(M, N, dtype=torch.bfloat16, seed=6)
+    ref0 = A.float() @ B.float().t()
+    tol = 0.15 if cdtype == torch.bfloat16 else 0.02
+
+    def run(flags, impl=2, **kw):
+        C = torch.full((M, N), 7.0, device="cuda", dtype=cdtype)
+        L.gemm(A, B, C, M=M, N=N, K=K, bias=bias, aux=aux, ldaux=N, flags=flags, impl=impl, **kw)
+        torch.cuda.synchronize()
+        return C.float()
+
+    assert (run(0) - ref0).abs().max() < tol
+    assert (run(L.EPI_BIAS | L.EPI_RELU) - torch.relu(ref0 + bias)).abs().max() < tol
+    assert (run(L.EPI_ADD_AUX) - (ref0 + aux.float())).abs().max() < tol
+    d = run(L.EPI_BIAS | L.EPI_RELU | L.EPI_DROPOUT, drop_p=0.25, seed=11, site=5)
+    d1 = run(L.EPI_BIAS | L.EPI_RELU | L.EPI_DROPOUT, impl=1, drop_p=0.25, seed=11, site=5)
+    pos = torch.relu(ref0 + bias) > 0.05
+    assert torch.equal((d != 0) & pos, (d1 != 0) & pos), "2-CTA and SIMT epilogues disagree on the dropout mask"
+
+
 def test_gemm_fp32_simt_exact():
     L = _lib()
     M, N, K = 77, 130, 500

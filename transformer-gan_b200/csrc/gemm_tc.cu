@@ -511,6 +511,240 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ============================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a CTA pair on one TPC computes a 256 x 256 tile.  Each CTA stages its own 128
+// rows of A and its own 128-row HALF of the B tile; one tcgen05.mma (M = 256) issued by the leader reads both CTAs'
+// shared memory and writes each CTA's 128 x 256 accumulator into that CTA's TMEM.  Per CTA and k-block the L2 -> SM
+// traffic drops from 48 KB (A 16 + B 32) to 32 KB: the 1-CTA kernel on the K = 512 projections is bound by exactly
+// that stream (9 GB at ~13 TB/s for the K/V projection).  nn.Linear layout only (A, B K-major), compile-time
+// epilogues only (TMA sink).
+// ============================================================================================================
+constexpr int STAGES2 = 5;
+constexpr int B2_BYTES = 128 * BK * 2;  // this CTA's half of the 256-row B tile
+constexpr int SMEM2 = STAGES2 * (A_BYTES + B2_BYTES) + EPI_WARPS * STAGE_BYTES + 8 * (2 * STAGES2 + 4) + 16 + 1024;
+static_assert(SMEM2 <= 232448, "shared memory budget");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the PEER CTA (the pair leader's)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <typename TC, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, int64_t ldc, int M, int N, int K, EpiParams ep) {
+    static_assert(EPI >= 0, "2-CTA kernel: compile-time epilogues only");
+    constexpr int BN2 = 256, BM2 = 256;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + STAGES2 * A_BYTES;
+    const uint32_t sStage = sB + STAGES2 * B2_BYTES;
+    const uint32_t sBar = sStage + EPI_WARPS * STAGE_BYTES;
+    const uint32_t full0 = sBar, empty0 = sBar + 8 * STAGES2, tfull0 = sBar + 16 * STAGES2, tempty0 = tfull0 + 16;
+    const uint32_t sTmemPtr = tempty0 + 16;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (sTmemPtr - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles_n = (N + BN2 - 1) / BN2, tiles_m = (M + BM2 - 1) / BM2;
+    const int num_tiles = tiles_m * tiles_n;
+    const int nk = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC); }
+    if (warp == 1) tmem_alloc_2sm(sTmemPtr, 2 * BN2);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; completion bytes land on the LEADER's full barrier) =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                const int m0 = (t / tiles_n) * BM2 + 128 * (int)rank, n0 = (t % tiles_n) * BN2 + 128 * (int)rank;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const uint32_t fb = mapa_u32(full0 + 8 * s, 0);
+                    if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + B2_BYTES));
+                    tma_load_2d_2sm(sA + s * A_BYTES, &tmA, fb, kb * BK, m0);
+                    tma_load_2d_2sm(sB + s * B2_BYTES, &tmB, fb, kb * BK, n0);
+                    if (++s == STAGES2) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM2, BN2, 0, 0);
+            const uint64_t da0 = umma_smem_desc(sA, 16, 1024), db0 = umma_smem_desc(sB, 16, 1024);
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int t = pair; t < num_tiles; t += npairs, ++it) {
+                const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * as, aph ^ 1);  // the epilogue warps of BOTH CTAs have drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN2;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = da0 + (uint64_t)((s * A_BYTES) >> 4), db = db0 + (uint64_t)((s * B2_BYTES) >> 4);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_commit_2sm(empty0 + 8 * s);
+                        if (kb == nk - 1) umma_commit_2sm(tfull0 + 8 * as);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES2) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (each CTA drains its own 128 x 256 accumulator) =====================
+        const int eq = warp & 3, eh = (warp - 2) >> 2;
+        constexpr int BOXC = 128 / (int)sizeof(TC);
+        const uint32_t dkey = step_fold(ep.drop_key);
+        const bool reduce = (ep.flags & (EPI_ATOMIC | TGAN_EPI_ACCUM)) != 0;
+        uint8_t* stage = gen_base + (sStage - base) + (warp - 2) * STAGE_BYTES;
+        const uint32_t stage_u32 = sStage + (warp - 2) * STAGE_BYTES;
+        const uint32_t tempty_leader = mapa_u32(tempty0, 0);
+        bool pending = false;
+        int it = 0;
+        for (int t = pair; t < num_tiles; t += npairs, ++it) {
+            const int m0 = (t / tiles_n) * BM2 + 128 * (int)rank, n0 = (t % tiles_n) * BN2;
+            const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tfull0 + 8 * as, aph);
+            tcgen05_fence_after();
+            const int row0 = m0 + 32 * eq;
+            const int64_t row = row0 + lane;
+#pragma unroll 1
+            for (int b0 = eh * (BN2 / 2); b0 < (eh + 1) * (BN2 / 2); b0 += BOXC) {
+                if (n0 + b0 >= N) break;
+#pragma unroll
+                for (int seg = 0; seg < BOXC / 32; ++seg) {
+                    const int c0 = b0 + 32 * seg;
+                    if (n0 + c0 >= N) break;
+                    uint32_t regs[32];
+                    tmem_ld32(tmem_base + as * BN2 + c0 + ((uint32_t)(32 * eq) << 16), regs);
+                    tmem_ld_wait();
+                    if (seg == 0 && pending) {
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                        pending = false;
+                    }
+                    if (row < M) epi_row32_smem<TC, EPI>(regs, row, lane, n0 + c0, seg, N, stage, ldc, ep, dkey);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (reduce) tma_reduce_add_2d(&tmC, stage_u32, n0 + b0, row0);
+                    else tma_store_2d(&tmC, stage_u32, n0 + b0, row0);
+                    tma_store_commit();
+                }
+                pending = true;
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);
+        }
+        if (pending && lane == 0) tma_store_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm(tmem_base, 2 * BN2);
+    }
+}
+
+template <typename TC, int EPI>
+int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int64_t ldc, int M, int N, int K,
+               const EpiParams& ep, cudaStream_t st) {
+    auto kern = gemm_tc2_kernel<TC, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+        attr_set = true;
+    }
+    const int tiles = ceil_div(M, 256) * ceil_div(N, 256);
+    const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    kern<<<2 * pairs, NUM_THREADS, SMEM2, st>>>(tmA, tmB, tmC, ldc, M, N, K, ep);  // __cluster_dims__(2, 1, 1)
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+#define TGAN_LAUNCH2_ARGS tmA, tmB, tmC, ldc, M, N, K, ep, st
+template <typename TC>
+int launch_tc2_epi(int epi_ct, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int64_t ldc, int M,
+                   int N, int K, const EpiParams& ep, cudaStream_t st) {
+    constexpr int B_ = TGAN_EPI_BIAS, R_ = TGAN_EPI_RELU, MP = TGAN_EPI_MASK_POS, AX = TGAN_EPI_ADD_AUX, DR = TGAN_EPI_DROPOUT;
+    switch (epi_ct) {
+        case 0: return launch_tc2<TC, 0>(TGAN_LAUNCH2_ARGS);
+        case B_ | R_: return launch_tc2<TC, B_ | R_>(TGAN_LAUNCH2_ARGS);
+        case B_ | R_ | DR: return launch_tc2<TC, B_ | R_ | DR>(TGAN_LAUNCH2_ARGS);
+        case AX: return launch_tc2<TC, AX>(TGAN_LAUNCH2_ARGS);
+        case AX | DR: return launch_tc2<TC, AX | DR>(TGAN_LAUNCH2_ARGS);
+        case B_ | AX: return launch_tc2<TC, B_ | AX>(TGAN_LAUNCH2_ARGS);
+        case B_ | AX | DR: return launch_tc2<TC, B_ | AX | DR>(TGAN_LAUNCH2_ARGS);
+        case MP: return launch_tc2<TC, MP>(TGAN_LAUNCH2_ARGS);
+        case MP | EPI_ALPHA: return launch_tc2<TC, MP | EPI_ALPHA>(TGAN_LAUNCH2_ARGS);
+        default: return -1;
+    }
+}
+
 template <int BN, bool A_MN, bool B_MN, typename TC, int EPI>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, void* C, int64_t ldc, int M, int N,
               int K, int splits, const EpiParams& ep, cudaStream_t st) {
@@ -648,6 +882,19 @@ int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const
         !getenv("TGAN_GEMM_NO_CT_EPI"))
         epi_ct = (ep.flags & (TGAN_EPI_BIAS | TGAN_EPI_RELU | TGAN_EPI_MASK_POS | TGAN_EPI_ADD_AUX | TGAN_EPI_DROPOUT)) |
                  (alpha != 1.0f ? EPI_ALPHA : 0);
+    // 2-CTA pairs for the nn.Linear layout when there are enough 256 x 256 tiles to fill the 74 pairs
+    static const int use_2cta = getenv("TGAN_GEMM_2CTA") ? atoi(getenv("TGAN_GEMM_2CTA")) : 1;
+    if (use_2cta && !transA && transB && epi_ct >= 0 && splits == 1 && M >= 2048 &&
+        ceil_div(M, 256) * ceil_div(N, 256) >= sm_count() / 2) {
+        CUtensorMap tmA2, tmB2;
+        rc = tc::make_tmap_2d(&tmA2, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, BK);
+        if (rc) return rc;
+        rc = tc::make_tmap_2d(&tmB2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, BK);
+        if (rc) return rc;
+        rc = dtype_c == TGAN_F32 ? launch_tc2_epi<float>(epi_ct, tmA2, tmB2, tmC, ldc, M, N, K, ep, st)
+                                 : launch_tc2_epi<bf16>(epi_ct, tmA2, tmB2, tmC, ldc, M, N, K, ep, st);
+        if (rc >= 0) return rc;
+    }
     if (dtype_c == TGAN_F32) {
         if (BN == 256) return launch_layout<256, float>(transA, transB, epi_ct, tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st);
         return launch_layout<128, float>(transA, transB, epi_ct, tmA, tmB, tmC, C, ldc, M, N, K, splits, ep, st);
