@@ -407,9 +407,20 @@ def main():
         t = e0.elapsed_time(e1) / reps / 1e3
         alg_flops = 2.0 * Mrows * WORK["d_model"] * 2 * WORK["d_model"]  # 2*B*K*D*2D
         peak = (pk or {}).get("bf16_tflops", 1590.0)
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (K/V projection, M=%d N=1280 K=512)" % Mrows,
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (taken at M = 589824 rows;
+        # the traffic is the A read + C write, linear in the rows), scaled to this run's rows
+        traffic, traffic_src = None, None
+        try:
+            for e in json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary_v2.json"))):
+                if "gemm_tc" in e["kernel"]:
+                    traffic = e["dram_bytes_total"] * Mrows / 589824.0
+                    traffic_src = "profiles/r1_ncu_full_summary_v2.json (%s, ncu --set full at 589824 rows, scaled by rows)" % e["report"]
+        except Exception:  # noqa: BLE001
+            pass
+        roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel (K/V projection, M=%d N=1280 K=512, CTA pairs)" % Mrows,
                 "achieved": alg_flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": alg_flops / t / 1e12 / peak, "traffic": None,
+                "frac": alg_flops / t / 1e12 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": alg_flops, "padded_flops_per_launch": 2.0 * Mrows * 512 * 1280,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if pk else "fallback 1.59 PFLOP/s",
                 "us_per_launch": t * 1e6}
         del A, W, C
