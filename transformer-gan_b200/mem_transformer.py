@@ -157,7 +157,7 @@ class _GraphEntry:
     """One captured MLE segment: forward graph, backward graph, their static inputs and outputs."""
     fwd = bwd = ectx = None
     n_fwd = n_bwd = 0
-    grad_ptrs = None
+    staged = None
 
 
 class _TxlGraphFunction(torch.autograd.Function):
@@ -182,28 +182,33 @@ class _TxlGraphFunction(torch.autograd.Function):
     def backward(ctx, gout):
         model, entry = ctx.model, ctx.entry
         eng = model._get_engine()
-        targets = {}
-        for n, prm in zip(ctx.names, ctx.params):
-            if prm.grad is None:
-                prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
-            targets[n] = prm.grad
-        ptrs = tuple(t.data_ptr() for t in targets.values())
         entry.dnll.copy_(gout.reshape(-1))
-        if entry.bwd is None or entry.grad_ptrs != ptrs:
-            if entry.ectx.layers is None:
-                raise RuntimeError("the gradient tensors moved after the backward graph was captured; keep .grad "
-                                   "allocated (zero it in place) when use_cuda_graphs is on")
-            eng._unpack_desc_for(targets)  # descriptor table staged outside the capture
+        if entry.bwd is None:
+            # The graph writes the step's parameter gradients into engine-owned staging tensors (reference layout), so
+            # it never depends on where the caller keeps .grad (zero_grad(set_to_none=True) moves it every step).
+            if model._grad_staging is None:  # shared by every captured segment of this model (replayed one at a time)
+                model._grad_staging = {n: torch.empty_like(prm, memory_format=torch.contiguous_format)
+                                       for n, prm in zip(ctx.names, ctx.params)}
+            entry.staged = model._grad_staging
+            # descriptor table staged outside the capture; the entry keeps it alive for the graph's lifetime
+            entry.staged_desc = eng._unpack_desc_for(entry.staged)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(g, pool=eng.graph_pool()):
-                eng.backward(entry.ectx, dnll=entry.dnll, grad_targets=targets)
-            entry.bwd, entry.n_bwd, entry.grad_ptrs = g, L.launch_count() - n0, ptrs
+                eng.backward(entry.ectx, dnll=entry.dnll, grad_targets=entry.staged, accumulate=False)
+            entry.bwd, entry.n_bwd = g, L.launch_count() - n0
             # eng.backward dropped the activations: their pool blocks may now be reused by the next key's capture
             # (graphs that share the pool are replayed strictly one after the other)
         entry.bwd.replay()
         L.note_graph_replay(entry.n_bwd)
+        grads, staged = [], []
+        for n, prm in zip(ctx.names, ctx.params):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
+            grads.append(prm.grad)
+            staged.append(entry.staged[n])
+        torch._foreach_add_(grads, staged)  # one multi-tensor kernel: .grad += this segment's gradients
         model._graph_pending = None
         return (None, None, None) + (None,) * len(ctx.names)
 
@@ -253,6 +258,7 @@ class MemTransformerLM(nn.Module):
         self.use_cuda_graphs = False
         self._graphs = {}
         self._graph_pending = None
+        self._grad_staging = None
 
     # ---- reference API ---------------------------------------------------------------------------------
     def reset_length(self, tgt_len, mem_len):

@@ -527,11 +527,12 @@ class TxlEngine:
 
     # -- backward -----------------------------------------------------------------------------------------
     def backward(self, ctx: _Ctx, dnll: Optional[torch.Tensor] = None, dlogits32: Optional[torch.Tensor] = None,
-                 need_dinput: bool = False, grad_targets: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                 need_dinput: bool = False, grad_targets: Optional[Dict[str, torch.Tensor]] = None,
+                 accumulate: bool = True) -> Dict[str, torch.Tensor]:
         """Gradients (reference layout, fp32) of sum(nll * dnll) [+ sum(logits * dlogits32)] w.r.t. every
         generator parameter.  With ``grad_targets`` ({state_dict name: fp32 tensor}, e.g. the parameters' ``.grad``)
-        the gradients are ACCUMULATED into those tensors by one kernel (no per-tensor allocation, no autograd
-        accumulate nodes); otherwise fresh tensors are returned.  With need_dinput the gradient w.r.t. the soft
+        the gradients are ACCUMULATED into (``accumulate=False``: written to) those tensors by one kernel (no per-tensor
+        allocation, no autograd accumulate nodes); otherwise fresh tensors are returned.  With need_dinput the gradient w.r.t. the soft
         one-hot input rows is returned under the key '__dinput__' (fp32 [Q*B, VP])."""
         d, lay, dt = self.d, self.layout, self.dtype
         DP, NH, DIP, VP, D = d.DP, d.NH, d.DIP, d.VP, d.d_model
@@ -653,7 +654,7 @@ class TxlEngine:
         # ---- unpack to reference-layout gradients
         if grad_targets is not None:
             desc = self._unpack_desc_for(grad_targets)
-            L.unpack_grads(gm, gv, desc, desc.shape[0], self._max_elems, accumulate=True)
+            L.unpack_grads(gm, gv, desc, desc.shape[0], self._max_elems, accumulate=accumulate)
             grads = {}
         else:
             grads = {}
