@@ -545,17 +545,16 @@ class TxlEngine:
         cur_off = ctx.cur_off
         impl = self.impl
         gm, gv = self.gmat, self.gvec
+        # every weight-gradient GEMM accumulates (TMA reduce-add / split-K partial sums) into buffers zeroed ONCE here:
+        # one 60 MB memset instead of a memset node in front of each of the ~37 split-K launches
         gv.zero_()
-        written = set()
+        gm.zero_()
 
         def wgrad(name, dY, X, rows, n_out, k_in, *, dy_off=0, x_off=0, ldy=None, ldx=None, row_off=0):
             """gmat[name][row_off : row_off+n_out, :k_in] (+)= dY^T X"""
             goff, _, gld = lay.gmat[name]
-            key = (name, row_off)
             L.gemm(dY, X, gm, transA=True, transB=False, M=n_out, N=k_in, K=rows, lda=ldy, ldb=ldx, ldc=gld,
-                   a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld,
-                   flags=L.EPI_ACCUM if key in written else 0, impl=impl)
-            written.add(key)
+                   a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld, flags=L.EPI_ACCUM, impl=impl)
 
         # ---- loss head
         dl = self._buf(RT, VP)
