@@ -164,13 +164,16 @@ class ParamLayout:
             vo += n
 
         add_mat("E", VP, DP)
+        # the r_net weights of all layers sit back to back: r = r_net(pos_emb) of every layer is ONE GEMM per forward
+        # ([K, n_layer * N*64]), and their gradients one GEMM per backward
+        for l in range(d.n_layer):
+            add_mat(f"l{l}.Wr", NH, DP, transposed=False)
         add_vec("u", NH)
         add_vec("vb", NH)
         add_vec("bias_out", VP)
         for l in range(d.n_layer):
             p = f"l{l}."
             add_mat(p + "Wqkv", 3 * NH, DP)
-            add_mat(p + "Wr", NH, DP, transposed=False)
             add_mat(p + "Wo", DP, NH)
             add_mat(p + "W1", DIP, DP)
             add_mat(p + "W2", DP, DIP)
@@ -420,6 +423,8 @@ class TxlEngine:
         ctx.pe = pe
         scale = 1.0 / math.sqrt(d.d_head)
         ctx.layers = []
+        r_all = self._buf(K, d.n_layer * NH)
+        L.gemm(pe, self.pmat, r_all, M=K, N=d.n_layer * NH, K=DP, ldb=DP, b_off=self._m("l0.Wr")[0], impl=self.impl)
         # Projected-K/V cache (the reference re-projects every memory row at each of the 123 sampling
         # steps / every generated token, mem_transformer.py:166-170).  For decode-sized calls the K/V rows live in a
         # buffer that mirrors the ring; rows projected by an earlier call with the same packed parameters are reused
@@ -438,7 +443,7 @@ class TxlEngine:
             sv = _Ctx()
             woff, wld = self._m(p + "Wqkv")
             q = self._buf(R, NH)
-            r = self._buf(K, NH)
+            r = r_all[:, l * NH:(l + 1) * NH]  # view: row pitch n_layer * NH
             x_base = l * slab_elems
             L.gemm(slabs, self.pmat, q, M=R, N=NH, K=DP, lda=DP, ldb=wld, a_off=cur_off[l], b_off=woff, impl=self.impl)
             if use_cache:
@@ -453,8 +458,6 @@ class TxlEngine:
                     L.gemm(slabs, self.pmat, kv, M=n * B, N=2 * NH, K=DP, lda=DP, ldb=wld, a_off=x_base + pos * B * DP,
                            b_off=woff + NH * wld, c_off=row * B * 2 * NH, impl=self.impl)
                     row += n
-            roff, rld = self._m(p + "Wr")
-            L.gemm(pe, self.pmat, r, M=K, N=NH, K=DP, ldb=rld, b_off=roff, impl=self.impl)
             att = self._buf(R, NH)
             lse = self._buf(B * d.n_head * Q, dtype=torch.float32)
             L.relattn_fwd(q, kv, kv, 2 * NH, r, self._v("u"), self._v("vb"), reset_u8, att, lse, B, d.n_head, Q, M, msl,
@@ -575,6 +578,7 @@ class TxlEngine:
         if p_drop > 0:
             L.dropout(dx, dx, RT, DP, DP, DP, p_drop, seed, self._site(cid, 2), src_off=dxo, dst_off=dxo)
         scale = 1.0 / math.sqrt(d.d_head)
+        dr_all32 = self._buf(K, d.n_layer * NH, dtype=torch.float32)
         for l in reversed(range(d.n_layer)):
             p = f"l{l}."
             sv = ctx.layers[l]
@@ -608,18 +612,12 @@ class TxlEngine:
             # attention core backward
             dq = self._buf(R, NH)
             dkv = self._buf(KR, 2 * NH)
-            dr32 = self._buf(K, NH, dtype=torch.float32)
+            dr32 = dr_all32[:, l * NH:(l + 1) * NH]  # view: this layer's column block
             delta = self._buf(B * d.n_head * Q, dtype=torch.float32)
             L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
                           sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
                           ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,
                           k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
-            if dt == torch.float32:
-                dr = dr32
-            else:
-                dr = self._buf(K, NH)
-                L.convert(dr32, NH, dr, NH, K, NH, NH)
-            wgrad(p + "Wr", dr, ctx.pe, K, NH, DP, ldy=NH, ldx=DP)
             wgrad(p + "Wqkv", dq, slabs, R, NH, DP, ldy=NH, ldx=DP, x_off=cur_off[l])
             row = 0
             for pos, n in ctx.x_segs:
@@ -634,6 +632,15 @@ class TxlEngine:
             dx = self._buf(R, DP)
             L.gemm(dkv, self.pmat, dx, M=R, N=DP, K=2 * NH, lda=2 * NH, ldb=wtld, a_off=M * B * 2 * NH,
                    b_off=wtoff + NH, aux=t, ldaux=DP, flags=L.EPI_ADD_AUX, impl=impl)
+        # ---- r_net weight gradients of all layers: dWr_all = dR_all^T pos_emb
+        NL = d.n_layer * NH
+        if dt == torch.float32:
+            dr_all = dr_all32
+        else:
+            dr_all = self._buf(K, NL)
+            L.convert(dr_all32, NL, dr_all, NL, K, NL, NL)
+        L.gemm(dr_all, ctx.pe, gm, transA=True, transB=False, M=NL, N=DP, K=K, lda=NL, ldb=DP, ldc=DP,
+               c_off=lay.gmat["l0.Wr"][0], flags=L.EPI_ACCUM, impl=impl)
         # ---- embedding
         out: Dict[str, torch.Tensor] = {}
         goff, _, gld = lay.gmat["E"]
