@@ -259,6 +259,9 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             // 3. add the shifted position scores, mask, tile maximum
             const int j0 = (t_lo + tt) * BJ;
             const int start = (BQ - 1 - ii + BJ * tt) % RING_COLS;  // ring column of jj = 0
+            const int wrap = RING_COLS - start;                      // first jj that wraps around the ring
+            const __half* g0 = ring + start * BQ + ii;               // element jj sits at g0[jj * BQ] before the wrap,
+            const __half* g1 = g0 - RING_COLS * BQ;                  // at g1[jj * BQ] after it: one select, no index math
             float x[32];
             float mx = -INFINITY;
             // CTA-uniform: a tile strictly inside every row's [lower, causal] window needs no per-element mask
@@ -267,9 +270,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             if (interior) {
 #pragma unroll
                 for (int jj = 0; jj < BJ; ++jj) {
-                    int col = start + jj;
-                    col -= (col >= RING_COLS) ? RING_COLS : 0;
-                    x[jj] = __uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii]);
+                    x[jj] = __uint_as_float(sr[jj]) + __half2float((jj < wrap ? g0 : g1)[jj * BQ]);
                     mx = fmaxf(mx, x[jj]);
                 }
             } else {
@@ -280,9 +281,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 lim_hi = min(lim_hi, p.K - 1 - j0);
 #pragma unroll
                 for (int jj = 0; jj < BJ; ++jj) {
-                    int col = start + jj;
-                    col -= (col >= RING_COLS) ? RING_COLS : 0;
-                    float v = __uint_as_float(sr[jj]) + __half2float(ring[col * BQ + ii]);
+                    float v = __uint_as_float(sr[jj]) + __half2float((jj < wrap ? g0 : g1)[jj * BQ]);
                     x[jj] = (jj >= lim_lo && jj <= lim_hi) ? v : -INFINITY;
                     mx = fmaxf(mx, x[jj]);
                 }
