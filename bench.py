@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the GAN-phase and generation side measurements")
+    ap.add_argument("--extras-only", type=float, default=None, metavar="MLE_MS",
+                    help="(internal) run only the side measurements in this process and print their JSON")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from the host instead of replaying "
                     "the captured forward / backward CUDA graphs of each ring phase")
     ap.add_argument("--cpu-batch", type=int, default=4)
@@ -287,10 +289,30 @@ def generate_extra(model, dev, B=128, mem_len=4146, steps=48):
             "note": "logits only (sampling / top-k is the caller's, generate.py:228-304); host-launched"}
 
 
+def run_extras_only(args):
+    """Side measurements in their own process: a failure there can never take the headline line with it."""
+    import mem_transformer as MT
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    model = MT.MemTransformerLM(make_cfg(), WORK["n_token"], 0)
+    init_like_train_py(model, 1111)
+    model = model.to(dev).train()
+    extras = {}
+    for name, fn in (("generate", lambda: generate_extra(model, dev)),
+                     ("gan_phase", lambda: gan_phase_extra(dev, args.global_batch, args.extras_only, not args.no_graphs))):
+        try:
+            extras[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            extras[name] = {"error": repr(e)[:200]}
+    print(json.dumps(extras))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.extras_only is not None:
+        return run_extras_only(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -429,15 +451,16 @@ def main():
         del A, W, C
     extras = None
     if rank == 0 and world == 1 and not args.no_extras and args.dtype == "bf16":
-        extras = {}
+        cmd = [sys.executable, os.path.abspath(__file__), "--extras-only", repr(ms_dev / args.steps), "--global-batch",
+               str(args.global_batch)] + (["--no-graphs"] if args.no_graphs else [])
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)))
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
         try:
-            extras["generate"] = generate_extra(model, dev)
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+            extras = json.loads(out.stdout.strip().splitlines()[-1])
         except Exception as e:  # noqa: BLE001  (side measurement: never lose the headline line)
-            extras["generate"] = {"error": repr(e)[:200]}
-        try:
-            extras["gan_phase"] = gan_phase_extra(dev, args.global_batch, ms_dev / args.steps, not args.no_graphs)
-        except Exception as e:  # noqa: BLE001
-            extras["gan_phase"] = {"error": repr(e)[:200]}
+            extras = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.cpu_batch)
