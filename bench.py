@@ -257,7 +257,7 @@ def gan_phase_extra(dev, B, mle_ms, graphs):
     return res
 
 
-def generate_extra(model, dev, B=128, mem_len=4146, steps=48):
+def generate_extra(model, dev, B=128, mem_len=4146, steps=32):
     """inference_unconditional.yml decode step (generate.py:132-226 -> forward_generate, mem_transformer.py:578-600):
     one new token per sequence against a full memory of 4146 positions, K/V projections served from the cache."""
     V = WORK["n_token"]
@@ -278,9 +278,9 @@ def generate_extra(model, dev, B=128, mem_len=4146, steps=48):
             def step():
                 logits, state["mems"] = model.forward_generate(tok, state["mems"])
                 return logits
-            for _ in range(3):
+            for _ in range(8):
                 step()
-            ms = time_calls(lambda: [step() for _ in range(steps)], 2) / steps
+            ms = time_calls(lambda: [step() for _ in range(steps)], 3) / steps
     finally:
         model.reset_length(*cached)
         model.train(was_training)

@@ -344,10 +344,34 @@ class TxlEngine:
         if ring.length > mem_len:  # reset_length shrank the memory: keep the most recent rows
             ring.start = (ring.start + ring.length - mem_len) % ring.capacity
             ring.length = mem_len
-        if ring.capacity < min(ring.length, mem_len) + Q or w + Q > ring.capacity or ring.capacity < mem_len + Q:
-            # re-layout (rare: tgt_len / mem_len changed between calls): compact into a fresh ring
-            return self.import_mems(ring.materialize(), Q, mem_len)
+        # decode-sized calls keep [memory; new rows] physically contiguous (the projected-K/V cache and the attention
+        # kernels' single K / V base pointer need it): compact just before the window would wrap
+        wraps = Q <= self.kv_cache_max_q and ring.start + ring.length + Q > ring.capacity
+        if (ring.capacity < min(ring.length, mem_len) + Q or w + Q > ring.capacity or ring.capacity < mem_len + Q
+                or wraps):
+            # re-layout: the write position reached the end of the buffer (every capacity - mem_len decode steps) or
+            # tgt_len / mem_len changed between calls
+            return self._relayout(ring, Q, mem_len)
         return ring
+
+    def _relayout(self, ring: RingMems, Q: int, mem_len: int) -> RingMems:
+        """Compact the live window to position 0 of a fresh ring in the compute dtype (plain row copies), carrying the
+        projected-K/V cache rows along so that a long decode never re-projects its memory."""
+        new = self.new_ring(ring.bsz, Q, max(mem_len, ring.length))
+        n = ring.length
+        keep_kv = (ring.kv["buf"] is not None and ring.kv["tag"] == self.pack_epoch and n > 0 and
+                   len(ring.segments(0, n)) == 1 and ring.kv["lo"] <= ring.start and ring.kv["hi"] == ring.start + n)
+        row = 0
+        for pos, cnt in ring.segments(0, n):
+            new.slabs[:, row:row + cnt].copy_(ring.slabs[:, pos:pos + cnt])
+            row += cnt
+        if keep_kv:
+            buf = ring.kv["buf"]
+            nb = torch.empty(buf.shape[0], new.capacity, buf.shape[2], buf.shape[3], dtype=buf.dtype, device=buf.device)
+            nb[:, :n].copy_(buf[:, ring.start:ring.start + n])
+            new.kv.update(buf=nb, lo=0, hi=n, tag=self.pack_epoch)
+        new.length = n
+        return new
 
     # -- forward ------------------------------------------------------------------------------------------
     def forward(self, inp: torch.Tensor, reset: Optional[torch.Tensor], mems, *, mem_len: int, same_length: bool,

@@ -112,7 +112,14 @@ def _ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """raw handle of torch's current CUDA stream (the C accessor is ~20x cheaper than the Stream object; a decode
+    step makes ~55 calls)"""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
