@@ -90,9 +90,12 @@ int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t ld, int kle
 
 /* ---- LayerNorm (eps 1e-5) over the first D of DP lanes: mem_transformer.py:58, 255 ---------------------
  * y = LN(z) * gamma + beta; z is fp32 (the GEMM epilogue wrote x + residual in fp32), y has `dtype`;
- * mean / rstd (fp32 [rows]) are saved for the backward.                                                     */
+ * mean / rstd (fp32 [rows]) are saved for the backward.  pad_one (needs D < DP): lane D of every output row is set to
+ * 1.0 instead of 0 -- a ones column in the pad lanes: the weight-gradient GEMM dW = dY^T y of the Linear that consumes y
+ * then delivers that Linear's BIAS gradient (column sums of dY) in column D for free; the weights' pad columns are zero,
+ * so the forward value is unchanged.                                                                          */
 int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
-                const float* beta, float* mean, float* rstd, int rows, int D, int DP, void* stream);
+                const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one, void* stream);
 /* dz = LN'(dy) ; dz_drop (optional) = dropmask(seed, site)(dz) / (1-p) -- the gradient entering the dropout
  * that precedes the residual add; dgamma / dbeta (fp32 [D]) are accumulated (+=).  dsum (optional, fp32 [D],
  * accumulated): column sums of dz_drop (of dz when dz_drop is NULL) = the bias gradient of the Linear whose output

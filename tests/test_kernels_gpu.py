@@ -156,6 +156,9 @@ def test_layernorm_fwd_bwd(dtype):
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     assert (y[:, :D].double() - ref).abs().max() < tol
     assert torch.all(y[:, D:] == 0)
+    y1 = torch.empty_like(y)
+    L.ln_fwd(z, y1, gamma, beta, mean, rstd, rows, D, DP, pad_one=True)  # ones column in the first pad lane
+    assert torch.equal(y1[:, :D], y[:, :D]) and torch.all(y1[:, D] == 1) and torch.all(y1[:, D + 1:] == 0)
     dy = _rand(rows, DP, dtype=dtype, seed=4)
     dz, dzd = torch.empty_like(dy), torch.empty_like(dy)
     dg, db = torch.zeros(DP, device="cuda"), torch.zeros(DP, device="cuda")

@@ -147,7 +147,7 @@ __device__ __forceinline__ void store4(bf16* p, const float* v) {
 template <typename T, int MAXU>
 __global__ void ln_fwd_kernel(const float* __restrict__ z, int64_t ldz, T* __restrict__ y, int64_t ldy,
                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, int DP) {
+                              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, int DP, int pad_one) {
     int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* zr = z + (int64_t)row * ldz;
@@ -183,7 +183,8 @@ __global__ void ln_fwd_kernel(const float* __restrict__ z, int64_t ldz, T* __res
             float g[4], bt[4], o[4];
             load4(gamma + c, g); load4(beta + c, bt);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) o[t] = c + t < D ? (v[u][t] - mu) * rs * g[t] + bt[t] : 0.f;
+            for (int t = 0; t < 4; ++t)
+                o[t] = c + t < D ? (v[u][t] - mu) * rs * g[t] + bt[t] : ((pad_one && c + t == D) ? 1.f : 0.f);
             store4(yr + c, o);
         }
     }
@@ -636,17 +637,19 @@ extern "C" int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t 
 }
 
 extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
-                           const float* beta, float* mean, float* rstd, int rows, int D, int DP, void* stream) {
+                           const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one,
+                           void* stream) {
     if (rows <= 0) return 0;
     TGAN_CHECK_ARG(DP % 8 == 0 && ldz % 4 == 0 && ldy % 8 == 0 && D <= DP, "tgan_ln_fwd: alignment");
+    TGAN_CHECK_ARG(!pad_one || D < DP, "tgan_ln_fwd: pad_one needs a pad lane (D < DP)");
     TGAN_CHECK_ARG(DP <= 1024 && (((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)z) & 15) == 0 && ((uintptr_t)y & 7) == 0,
                    "tgan_ln_fwd: DP <= 1024, 16-byte aligned z / gamma / beta");
     if (DP <= 512) {
         DISPATCH_T(dtype, (ln_fwd_kernel<T, 4><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
-                                                                                          mean, rstd, rows, D, DP)));
+                                                                                          mean, rstd, rows, D, DP, pad_one)));
     } else {
         DISPATCH_T(dtype, (ln_fwd_kernel<T, 8><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
-                                                                                          mean, rstd, rows, D, DP)));
+                                                                                          mean, rstd, rows, D, DP, pad_one)));
     }
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();

@@ -274,7 +274,13 @@ class TxlEngine:
             else:
                 off, _ = lay.vec[name]
                 rows_pack.append([t.data_ptr(), off, r, c, c, rg, rgp, cg, cgp, 0, 1, 0])
-                rows_unpack.append([0, off, r, c, c, rg, rgp, cg, cgp, 0, 1, 0])
+                if name.endswith(".b1") and d.DP > d.d_model:
+                    # db1 is column d_model of the padded dW1 (ones column in LayerNorm-1's pad lane, see forward):
+                    # read it as a [d_inner, 1] matrix with row pitch DP out of the matrix-gradient buffer
+                    goff, _, gld = lay.gmat[name[:-2] + "W1"]
+                    rows_unpack.append([0, goff + d.d_model, c, 1, gld, 1, 1, 1, 1, 0, 0, 0])
+                else:
+                    rows_unpack.append([0, off, r, c, c, rg, rgp, cg, cgp, 0, 1, 0])
         self._pack_desc = torch.tensor(rows_pack, dtype=torch.int64, device=self.device)
         self._unpack_rows = rows_unpack
         self._max_elems = max_elems
@@ -495,7 +501,8 @@ class TxlEngine:
                    site=self._site(cid, 9 + 4 * l), impl=self.impl)
             a = self._buf(R, DP)
             mean1, rstd1 = self._buf(R, dtype=torch.float32), self._buf(R, dtype=torch.float32)
-            L.ln_fwd(z1, a, self._v(p + "ln1_g"), self._v(p + "ln1_b"), mean1, rstd1, R, D, DP)
+            # lane D of `a` is a ones column when the padding leaves room: dW1 = dh^T a then carries db1 in column D
+            L.ln_fwd(z1, a, self._v(p + "ln1_g"), self._v(p + "ln1_b"), mean1, rstd1, R, D, DP, pad_one=DP > D)
             # FFN
             w1off, w1ld = self._m(p + "W1")
             h = self._buf(R, DIP)
@@ -618,7 +625,8 @@ class TxlEngine:
             dh = self._buf(R, DIP)
             L.gemm(g2, self.pmat, dh, M=R, N=DIP, K=DP, ldb=w2tld, b_off=w2toff, aux=sv.h, ldaux=DIP,
                    flags=L.EPI_MASK_POS, alpha=1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0, impl=impl)
-            L.colsum(dh, gv, R, d.d_inner, ld=DIP, out_off=lay.vec[p + "b1"][0])
+            if DP == D:  # no pad lane for the ones column: separate pass for db1
+                L.colsum(dh, gv, R, d.d_inner, ld=DIP, out_off=lay.vec[p + "b1"][0])
             wgrad(p + "W1", dh, sv.a, R, DIP, DP, ldy=DIP, ldx=DP)
             w1toff, w1tld = self._m(p + "W1.T")
             da = self._buf(R, DP)

@@ -42,7 +42,7 @@ _SIGS = {
     "tgan_embed_fwd": [I, P, P, L, P, L, I, I, I, F, F, U, U, P],
     "tgan_embed_bwd": [I, P, P, L, P, L, I, I, I, F, F, U, U, P],
     "tgan_pos_emb": [I, P, P, L, I, I, I, I, F, U, U, P],
-    "tgan_ln_fwd": [I, P, L, P, L, P, P, P, P, I, I, I, P],
+    "tgan_ln_fwd": [I, P, L, P, L, P, P, P, P, I, I, I, I, P],
     "tgan_ln_bwd": [I, P, L, P, L, P, P, P, P, L, P, L, P, P, P, I, I, I, F, U, U, P],
     "tgan_dropout": [I, P, L, P, L, I, I, F, U, U, P],
     "tgan_relattn_fwd": [I, P, L, P, P, L, P, L, P, P, P, P, L, P, I, I, I, I, I, I, F, F, U, U, I, P],
@@ -171,9 +171,9 @@ def pos_emb(inv_freq, pe, klen, D, DP, clamp_len, drop_p, seed, site):
           clamp_len, drop_p, seed, site, _stream())
 
 
-def ln_fwd(z, y, gamma, beta, mean, rstd, rows, D, DP, y_off=0):
+def ln_fwd(z, y, gamma, beta, mean, rstd, rows, D, DP, y_off=0, pad_one=False):
     _call("tgan_ln_fwd", dtype_code(y.dtype), z.data_ptr(), z.stride(0), y.data_ptr() + y_off * y.element_size(),
-          DP, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), rows, D, DP, _stream())
+          DP, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), rows, D, DP, int(pad_one), _stream())
 
 
 def ln_bwd(dy, z, gamma, mean, rstd, dz, dz_drop, dgamma, dbeta, rows, D, DP, drop_p, seed, site, dy_off=0, dsum=None):
