@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- train tokens/sec of the Transformer-XL MLE training step (experiment_baseline.yml shapes) on N B200s.
+"""bench.py -- train tokens/sec of the Transformer-XL + GAN training cycle (experiment_spanbert.yml shapes) on N B200s.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C-ABI)
-    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU implementation of the same path
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU implementation of the same cycle
 
-A "step" is one optimizer step of the reference's train loop (train.py:859-921) on synthetic MAESTRO-vocab tokens:
-forward + backward of MemTransformerLM over the global batch (512 sequences x 128 tokens, memory 1024), gradient
-clip + Adam.  One process per GPU; N > 1 shards the batch columns (data parallel, global batch fixed = strong
-scaling as in train.py:226-227) and all-reduces the flat gradient buffer once per step over NCCL.
-Prints ONE JSON line on rank 0.
+BASELINE.json's metric is "train tokens/sec (GAN step)".  A "step" is one iteration of the reference's train loop
+(train.py:859-1090) on synthetic MAESTRO-vocab tokens: an MLE optimizer step of MemTransformerLM over the global batch
+(512 sequences x 128 tokens, memory 1024; forward + backward + gradient clip + Adam) and, on every 5th iteration
+(DISCRIMINATOR.dis_loss_freq = gen_loss_freq = 5), one discriminator update (TransformerGAN.forward(..., "dis_loss"):
+123 Gumbel-softmax sampling steps, BERT 5x768 discriminator on real / fake, WGAN-GP) and one generator update
+("gen_loss": the same sampling chain with gradient, discriminator forward / backward to the samples).  Tokens counted
+= the MLE target tokens, exactly what train.py logs (train.py:906, 1158-1163).  K should be a multiple of 5 (whole
+cycles); the timed region starts on a cycle boundary.  `extras.mle_only` keeps round 1's headline (the MLE step of
+experiment_baseline.yml alone).
+
+One process per GPU; N > 1 shards the batch columns (data parallel, global batch fixed = strong scaling as in
+train.py:226-227) and all-reduces the flat gradient buffers over NCCL.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -27,40 +34,74 @@ sys.path.insert(0, os.path.join(ROOT, "transformer-gan_b200"))
 
 import torch  # noqa: E402
 
-# experiment_baseline.yml (model/training_config/experiment_baseline.yml:8-38)
+# experiment_spanbert.yml / experiment_baseline.yml (model/training_config/*.yml): same generator and MLE shapes
 WORK = dict(n_layer=6, n_head=10, d_model=500, d_inner=1000, n_token=310, tgt_len=128, mem_len=1024,
-            global_batch=512, dropout=0.1, dropatt=0.1, clip=1.0, lr=0.004)
+            global_batch=512, dropout=0.1, dropatt=0.1, clip=1.0, lr=0.002,
+            dis_tgt_len=128, dis_mem_len=128, context_len=5, sample_chunks_mem=2, gan_freq=5)
+BERT_CFG = dict(vocab_size=311, hidden_size=768, num_hidden_layers=5, num_attention_heads=12, intermediate_size=3072,
+                max_position_embeddings=512, type_vocab_size=2, hidden_act="gelu", hidden_dropout_prob=0.1,
+                attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12, model_type="bert")
+# where the "largest share of the timed cycle" claim of `roofline` comes from
+ROOFLINE_NOTE = "profiles/r2_launch_summary_cycle.txt"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-chunk", type=int, default=1, help="micro-batches per step (reference yml: 4; native: 1)")
+    ap.add_argument("--workload", default="gan", choices=["gan", "mle"],
+                    help="gan: experiment_spanbert.yml cycle (the BASELINE metric); mle: experiment_baseline.yml MLE step only")
+    ap.add_argument("--batch-chunk", type=int, default=1, help="micro-batches per step (reference yml: 16; native: 1)")
     ap.add_argument("--global-batch", type=int, default=WORK["global_batch"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the GAN-phase and generation side measurements")
-    ap.add_argument("--extras-only", type=float, default=None, metavar="MLE_MS",
-                    help="(internal) run only the side measurements in this process and print their JSON")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (phases, eager GPU bar)")
+    ap.add_argument("--extras-only", action="store_true", help="(internal) run only the side measurements and print their JSON")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from the host instead of replaying "
-                    "the captured forward / backward CUDA graphs of each ring phase")
+                    "the captured CUDA graphs (MLE forward / backward per ring phase, one graph per adversarial phase)")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--warm-segments", type=int, default=None,
-                    help="untimed steps before timing (default: enough to fill the recurrence memory, >= --warmup)")
+                    help="untimed MLE steps before timing (default: enough to fill the recurrence memory + capture graphs)")
     return ap.parse_args()
 
 
-def make_cfg():
+class Vocab:
+    vec_len = 0
+
+    def __len__(self):
+        return WORK["n_token"]
+
+
+def make_cfg(bert_dir, dis_batch_chunk=1):
     ns = types.SimpleNamespace
     return ns(MODEL=ns(num_layers=WORK["n_layer"], num_heads=WORK["n_head"], units=WORK["d_model"],
                        inner_size=WORK["d_inner"], dropout=WORK["dropout"], attention_dropout=WORK["dropatt"],
                        tie_embedding=True, tie_proj=False, pre_lnorm=False, same_length=False, clamp_len=-1),
               TRAIN=ns(tgt_length=WORK["tgt_len"], mem_length=WORK["mem_len"], pad_type="model",
-                       replace_start_with_pad=False, append_note_status=False))
+                       replace_start_with_pad=False, append_note_status=False),
+              DISCRIMINATOR=ns(type="bert" if bert_dir else "Null", tgt_len=WORK["dis_tgt_len"], mem_len=WORK["dis_mem_len"],
+                               context_len=WORK["context_len"], sample_chunks_mem=WORK["sample_chunks_mem"],
+                               truncate_backprop=False, backprop_outside=True, gen_loss_factor=1.0, dis_loss_factor=1.0,
+                               batch_chunk=dis_batch_chunk,
+                               BERT=ns(model_path=bert_dir, loss_type="wgan-gp", model_type="bert_lm", random_weights=False,
+                                       freeze_layers=["0", "1", "2", "3", "4"]),
+                               CNN=ns(embed_dim=64, hidden_dim=64, num_rep=64, init="uniform", loss_type="rsgan")),
+              PPO=ns(dis_D_type="bert", dis_D_num_rep=1, clip_param=0.4))
+
+
+def synth_bert_checkpoint(seed=0):
+    """experiment_spanbert.yml points at ../BERT/checkpoint-1969000, which the reference does not ship: synthesize a
+    seed-initialised BertForMaskedLM checkpoint of the same architecture so that the SHIPPED code path runs
+    (random_weights False -> embeddings + all 5 layers frozen, pooler + classifier train)."""
+    from transformers import BertConfig, BertForMaskedLM
+    d = tempfile.mkdtemp(prefix="tgan_bert_")
+    torch.manual_seed(seed)
+    cfg = BertConfig(**{k: v for k, v in BERT_CFG.items() if k != "model_type"})
+    BertForMaskedLM(cfg).save_pretrained(d)
+    return d
 
 
 def init_like_train_py(model, seed):
@@ -96,8 +137,7 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         while not self._stop.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
@@ -134,67 +174,117 @@ def peaks():
         return None
 
 
+def workload_config(args, world):
+    gan = args.workload == "gan"
+    name = ("experiment_spanbert.yml Transformer-XL + GAN training cycle: every iteration an MLE optimizer step, every 5th "
+            "iteration one discriminator update + one generator update (123 Gumbel-softmax sampling steps, BERT 5x768 "
+            "discriminator, WGAN-GP)") if gan else "experiment_baseline.yml Transformer-XL MLE training step"
+    return {"workload": name + " (6 layers, 10 heads, d_model 500, d_inner 1000, vocab 310, tgt_len 128, mem_len 1024, "
+                        "dropout 0.1), synthetic MAESTRO-vocab tokens",
+            "global_batch": args.global_batch, "seq_len": WORK["tgt_len"], "mem_len": WORK["mem_len"],
+            "batch_chunk": args.batch_chunk, "parallelism": f"dp{world}",
+            "gan": {"dis_tgt_len": 128, "dis_mem_len": 128, "context_len": 5, "sample_chunks_mem": 2, "freq": 5,
+                    "discriminator": "BERT 5x768, shipped trainable set (pooler + classifier), wgan-gp",
+                    "dis_batch": args.global_batch} if gan else None,
+            "launch": "host launches" if args.no_graphs else
+                      "CUDA graphs (MLE: one forward + one backward graph per ring phase; one graph per adversarial phase)",
+            "l2": "per-step working set (activations + recurrence memory, several GB) is far larger than the 126 MB L2"}
+
+
 # ---------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference path (oracle/txl_oracle.py), all host threads
+# CPU implementation of the same cycle: the oracle port of the reference path, all host threads
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_setup(batch):
+def cpu_cycle_setup(batch, gan=True):
+    """-> step(i): runs iteration i of the cycle on the CPU (fp32) at `batch` sequences, returns tokens consumed."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import txl_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     shape = O.TxlShape(n_layer=WORK["n_layer"], n_head=WORK["n_head"], d_model=WORK["d_model"],
                        d_inner=WORK["d_inner"], n_token=WORK["n_token"], mem_len=WORK["mem_len"])
+    shape_gan = O.TxlShape(n_layer=WORK["n_layer"], n_head=WORK["n_head"], d_model=WORK["d_model"],
+                           d_inner=WORK["d_inner"], n_token=WORK["n_token"], mem_len=WORK["dis_mem_len"])
     p = O.init_params(shape, 1111)
     for t in p.values():
         t.requires_grad_(True)
     g = torch.Generator().manual_seed(1111)
-    Q = WORK["tgt_len"]
-    # warm the memory to M = mem_len without running 8 segments: steady-state shapes only need a full-size memory
-    mems = 0.1 * torch.randn(shape.n_layer + 1, WORK["mem_len"], batch, shape.d_model, generator=g)
+    Q, V = WORK["tgt_len"], WORK["n_token"]
+    # steady-state shapes only need a full-size memory: start from a random one instead of running 8 segments
+    state = {"mems": 0.1 * torch.randn(shape.n_layer + 1, WORK["mem_len"], batch, shape.d_model, generator=g)}
+    disc = None
+    if gan:
+        from transformers import BertConfig, BertForSequenceClassification
+        torch.manual_seed(0)
+        cfg = BertConfig(**{k: v for k, v in BERT_CFG.items() if k != "model_type"})
+        cfg._attn_implementation = "eager"
+        bert = BertForSequenceClassification(cfg).train()
+        for name, prm in bert.named_parameters():  # shipped trainable set (transformer_gan.py:568-585)
+            prm.requires_grad_(not (name.startswith("bert.embeddings") or name.startswith("bert.encoder.layer")))
+        E = bert.bert.embeddings.word_embeddings.weight
+        on_emb = lambda e: bert(inputs_embeds=e)[0][:, 0]
+        disc = (lambda x: on_emb(x @ E)), (lambda x: x @ E), on_emb
 
-    def step():
-        data = torch.randint(2, WORK["n_token"], (Q, batch), generator=g)
-        target = torch.randint(2, WORK["n_token"], (Q, batch), generator=g)
-        loss, new_mems = O.mle_forward(data, target, torch.zeros(batch, dtype=torch.bool), mems, p, shape)
-        loss.mean().backward()
+    def clear():
         for t in p.values():
             t.grad = None
+
+    def step(i):
+        data = torch.randint(2, V, (Q, batch), generator=g)
+        target = torch.randint(2, V, (Q, batch), generator=g)
+        loss, state["mems"] = O.mle_forward(data, target, torch.zeros(batch, dtype=torch.bool), state["mems"], p, shape)
+        loss.mean().backward()
+        clear()
+        if gan and i % WORK["gan_freq"] == 0:
+            T, ctx, ch = WORK["dis_tgt_len"], WORK["context_len"], WORK["sample_chunks_mem"]
+            for mode in ("dis_loss", "gen_loss"):
+                dis_data = torch.randint(2, V, (T, batch), generator=g)
+                U = [torch.rand(1, batch, V, generator=g) for _ in range(T - ctx)]
+                al = [torch.rand(batch, generator=g) for _ in range(ch)]
+                O.gan_step(mode, dis_data, p, shape_gan, disc[0], 1, "wgan-gp", 1.0, U, al, T, ctx, ch,
+                           embed=disc[1], disc_on_embeds=disc[2])
+                clear()
         return Q * batch
 
     return step
 
 
-def cpu_baseline(batch, budget_s=20.0):
-    step = cpu_reference_setup(batch)
-    step()  # warm-up (thread pools, allocator)
+def cpu_baseline(batch, gan, budget_s=25.0):
+    step = cpu_cycle_setup(batch, gan)
     t0 = time.perf_counter()
     toks, n = 0, 0
-    while n < 1 or (time.perf_counter() - t0 < budget_s and n < 8):
-        toks += step()
+    # whole cycles only (iteration 0 of each carries the GAN updates); stop after the first cycle past the budget
+    while True:
+        toks += step(n)
         n += 1
+        if n % WORK["gan_freq"] == 0 and (time.perf_counter() - t0 >= budget_s or n >= 4 * WORK["gan_freq"]):
+            break
     dt = time.perf_counter() - t0
     return {"value": toks / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle/txl_oracle.py fp32 fwd+bwd, {n} micro-batches of B={batch} x Q=128 tokens at M=1024 "
-                      f"(same model / shapes as the GPU workload, reduced batch)"}
+            "sample": f"oracle/txl_oracle.py fp32 on the host: {n} iterations ({n // WORK['gan_freq']} whole cycle(s): "
+                      f"MLE fwd+bwd each iteration, dis + gen update every 5th) at B={batch} sequences x Q=128 tokens, "
+                      f"M=1024 (same model / shapes as the GPU workload, reduced batch)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step = cpu_reference_setup(args.cpu_batch)
-    for _ in range(args.warmup):
-        step()
+    gan = args.workload == "gan"
+    step = cpu_cycle_setup(args.cpu_batch, gan)
+    for w in range(args.warmup):  # warm-up: MLE iterations (the GAN updates run inside the timed region from iteration 0)
+        step(1)
     t0 = time.perf_counter()
     toks = 0
-    for _ in range(args.steps):
-        toks += step()
+    for i in range(args.steps):
+        toks += step(i)
     dt = time.perf_counter() - t0
     v = toks / dt
     cores = torch.get_num_threads()
-    sample = (f"each step = oracle port of MemTransformerLM fwd+bwd (fp32) on B={args.cpu_batch} x Q=128 tokens at "
-              f"M=1024: a bounded sample of the 512 x 128-token step")
+    sample = (f"each step = one iteration of the cycle on the oracle port (fp32, {cores} threads) at B={args.cpu_batch} x "
+              f"Q=128 tokens, M=1024; iterations 0, 5, ... carry the dis + gen updates (123 sampling steps, HF BERT 5x768, "
+              f"WGAN-GP): a bounded sample of the 512-sequence step")
     print(json.dumps({
-        "impl": "reference", "metric": "train tokens/sec", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "train tokens/sec (GAN step)" if gan else "train tokens/sec", "value": v,
+        "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
@@ -202,18 +292,176 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, world):
-    return {"workload": "experiment_baseline.yml Transformer-XL MLE training step (6 layers, 10 heads, d_model 500, "
-                        "d_inner 1000, vocab 310, tgt_len 128, mem_len 1024, dropout 0.1), synthetic MAESTRO-vocab tokens",
-            "global_batch": args.global_batch, "seq_len": WORK["tgt_len"], "mem_len": WORK["mem_len"],
-            "batch_chunk": args.batch_chunk, "parallelism": f"dp{world}",
-            "launch": "host launches" if args.no_graphs else "CUDA graphs (one forward + one backward graph per ring phase)",
-            "l2": "per-step working set (activations + recurrence memory, several GB) is far larger than the 126 MB L2"}
+# ---------------------------------------------------------------------------------------------------------
+# the GPU workload
+# ---------------------------------------------------------------------------------------------------------
+class Cycle:
+    """The train.py iteration on this rank's shard: MLE step every call, dis + gen update every 5th."""
+
+    def __init__(self, args, dev, world, rank):
+        import transformer_gan as TG
+        from tgan_b200 import dp
+        from tgan_b200 import lib as L
+        self.L, self.dp, self.args, self.dev, self.world = L, dp, args, dev, world
+        self.gan = args.workload == "gan"
+        Q, V = WORK["tgt_len"], WORK["n_token"]
+        self.B = args.global_batch // world            # sequences on this rank
+        self.n_chunks = args.batch_chunk
+        self.Bc = self.B // self.n_chunks
+        bert_dir = synth_bert_checkpoint() if self.gan else None
+        torch.manual_seed(0)
+        model = TG.TransformerGAN(make_cfg(bert_dir), Vocab())
+        init_like_train_py(model.generator, 1111)
+        model = model.to(dev).train()
+        gen = model.generator
+        gen.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+        gen.kernel_impl = args.kernel_impl
+        gen.use_cuda_graphs = not args.no_graphs
+        model.use_cuda_graphs = not args.no_graphs
+        model.temperature = 1.0
+        self.model, self.generator = model, gen
+        # one flat parameter / gradient buffer per optimizer group: all-reduce, clip and Adam are one call each
+        self.fp = dp.FlatParams(gen.parameters())
+        lr = WORK["lr"] / world  # train.py:392 divides lr by the GPU count
+        self.opt = dp.FusedClipAdam(self.fp, lr, clip=WORK["clip"], world=world)       # `optimizer` (MLE)
+        self.gen_opt = dp.FusedClipAdam(self.fp, lr, clip=WORK["clip"], world=world)   # `gen_optimizer` (train.py:1085-1090)
+        self.dis_opt = self.dfp = None
+        if self.gan:
+            d = model.discriminator
+            trainable = []
+            for i, prm in enumerate(d.parameters()):  # train.py:944-947 toggles exactly these
+                prm.requires_grad_(i in d.unfreeze_idx)
+                if i in d.unfreeze_idx:
+                    trainable.append(prm)
+            self.dfp = dp.FlatParams(trainable)
+            self.dis_opt = dp.FusedClipAdam(self.dfp, lr, clip=WORK["clip"], world=world)
+        g = torch.Generator().manual_seed(dp.rank_seed(1111, rank))  # train.py:224
+        pin = lambda t: t.pin_memory()
+        nbuf = 4 * self.n_chunks
+        self.host_data = [pin(torch.randint(2, V, (Q, self.Bc), generator=g)) for _ in range(nbuf)]
+        self.host_tgt = [pin(torch.randint(2, V, (Q, self.Bc), generator=g)) for _ in range(nbuf)]
+        self.host_dis = [pin(torch.randint(2, V, (WORK["dis_tgt_len"], self.B), generator=g)) for _ in range(4)]
+        self.dev_data = [t.to(dev) for t in self.host_data]
+        self.dev_tgt = [t.to(dev) for t in self.host_tgt]
+        self.dev_dis = [t.to(dev) for t in self.host_dis]
+        self.reset = torch.zeros(self.Bc, dtype=torch.bool, device=dev)
+        self.mems = [None] * self.n_chunks
+        self.loss_host = torch.zeros(3).pin_memory()
+        self.it = 0
+        self.h2d = self.d2h = 0
+
+    def mle_step(self, e2e):
+        model, nck = self.model, self.n_chunks
+        total = None
+        for c in range(nck):
+            i = (self.it * nck + c) % len(self.host_data)
+            if e2e:
+                data = self.host_data[i].to(self.dev, non_blocking=True)
+                tgt = self.host_tgt[i].to(self.dev, non_blocking=True)
+                self.h2d += 2 * data.numel() * 8
+            else:
+                data, tgt = self.dev_data[i], self.dev_tgt[i]
+            ret = model(data, tgt, self.reset, "mle", self.mems[c])
+            loss, self.mems[c] = ret["mle"], ret["mems"]
+            l = loss.mean() / nck  # train.py:891-892 (no pad tokens in the synthetic stream)
+            l.backward()
+            total = l.detach() if total is None else total + l.detach()
+        self.opt.step()  # one NCCL all-reduce of the flat gradient per optimizer step, then fused clip + Adam
+        if e2e:
+            self.loss_host[0:1].copy_(total.view(1), non_blocking=True)
+            self.d2h += 4
+        return total
+
+    def gan_updates(self, e2e):
+        model = self.model
+        k = (self.it // WORK["gan_freq"]) % 2
+        for j, (phase, opt) in enumerate((("dis_loss", self.dis_opt), ("gen_loss", self.gen_opt))):
+            if e2e:
+                dis_data = self.host_dis[2 * k + j].to(self.dev, non_blocking=True)
+                self.h2d += dis_data.numel() * 8
+            else:
+                dis_data = self.dev_dis[2 * k + j]
+            ret = model(dis_data, None, None, phase)  # backward runs inside (backprop_outside, transformer_gan.py:487-502)
+            opt.step()
+            # neither phase may leave gradients in the other model's buffers (train.py zero_grads both optimizers)
+            self.fp.zero_grad()
+            self.dfp.zero_grad()
+            if e2e:
+                self.loss_host[1 + j:2 + j].copy_(ret[phase].detach().float().view(1), non_blocking=True)
+                self.d2h += 4
+
+    def iteration(self, e2e=False):
+        self.mle_step(e2e)
+        if self.gan and self.it % WORK["gan_freq"] == 0:
+            self.gan_updates(e2e)
+        self.it += 1
 
 
-# ---------------------------------------------------------------------------------------------------------
-# Side measurements of the other hot-path configurations: reported next to the headline, not part of it
-# ---------------------------------------------------------------------------------------------------------
+def attention_roofline(dev, B, pk):
+    """Live CUDA-event timing of the kernel with the largest share of the timed cycle -- the fused relative-position
+    attention BACKWARD at the MLE step's shape (B sequences x 10 heads, Q = 128, K = 1152, dropout 0.1) -- and of the
+    forward; algorithmic FLOPs = SURVEY 8d's 3 * 2 * B * N * Q * K * d_head per pass, backward = 2x forward."""
+    from tgan_b200 import lib as L
+    N, Q, M, dh, HS = WORK["n_head"], WORK["tgt_len"], WORK["mem_len"], WORK["d_model"] // WORK["n_head"], 64
+    K, NH = Q + M, N * HS
+    g = torch.Generator().manual_seed(0)
+
+    def mk(rows):
+        x = torch.zeros(rows, N, HS)
+        x[..., :dh] = torch.randn(rows, N, dh, generator=g)
+        return x.reshape(rows, NH).to(dev).bfloat16()
+    q, do, r = mk(Q * B), mk(Q * B), mk(K)
+    kv = torch.cat([mk(K * B), mk(K * B)], 1).contiguous()
+    u, vb = torch.zeros(NH, device=dev), torch.zeros(NH, device=dev)
+    out = torch.empty(Q * B, NH, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B * N * Q, device=dev)
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    dr = torch.empty(K, NH, device=dev)
+    du, dvb = torch.zeros(NH, device=dev), torch.zeros(NH, device=dev)
+    delta = torch.empty(B * N * Q, device=dev)
+    scale = 1 / math.sqrt(dh)
+
+    def fwd():
+        L.relattn_fwd(q, kv, kv, 2 * NH, r, u, vb, None, out, lse, B, N, Q, M, Q, False, scale, 0.1, 1, 2, impl=2, v_off=NH)
+
+    def bwd():
+        L.relattn_bwd(q, kv, kv, 2 * NH, r, u, vb, None, out, do, lse, delta, dq, dkv, dkv, 2 * NH, dr, du, dvb, B, N, Q,
+                      M, Q, False, scale, 0.1, 1, 2, impl=2, v_off=NH, dv_off=NH)
+    res = {}
+    for name, fn, mult in (("fwd", fwd, 1.0), ("bwd", bwd, 2.0)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps / 1e3
+        flops = mult * 3 * 2.0 * B * N * Q * K * dh
+        res[name] = (t, flops)
+    peak = (pk or {}).get("bf16_tflops", 1590.0)
+    src = "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if pk else "fallback 1.59 PFLOP/s"
+
+    def entry(name, kernel, traffic_key):
+        t, flops = res[name]
+        traffic = None
+        try:
+            for e in json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_full_summary.json"))):
+                if traffic_key in e["kernel"]:
+                    traffic = e["dram_bytes_total"] * B / float(e.get("batch", 512))
+        except Exception:  # noqa: BLE001
+            pass
+        return {"bound": "tensor", "kernel": kernel, "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": flops / t / 1e12 / peak, "traffic": traffic, "algorithmic_flops_per_launch": flops,
+                "us_per_launch": t * 1e6, "peak_source": src, "share_source": ROOFLINE_NOTE,
+                "shape": f"B={B} N=10 Q=128 K=1152 d_head=50 (padded 64), attention dropout 0.1; L2-cold (K/V of one "
+                         f"launch = {2 * K * B * NH * 2 / 1e6:.0f} MB)"}
+    return entry("bwd", "relattn_bwd_tc_kernel", "relattn_bwd"), entry("fwd", "relattn_fwd_tc_kernel", "relattn_fwd")
+
+
 def time_calls(fn, reps):
     ts = []
     for _ in range(reps):
@@ -227,83 +475,88 @@ def time_calls(fn, reps):
     return sorted(ts)[len(ts) // 2]
 
 
-def gan_phase_extra(dev, B, mle_ms, graphs):
-    """experiment_spanbert.yml adversarial phase (transformer_gan.py:232-533): one "dis_loss" and one "gen_loss" call on
-    a [128, B] batch -- 123 Gumbel sampling steps, BERT 5x768 discriminator (seeded random weights), WGAN-GP -- and the
-    tokens/s of the 5-step cycle train.py runs (dis_loss_freq = gen_loss_freq = 5)."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import gan_bench as G
-    from tgan_b200 import lib as L
-    model = G.build(dev)
-    model.temperature = 1.0
-    model.use_cuda_graphs = graphs
-    data = torch.randint(2, WORK["n_token"], (128, B), generator=torch.Generator().manual_seed(7)).to(dev)
-    res = {"batch": B, "sampling_steps": 123, "discriminator": "BERT 5x768 (HuggingFace, TF32), wgan-gp",
-           "launch": "one CUDA graph per phase" if graphs else "host launches"}
-    for phase in ("dis_loss", "gen_loss"):
-        def call():
-            model.zero_grad(set_to_none=False)
-            float(model(data, None, None, phase)[phase])
-        for _ in range(2 if graphs else 1):  # eager (lazy initialisation), then the capturing call
-            call()
-        n0 = L.launch_count()
-        res[phase + "_ms"] = time_calls(call, 2)
-        res[phase + "_launches"] = (L.launch_count() - n0) // 2
-    toks = 5 * WORK["tgt_len"] * B
-    res["cycle_tokens_per_s"] = toks / ((5 * mle_ms + res["dis_loss_ms"] + res["gen_loss_ms"]) / 1e3)
-    res["cycle"] = "5 MLE steps + 1 discriminator update + 1 generator update (train.py:924-1090)"
-    del model
-    torch.cuda.empty_cache()
-    return res
+def eager_gpu_bar(dev):
+    """BASELINE.md 4.6 / SURVEY 2a: the same modules run EAGER on the B200 (library kernels: ATen / cuBLAS) -- the
+    oracle port executes unchanged on CUDA tensors.  MLE fwd+bwd at B = 32 (the oracle materialises the [B, N, Q, K]
+    score tensors in fp32 like the reference does), TF32 matmuls and bf16 autocast."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import txl_oracle as O
+    shape = O.TxlShape(n_layer=WORK["n_layer"], n_head=WORK["n_head"], d_model=WORK["d_model"],
+                       d_inner=WORK["d_inner"], n_token=WORK["n_token"], mem_len=WORK["mem_len"])
+    B, Q, V = 32, WORK["tgt_len"], WORK["n_token"]
+    p = {k: v.to(dev).requires_grad_(True) for k, v in O.init_params(shape, 1111).items()}
+    g = torch.Generator().manual_seed(1)
+    mems = (0.1 * torch.randn(shape.n_layer + 1, WORK["mem_len"], B, shape.d_model, generator=g)).to(dev)
+    data = torch.randint(2, V, (Q, B), generator=g).to(dev)
+    target = torch.randint(2, V, (Q, B), generator=g).to(dev)
+    reset = torch.zeros(B, dtype=torch.bool, device=dev)
+    out = {"batch": B, "what": "oracle/txl_oracle.py (the reference's algorithm, eager torch) on cuda: MLE fwd+bwd, M=1024"}
+    prev = torch.backends.cuda.matmul.allow_tf32
 
-
-def generate_extra(model, dev, B=128, mem_len=4146, steps=32):
-    """inference_unconditional.yml decode step (generate.py:132-226 -> forward_generate, mem_transformer.py:578-600):
-    one new token per sequence against a full memory of 4146 positions, K/V projections served from the cache."""
-    V = WORK["n_token"]
-    g = torch.Generator().manual_seed(3)
-    was_training, cached = model.training, (model.tgt_len, model.mem_len)
-    graphs, model.use_cuda_graphs = model.use_cuda_graphs, False
-    model.eval()
+    def step():
+        loss, _ = O.mle_forward(data, target, reset, mems, p, shape)
+        loss.mean().backward()
+        for t in p.values():
+            t.grad = None
     try:
-        with torch.no_grad():
-            mems = None
-            model.reset_length(128, mem_len)
-            for _ in range((mem_len + 127) // 128):  # fill the memory with 128-token segments
-                _, mems = model.forward_generate(torch.randint(2, V, (128, B), generator=g).to(dev), mems)
-            model.reset_length(1, mem_len)
-            tok = torch.randint(2, V, (1, B), generator=g).to(dev)
-            state = {"mems": mems}
+        torch.backends.cuda.matmul.allow_tf32 = True
+        step()
+        out["tf32_tokens_per_s"] = Q * B / (time_calls(step, 3) / 1e3)
 
-            def step():
-                logits, state["mems"] = model.forward_generate(tok, state["mems"])
-                return logits
-            for _ in range(8):
-                step()
-            ms = time_calls(lambda: [step() for _ in range(steps)], 3) / steps
+        def step_bf16():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss, _ = O.mle_forward(data, target, reset, mems, p, shape)
+            loss.float().mean().backward()
+            for t in p.values():
+                t.grad = None
+        step_bf16()
+        out["bf16_autocast_tokens_per_s"] = Q * B / (time_calls(step_bf16, 3) / 1e3)
     finally:
-        model.reset_length(*cached)
-        model.train(was_training)
-        model.use_cuda_graphs = graphs
-    return {"batch": B, "mem_len": mem_len, "ms_per_step": ms, "tokens_per_s": B / (ms / 1e3),
-            "note": "logits only (sampling / top-k is the caller's, generate.py:228-304); host-launched"}
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
 
 
 def run_extras_only(args):
     """Side measurements in their own process: a failure there can never take the headline line with it."""
-    import mem_transformer as MT
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    model = MT.MemTransformerLM(make_cfg(), WORK["n_token"], 0)
-    init_like_train_py(model, 1111)
-    model = model.to(dev).train()
     extras = {}
-    for name, fn in (("generate", lambda: generate_extra(model, dev)),
-                     ("gan_phase", lambda: gan_phase_extra(dev, args.global_batch, args.extras_only, not args.no_graphs))):
+    cyc = Cycle(args, dev, 1, 0)
+    fill = WORK["mem_len"] // WORK["tgt_len"]
+    phases = 0 if args.no_graphs else (WORK["mem_len"] + WORK["tgt_len"]) // WORK["tgt_len"]
+    try:
+        for _ in range(fill + phases + 2):
+            cyc.mle_step(False)
+        ms = time_calls(lambda: [cyc.mle_step(False) for _ in range(5)], 3) / 5
+        toks = WORK["tgt_len"] * args.global_batch
+        extras["mle_only"] = {"ms_per_step": ms, "tokens_per_s": toks / (ms / 1e3),
+                              "step_tensor_frac_of_sustained_peak": 231.8e6 * toks / (ms / 1e3) /
+                              ((peaks() or {}).get("bf16_tflops_sustained", 1400.0) * 1e12),
+                              "what": "experiment_baseline.yml MLE step alone (round 1's headline), 231.8 MFLOP/token fwd+bwd"}
+        if cyc.gan:
+            res = {}
+            L = cyc.L
+            for phase, opt in (("dis_loss", cyc.dis_opt), ("gen_loss", cyc.gen_opt)):
+                def call():
+                    cyc.model(cyc.dev_dis[0], None, None, phase)
+                    opt.step()
+                    cyc.fp.zero_grad()
+                    cyc.dfp.zero_grad()
+                for _ in range(3):
+                    call()
+                n0 = L.launch_count()
+                res[phase + "_ms"] = time_calls(call, 3)
+                res[phase + "_launches"] = (L.launch_count() - n0) // 3
+            extras["gan_phases"] = res
+    except Exception as e:  # noqa: BLE001
+        extras["phases_error"] = repr(e)[:300]
+    del cyc
+    torch.cuda.empty_cache()
+    for name, fn in (("eager_gpu_bar", lambda: eager_gpu_bar(dev)),):
         try:
             extras[name] = fn()
         except Exception as e:  # noqa: BLE001
-            extras[name] = {"error": repr(e)[:200]}
+            extras[name] = {"error": repr(e)[:300]}
     print(json.dumps(extras))
 
 
@@ -311,7 +564,7 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
-    if args.extras_only is not None:
+    if args.extras_only:
         return run_extras_only(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -321,55 +574,13 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    import mem_transformer as MT
     from tgan_b200 import lib as L
 
     if args.global_batch % (world * args.batch_chunk):
         raise SystemExit("global batch must divide by gpus * batch_chunk")
-    Bc = args.global_batch // world // args.batch_chunk  # sequences per micro-batch on this rank
-    Q, V = WORK["tgt_len"], WORK["n_token"]
-    model = MT.MemTransformerLM(make_cfg(), V, 0)
-    init_like_train_py(model, 1111)
-    model = model.to(dev).train()
-    model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    model.kernel_impl = args.kernel_impl
-    model.use_cuda_graphs = not args.no_graphs
-    from tgan_b200 import dp
-    fp = dp.FlatParams(model.parameters())  # one flat parameter / gradient buffer: all-reduce, clip and Adam are one call each
-    lr = WORK["lr"] / world  # train.py:392 divides lr by the GPU count
-    opt = dp.FusedClipAdam(fp, lr, clip=WORK["clip"], world=world)
-    gen = torch.Generator().manual_seed(dp.rank_seed(1111, rank))  # train.py:224
-    n_chunks = args.batch_chunk
-    pin = lambda t: t.pin_memory()
-    host_data = [pin(torch.randint(2, V, (Q, Bc), generator=gen)) for _ in range(4 * n_chunks)]
-    host_tgt = [pin(torch.randint(2, V, (Q, Bc), generator=gen)) for _ in range(4 * n_chunks)]
-    dev_data = [t.to(dev) for t in host_data]
-    dev_tgt = [t.to(dev) for t in host_tgt]
-    reset = torch.zeros(Bc, dtype=torch.bool, device=dev)
-    mems = [None] * n_chunks
-    loss_host = torch.zeros(1).pin_memory()
-    step_no = [0]
-
-    def train_step(e2e):
-        step_no[0] += 1
-        total = None
-        for c in range(n_chunks):
-            i = (step_no[0] * n_chunks + c) % len(host_data)
-            if e2e:
-                data = host_data[i].to(dev, non_blocking=True)
-                tgt = host_tgt[i].to(dev, non_blocking=True)
-            else:
-                data, tgt = dev_data[i], dev_tgt[i]
-            loss, mems[c] = model(data, tgt, reset, mems[c])
-            l = loss.mean() / n_chunks  # train.py:891-892
-            l.backward()
-            total = l.detach() if total is None else total + l.detach()
-        opt.step()  # one NCCL all-reduce of the flat gradient per optimizer step, then fused clip + Adam
-        # the flat buffer changed in place: tell the engine to re-pack (parameter views share its version counter)
-        model._engine._packed_version = None
-        if e2e:
-            loss_host.copy_(total.view(1), non_blocking=True)
-        return total
+    Q = WORK["tgt_len"]
+    cyc = Cycle(args, dev, world, rank)
+    freq = WORK["gan_freq"]
 
     def barrier():
         if world > 1:
@@ -377,12 +588,14 @@ def main():
         torch.cuda.synchronize()
 
     def timed(k, e2e):
+        cyc.it = 0  # the timed region starts on a cycle boundary: iterations 0, 5, ... carry the GAN updates
+        cyc.h2d = cyc.d2h = 0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = L.launch_count()
         e0.record()
         for _ in range(k):
-            train_step(e2e)
+            cyc.iteration(e2e)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -390,96 +603,71 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), L.launch_count() - l0
 
-    # Untimed steps: the --warmup W steps the contract asks for, preceded by what the workload itself needs before it is
-    # in steady state -- 8 segments to fill the 1024-position recurrence memory (the timed step must attend over a
-    # full memory), then one pass over the 9 ring phases so that every phase's CUDA graphs exist.  Reported as
-    # "untimed_steps"; "warmup" echoes W.
-    # ... then one more pass over every ring phase so that each phase's forward / backward graph is captured
+    # Untimed: what the workload needs before it is in steady state -- 8 MLE segments to fill the 1024-position
+    # recurrence memory, one pass over the 9 ring phases so that every phase's CUDA graphs exist, the eager +
+    # capturing calls of both adversarial phases -- then the --warmup W iterations the contract asks for.
     fill = WORK["mem_len"] // Q
     phases = 0 if args.no_graphs else (WORK["mem_len"] + Q) // Q
-    warm_segments = args.warm_segments if args.warm_segments is not None else max(args.warmup, fill) + phases + 1
+    warm_segments = args.warm_segments if args.warm_segments is not None else fill + phases + 1
     for _ in range(warm_segments):
-        train_step(False)
+        cyc.mle_step(False)
+    if cyc.gan:
+        for _ in range(3):
+            cyc.gan_updates(False)
+    cyc.it = 0
+    for _ in range(args.warmup):
+        cyc.iteration(False)
+    untimed = warm_segments + args.warmup
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev, launches = timed(args.steps, False)
     clocks = sampler.stop()
     ms_e2e, _ = timed(args.steps, True)
-    final_loss = float(loss_host.item())
+    h2d, d2h = cyc.h2d / args.steps, cyc.d2h / args.steps
+    torch.cuda.synchronize()
+    final_loss = [float(x) for x in cyc.loss_host]
     tokens = Q * args.global_batch * args.steps
     value = tokens / (ms_dev / 1e3)
     e2e_value = tokens / (ms_e2e / 1e3)
+    gan_updates = len([i for i in range(args.steps) if i % freq == 0]) if cyc.gan else 0
+    B_rank = cyc.B
+    del cyc
+    torch.cuda.empty_cache()
 
-    # roofline of the dominant dense contraction: K/V projection over [memory; segment] rows (58% of the FLOPs)
-    roof = None
+    roof = roof2 = None
     if rank == 0:
-        pk = peaks()
-        Mrows = (WORK["mem_len"] + Q) * Bc
-        DP, NH = 512, 640
-        A = torch.randn(Mrows, DP, device=dev).to(torch.bfloat16)
-        W = torch.randn(2 * NH, DP, device=dev).to(torch.bfloat16)
-        C = torch.empty(Mrows, 2 * NH, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            L.gemm(A, W, C, M=Mrows, N=2 * NH, K=DP, impl=args.kernel_impl)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            L.gemm(A, W, C, M=Mrows, N=2 * NH, K=DP, impl=args.kernel_impl)
-        e1.record()
-        torch.cuda.synchronize()
-        t = e0.elapsed_time(e1) / reps / 1e3
-        alg_flops = 2.0 * Mrows * WORK["d_model"] * 2 * WORK["d_model"]  # 2*B*K*D*2D
-        peak = (pk or {}).get("bf16_tflops", 1590.0)
-        # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (taken at M = 589824 rows;
-        # the traffic is the A read + C write, linear in the rows), scaled to this run's rows
-        traffic, traffic_src = None, None
         try:
-            for e in json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary_v2.json"))):
-                if "gemm_tc" in e["kernel"]:
-                    traffic = e["dram_bytes_total"] * Mrows / 589824.0
-                    traffic_src = "profiles/r1_ncu_full_summary_v2.json (%s, ncu --set full at 589824 rows, scaled by rows)" % e["report"]
-        except Exception:  # noqa: BLE001
-            pass
-        roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel (K/V projection, M=%d N=1280 K=512, CTA pairs)" % Mrows,
-                "achieved": alg_flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": alg_flops / t / 1e12 / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_flops_per_launch": alg_flops, "padded_flops_per_launch": 2.0 * Mrows * 512 * 1280,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if pk else "fallback 1.59 PFLOP/s",
-                "us_per_launch": t * 1e6}
-        del A, W, C
+            roof, roof2 = attention_roofline(dev, B_rank, peaks())
+        except Exception as e:  # noqa: BLE001
+            roof = {"error": repr(e)[:200]}
     extras = None
     if rank == 0 and world == 1 and not args.no_extras and args.dtype == "bf16":
-        cmd = [sys.executable, os.path.abspath(__file__), "--extras-only", repr(ms_dev / args.steps), "--global-batch",
-               str(args.global_batch)] + (["--no-graphs"] if args.no_graphs else [])
+        cmd = [sys.executable, os.path.abspath(__file__), "--extras-only", "--global-batch", str(args.global_batch),
+               "--workload", args.workload] + (["--no-graphs"] if args.no_graphs else [])
         env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)))
         for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
         try:
-            out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
             extras = json.loads(out.stdout.strip().splitlines()[-1])
         except Exception as e:  # noqa: BLE001  (side measurement: never lose the headline line)
             extras = {"error": repr(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.cpu_batch)
+        cpu = cpu_baseline(args.cpu_batch, args.workload == "gan")
     if rank == 0:
-        step_flops = 231.8e6 * Q * args.global_batch  # fwd+bwd algorithmic FLOPs per token
-        pk = peaks() or {}
         print(json.dumps({
-            "metric": "train tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "untimed_steps": warm_segments, "ms_per_step": ms_dev / args.steps,
+            "metric": "train tokens/sec (GAN step)" if args.workload == "gan" else "train tokens/sec",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "untimed_steps": untimed, "ms_per_step": ms_dev / args.steps,
+            "gan_updates_in_timed_region": {"dis": gan_updates, "gen": gan_updates},
             "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": 2 * 8 * Q * (args.global_batch // world),
-                    "d2h_bytes_per_step": 4, "final_loss": final_loss},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "final_losses_mle_dis_gen": final_loss},
             "gpu_launches": launches,
-            "step_tensor_frac_of_sustained_peak": step_flops / (ms_dev / args.steps / 1e3) / world /
-                                                  (pk.get("bf16_tflops_sustained", 1400.0) * 1e12),
-            "roofline": roof, "cpu_baseline": cpu, "extras": extras}))
+            "roofline": roof, "roofline_secondary": roof2, "cpu_baseline": cpu, "extras": extras}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -277,7 +277,8 @@ def generate_gumbel(data, temperature, mems, p, shape: TxlShape, U: torch.Tensor
 # A11 (generator side)  the sampling loop of TransformerGAN.forward      transformer_gan.py:273-349
 # ----------------------------------------------------------------------------------------------
 def sample_fake_chunks(data: torch.Tensor, p, shape_gen: TxlShape, temperature: float, noise: List[torch.Tensor],
-                       tgt_len: int, context_len: int, sample_chunks_mem: int, truncate_backprop: bool = False):
+                       tgt_len: int, context_len: int, sample_chunks_mem: int, truncate_backprop: bool = False,
+                       margins: Optional[List[torch.Tensor]] = None):
     """Replays the generator side of one 'gen_loss'/'dis_loss' call.  ``shape_gen.mem_len`` must be
     DISCRIMINATOR.mem_len (the call runs under reset_length(1, mem_len), transformer_gan.py:251).
     ``noise[k]`` is the uniform tensor [1,B,V] consumed by the k-th forward_generate_gumbel call.
@@ -302,7 +303,10 @@ def sample_fake_chunks(data: torch.Tensor, p, shape_gen: TxlShape, temperature: 
                 inp = seq[-1].argmax(-1)[None, :].detach()                            # :315
             else:
                 inp = seq[-1][None]                                                   # :319
-            st, mems, _, _ = generate_gumbel(inp, temperature, mems, p, shape_gen, noise[k])
+            st, mems, lg, _ = generate_gumbel(inp, temperature, mems, p, shape_gen, noise[k])
+            if margins is not None:  # top-2 margin of (logit + g) per sequence: where a lower-precision run may differ
+                top2 = (lg.detach()[0] + gumbel_noise(noise[k][0].to(lg.dtype))).topk(2, dim=-1).values
+                margins.append(top2[:, 0] - top2[:, 1])
             k += 1
             seq.append(st[0])
         if len(seq) == sample_len + 1:                                                # :339-340
@@ -335,12 +339,11 @@ def gradient_penalty(disc_on_onehot, real_1h: torch.Tensor, fake: torch.Tensor, 
     pass ``embed`` (x^ -> x^ E) and ``disc_on_embeds``."""
     B = real_1h.shape[0]
     a = alpha.to(real_1h.dtype).view(B, 1, 1)
-    x = a * real_1h + (1 - a) * fake.detach()
+    x = (a * real_1h + (1 - a) * fake.detach()).detach().requires_grad_(True)  # Variable(requires_grad=True), :208-209
     if embed is not None:
         x = embed(x)
         d = disc_on_embeds(x)
     else:
-        x = x.detach().requires_grad_(True)
         d = disc_on_onehot(x)
     (g,) = torch.autograd.grad(d, x, grad_outputs=torch.ones_like(d), create_graph=True, retain_graph=True)
     slopes = torch.sqrt(g.reshape(B, -1).pow(2).sum(1) + 1e-12)
@@ -358,7 +361,9 @@ def gan_step(mode: str, data: torch.Tensor, p, shape_gen: TxlShape, disc_on_oneh
     ``extra_col`` = 1 for the BERT discriminator (its vocabulary has one more id, :396-399), 0 for the CNN one."""
     V = shape_gen.n_token
     share = batch_chunk * sample_chunks_mem
-    chunks = sample_fake_chunks(data, p, shape_gen, temperature, noise, tgt_len, context_len, sample_chunks_mem)
+    margins: List[torch.Tensor] = []
+    chunks = sample_fake_chunks(data, p, shape_gen, temperature, noise, tgt_len, context_len, sample_chunks_mem,
+                                margins=margins)
     g_sum = d_sum = gp_sum = 0.0
     ids = []
     for k, (cs, fake) in enumerate(chunks):
@@ -382,7 +387,7 @@ def gan_step(mode: str, data: torch.Tensor, p, shape_gen: TxlShape, disc_on_oneh
                 (gp * dis_loss_factor / share).backward()
         else:
             (g_loss * gen_loss_factor / share).backward()
-    out = {"ids": torch.cat(ids, 0)}
+    out = {"ids": torch.cat(ids, 0), "margins": torch.stack(margins, 0) if margins else None}
     if mode == "dis_loss":
         out["dis_loss"] = dis_loss_factor * d_sum / sample_chunks_mem
         if "gp" in loss_type:

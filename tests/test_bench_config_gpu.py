@@ -1,0 +1,161 @@
+"""GPU parity of exactly what bench.py times: the real-size generator (6 layers x d_model 500,
+10 heads, d_inner 1000, vocab 310) at tgt_len 128 / mem_len 1024 in bf16 -- tcgen05 attention forward / backward, the
+CTA-pair GEMM, every phase of the recurrence-memory ring including the wrap, once with host launches and once through
+the captured forward / backward CUDA graphs -- against the CPU oracle (oracle/txl_oracle.py, fp32) on the same tokens
+and weights.  Reference: MemTransformerLM.forward mem_transformer.py:653-670 (+ everything it calls).
+
+Tolerances (BASELINE.json): loss within 1e-2 relative in bf16.  Gradients: per-tensor relative Frobenius error and
+cosine against the oracle's autograd; plus a flip-excluded element check (a ReLU pre-activation within bf16 rounding
+of zero flips its mask and moves single dW entries by one whole term -- those entries are excluded by a robust
+quantile, so a systematic 5 % error cannot hide under the Frobenius bound)."""
+import types
+
+import pytest
+import torch
+
+import txl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REAL = dict(n_layer=6, n_head=10, d_model=500, d_inner=1000, n_token=310)
+
+
+def _cfg(shape, tgt_len, dropout=0.0):
+    ns = types.SimpleNamespace
+    return ns(MODEL=ns(num_layers=shape.n_layer, num_heads=shape.n_head, units=shape.d_model,
+                       inner_size=shape.d_inner, dropout=dropout, attention_dropout=dropout, tie_embedding=True,
+                       tie_proj=False, pre_lnorm=False, same_length=shape.same_length, clamp_len=shape.clamp_len),
+              TRAIN=ns(tgt_length=tgt_len, mem_length=shape.mem_len, pad_type="model", replace_start_with_pad=False,
+                       append_note_status=False))
+
+
+def _build(shape, seed, tgt_len, dtype=torch.bfloat16):
+    import mem_transformer as MT
+    model = MT.MemTransformerLM(_cfg(shape, tgt_len), shape.n_token, 0)
+    p = O.init_params(shape, seed)
+    sd = {k: v.clone() for k, v in p.items()}
+    sd["crit.out_layers.0.weight"] = sd["word_emb.emb_layers.0.weight"]
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda()
+    model.compute_dtype = dtype
+    return model, p
+
+
+def _stream(B, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(2, 310, (n + 1, B), generator=g)
+
+
+def grad_report(got, want):
+    """(relative Frobenius error, cosine, flip-excluded relative error).  The last one is the 90 % quantile of
+    |got - want| / (|want| + rms(want)): robust against the few entries a ReLU-mask flip moves by a whole term, but a
+    uniform relative error e shows up as ~e."""
+    g, w = got.double().reshape(-1).cpu(), want.double().reshape(-1).cpu()
+    frob = ((g - w).norm() / w.norm().clamp_min(1e-30)).item()
+    cos = (torch.dot(g, w) / (g.norm() * w.norm()).clamp_min(1e-30)).item()
+    rms = w.norm() / max(w.numel(), 1) ** 0.5
+    rel = (g - w).abs() / (w.abs() + rms)
+    q90 = torch.quantile(rel[:: max(1, rel.numel() // 200000)], 0.9).item()
+    return frob, cos, q90
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_real_size_training_segments_match_oracle_through_all_ring_phases(graphs):
+    """20 segments of 128 tokens at B = 2: 8 fill the 1024-row memory, the next 9 visit every phase of the
+    1152-position ring (the wrap included), the rest re-visit phases (graph REPLAY rather than capture); a `reset_mems`
+    row in one steady-state segment.  Loss of every segment and the gradients of three steady-state segments are
+    compared with the oracle."""
+    shape = O.TxlShape(mem_len=1024, **REAL)
+    Q, B, nseg = 128, 2, 20
+    model, p = _build(shape, 21, Q)
+    model.train()  # dropout 0: the training code path (saved activations, backward) without noise
+    model.use_cuda_graphs = graphs
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    stream = _stream(B, Q * nseg, 5)
+    mems, mems_o = None, None
+    check_grads_at = {9, 13, 19}  # full memory; 13 carries the reset row; 19 is a graph REPLAY of a phase captured earlier
+    worst_loss = 0.0
+    for s in range(nseg):
+        data, target = stream[s * Q:(s + 1) * Q], stream[s * Q + 1:(s + 1) * Q + 1]
+        reset = torch.zeros(B, dtype=torch.bool)
+        if s == 13:
+            reset[1] = True
+        model.zero_grad(set_to_none=False)
+        loss, mems = model(data.cuda(), target.cuda(), reset.cuda(), mems)
+        loss.mean().backward()
+        for t in po.values():
+            t.grad = None
+        loss_o, mems_o = O.mle_forward(data, target, reset, mems_o, po, shape)
+        if s in check_grads_at:
+            loss_o.mean().backward()
+        got, want = loss.detach().cpu().double(), loss_o.detach().double()
+        assert got.shape == want.shape
+        rel_mean = abs(got.mean().item() - want.mean().item()) / want.mean().item()
+        rel_tok = ((got - want).abs() / want.abs().clamp_min(1.0)).max().item()
+        worst_loss = max(worst_loss, rel_mean)
+        assert rel_mean < 1e-2, (s, rel_mean)
+        assert rel_tok < 5e-2, (s, rel_tok)  # a single token's nll in bf16 (6 layers, 1152 keys)
+        if s in check_grads_at:
+            bad = {}
+            for name, prm in model.named_parameters():
+                want_g = po[name].grad
+                frob, cos, q90 = grad_report(prm.grad, want_g)
+                if not (frob < 0.08 and cos > 0.997 and q90 < 0.05):
+                    bad[name] = (frob, cos, q90)
+            assert not bad, (s, bad)
+    if graphs:
+        assert len(model._graphs) == 9, len(model._graphs)  # one (forward, backward) pair per ring phase
+    assert mems.size(1) == 1024
+    m = mems.materialize().cpu()
+    assert (m - mems_o).abs().max() < 0.25 and ((m - mems_o).norm() / mems_o.norm()) < 2e-2
+    print(f"\nreal-size bf16 graphs={graphs}: worst relative mean-loss error {worst_loss:.2e}")
+
+
+def test_real_size_eval_shape_same_length_matches_oracle():
+    """train.py's evaluate() shape (train.py:758-760): tgt_len 128, mem_len 2048, same_length=True, eval mode."""
+    shape = O.TxlShape(mem_len=2048, same_length=True, **REAL)
+    Q, B, nseg = 128, 2, 19  # 16 segments fill the memory, the rest run at K = 2176
+    model, p = _build(shape, 22, Q)
+    model.eval()
+    stream = _stream(B, Q * nseg, 6)
+    mems, mems_o = None, None
+    with torch.no_grad():
+        for s in range(nseg):
+            data, target = stream[s * Q:(s + 1) * Q], stream[s * Q + 1:(s + 1) * Q + 1]
+            loss, mems = model(data.cuda(), target.cuda(), None, mems)
+            loss_o, mems_o = O.mle_forward(data, target, None, mems_o, p, shape)
+            got, want = loss.cpu().double(), loss_o.double()
+            rel_mean = abs(got.mean().item() - want.mean().item()) / want.mean().item()
+            assert rel_mean < 1e-2, (s, rel_mean)
+            assert ((got - want).abs() / want.abs().clamp_min(1.0)).max().item() < 5e-2, s
+    assert mems.size(1) == 2048
+
+
+def test_gumbel_ids_bf16_respect_the_margin_rule():
+    """north_star: sampled ids bit-exact given the same Gumbel noise wherever the top-2 (logit + g) margin exceeds the
+    tolerance.  bf16 engine vs fp32 oracle, real-size model, 24 chained single-token steps."""
+    shape = O.TxlShape(mem_len=64, **REAL)
+    model, p = _build(shape, 23, 1)
+    model.eval()
+    B, V, steps, tau = 8, 310, 24, 0.8
+    g = torch.Generator().manual_seed(9)
+    ctx = torch.randint(2, V, (4, B), generator=g)
+    with torch.no_grad():
+        _, mems = model.forward_generate(ctx.cuda(), None)
+        _, mems_o = O.generate_logits(ctx, None, p, shape)
+        inp = torch.randint(2, V, (1, B), generator=g)
+        checked = 0
+        for t in range(steps):
+            U = torch.rand(1, B, V, generator=g)
+            st, mems = model.forward_generate_gumbel(inp.cuda(), tau, mems, noise=U)
+            st_o, mems_o, logits_o, _ = O.generate_gumbel(inp, tau, mems_o, p, shape, U)
+            z = logits_o.reshape(B, V).double() + O.gumbel_noise(U.reshape(B, V).double())
+            top2 = z.topk(2, dim=-1).values
+            margin = top2[:, 0] - top2[:, 1]
+            ids, ids_o = st.argmax(-1).cpu().view(-1), st_o.argmax(-1).view(-1)
+            # bf16 logits are within 1e-2 relative of |logit| ~ O(10): ids must agree wherever the margin clears that
+            clear = margin > 1e-2 * z.abs().max(dim=-1).values.clamp_min(1.0)
+            assert torch.equal(ids[clear], ids_o[clear]), (t, ids, ids_o, margin)
+            checked += int(clear.sum())
+            inp = ids_o.view(1, B)  # both chains continue from the oracle's token
+    assert checked > steps * B * 0.8

@@ -114,3 +114,95 @@ def test_gan_step_matches_reference_golden(name, tmp_path):
         assert checked >= 5
         if mode == "dis_loss":
             assert all(prm.grad is None for prm in model.generator.parameters())
+
+
+def _build_gan(name, tmp_path, dtype):
+    import transformer_gan as TG
+    z, shape = GU.load(name)
+    V = shape.n_token
+    bert_dir = str(tmp_path / "bert")
+    os.makedirs(bert_dir, exist_ok=True)
+    json.dump(dict(O.TINY_BERT, vocab_size=V + 1), open(os.path.join(bert_dir, "config.json"), "w"))
+    torch.manual_seed(0)
+    model = TG.TransformerGAN(_cfg(shape, z, bert_dir), _Vocab(V))
+    sd = {k: v.clone() for k, v in O.init_params(shape, int(z["seed"])).items()}
+    sd["crit.out_layers.0.weight"] = sd["word_emb.emb_layers.0.weight"]
+    model.generator.load_state_dict(sd, strict=False)
+    model.discriminator.load_state_dict(O.seeded_state(model.discriminator, int(z["seed"]) + 1), strict=False)
+    if hasattr(model.discriminator, "dropout"):
+        model.discriminator.dropout.p = 0.0
+    model = model.cuda().train()
+    model.generator.compute_dtype = dtype
+    model.temperature = float(z["temperature"])
+    return model, z, shape
+
+
+@pytest.mark.parametrize("name", ["gan_bert_tiny", "gan_cnn_tiny"])
+def test_gan_step_bf16_eager_and_graphed_match_reference(name, tmp_path):
+    """The configuration bench.py times: generator in bf16, projected-K/V cache, the whole adversarial phase replayed as
+    one CUDA graph (TransformerGAN.use_cuda_graphs).  Losses within 1e-2 (bf16 tolerance of BASELINE.json) of the
+    UNMODIFIED reference's goldens; sampled ids equal to the oracle's along every sequence up to the first step whose
+    top-2 (logit + g) margin is inside the tolerance; the graph replay reproduces the eager bf16 call."""
+    model, z, shape = _build_gan(name, tmp_path, torch.bfloat16)
+    V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
+    data = torch.from_numpy(z["data"]).cuda()
+    U = torch.from_numpy(z["U"]).cuda()
+    alpha = torch.from_numpy(z["alpha"]).cuda()
+    chunk_of = {"k": 0}
+    model.gumbel_noise_source = lambda step, shp: U[step:step + 1]
+
+    def alpha_src(b):
+        a = alpha[chunk_of["k"] % chunks]
+        chunk_of["k"] += 1
+        return a
+    model.gp_alpha_source = alpha_src
+    model.sources_graph_safe = True  # views of static device tensors
+    disc, dparams, extra, embed, on_emb = build_disc(z, shape, torch.float64)
+    Ul = [torch.from_numpy(z["U"][k:k + 1]).double() for k in range(T - ctx)]
+    al = [torch.from_numpy(z["alpha"][k]).double() for k in range(chunks)]
+    gen_rows = [i for i in range(T) if i >= ctx]
+
+    def run(mode):
+        model.zero_grad(set_to_none=False)
+        chunk_of["k"] = 0
+        r = model(data, None, None, mode)
+        torch.cuda.synchronize()
+        owner = model.discriminator if mode == "dis_loss" else model.generator
+        grads = {k: p.grad.detach().clone() for k, p in owner.named_parameters() if p.grad is not None}
+        return {k: float(v) for k, v in r.items() if v is not None and k != "mems"}, model.last_sampled_ids.clone(), grads
+
+    for mode in ("dis_loss", "gen_loss"):
+        model.use_cuda_graphs = False
+        for prm in model.parameters():
+            if prm.grad is None and prm.requires_grad:
+                prm.grad = torch.zeros_like(prm)
+        r_eager, ids_eager, g_eager = run(mode)
+        p = {k: v.double().requires_grad_(True) for k, v in O.init_params(shape, int(z["seed"])).items()}
+        ro = O.gan_step(mode, torch.from_numpy(z["data"]), p, shape, disc, extra, str(z["loss_type"]),
+                        float(z["temperature"]), Ul, al, T, ctx, chunks, embed=embed, disc_on_embeds=on_emb)
+        want_ids = torch.cat([c for c in torch.split(ro["ids"], T // chunks)], 0)[gen_rows]
+        margins = ro["margins"]  # [T - ctx, B]
+        ids = ids_eager.cpu()
+        all_on_prefix = True
+        for b in range(B):
+            for t in range(T - ctx):
+                if margins[t, b] < 2e-2:  # inside the bf16 tolerance: this and later steps of the column may differ
+                    all_on_prefix = False
+                    break
+                assert ids[t, b] == want_ids[t, b], (mode, t, b, float(margins[t, b]))
+        if all_on_prefix:  # same samples -> same discriminator inputs: the losses are comparable at the bf16 tolerance
+            for key in ("dis_loss", "gen_loss", "gp_loss"):
+                if f"{mode}.{key}" in z.files:
+                    want, got = float(z[f"{mode}.{key}"]), r_eager[key]
+                    assert abs(got - want) <= 1e-2 * max(1.0, abs(want)), (mode, key, got, want)
+        # graphed: warm call (eager), capturing call, replay -- each must reproduce the eager bf16 numbers
+        model.use_cuda_graphs = True
+        for rep in range(3):
+            r_g, ids_g, g_g = run(mode)
+            assert torch.equal(ids_g, ids_eager), (mode, rep)
+            for key, want in r_eager.items():
+                assert abs(r_g[key] - want) <= 2e-3 * max(1.0, abs(want)), (mode, rep, key, r_g[key], want)
+            for k, want in g_eager.items():
+                err = (g_g[k] - want).norm().item()
+                assert err <= 2e-2 * want.norm().item() + 1e-6, (mode, rep, k, err, want.norm().item())
+        assert any(k[0] == mode for k in model._gan_graphs), "the adversarial phase was not captured"

@@ -1,7 +1,7 @@
 """Times the GAN phases of experiment_spanbert.yml (transformer_gan.py:232-533) on one GPU: one "dis_loss" call and one
 "gen_loss" call of the drop-in TransformerGAN on a [128, B] batch of synthetic MAESTRO-vocab tokens
 (123 Gumbel-softmax sampling steps, BERT 5x768 discriminator with seeded random weights, WGAN-GP).
-Usage: python tools/gan_bench.py [B] [reps] [graphs 0/1]"""
+Usage: python tools/gan_bench.py [B] [reps] [graphs 0/1] [phases, e.g. gen_loss]"""
 import json, os, sys, tempfile, time, types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "transformer-gan_b200"))
@@ -74,7 +74,8 @@ if __name__ == "__main__":
     model.use_cuda_graphs = graphs
     g = torch.Generator().manual_seed(7)
     data = torch.randint(2, 310, (128, B), generator=g).to(dev)
-    for phase in ("dis_loss", "gen_loss"):
+    phases = sys.argv[4].split(",") if len(sys.argv) > 4 else ("dis_loss", "gen_loss")
+    for phase in phases:
         n0 = L.launch_count()
         warm = 2 if graphs else 1  # graphs: first call eager (lazy init), second call captures
         t, v = time_phase(model, data, phase, reps, warm)

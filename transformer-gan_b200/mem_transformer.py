@@ -8,6 +8,7 @@ the reference -- ``MemTransformerLM(cfg, n_token, vec_len)`` with ``forward(data
 CPU fallback: calling the model on a CPU tensor raises.
 """
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -204,7 +205,9 @@ class _TxlGraphFunction(torch.autograd.Function):
                 eng.backward(entry.ectx, dnll=entry.dnll, grad_targets=entry.staged, accumulate=False)
             entry.bwd, entry.n_bwd = g, L.launch_count() - n0
             # eng.backward dropped the activations: their pool blocks may now be reused by the next key's capture
-            # (graphs that share the pool are replayed strictly one after the other)
+            # (graphs that share the pool are replayed strictly one after the other).  The entry must not keep the
+            # ring alive either: its lifetime is the caller's `mems` handle (see _drop_ring_graphs)
+            entry.ectx.ring = entry.ectx.new_mems = entry.ectx.hid_t = None
         entry.bwd.replay()
         L.note_graph_replay(entry.n_bwd)
         grads, staged = [], []
@@ -262,6 +265,7 @@ class MemTransformerLM(nn.Module):
         # _TxlGraphFunction.  Off by default: it pins the input / gradient buffers of the captured shapes.
         self.use_cuda_graphs = False
         self._graphs = {}
+        self._graph_rings = {}
         self._graph_pending = None
         self._grad_staging = None
 
@@ -298,16 +302,23 @@ class MemTransformerLM(nn.Module):
     def _graph_entry(self, eng, data, target, reset_mems, ring):
         """The captured forward for this (ring phase, shape) key; captured on first use."""
         B, Q, T = data.shape[1], data.shape[0], target.shape[0]
-        key = (ring.slabs.data_ptr(), ring.start, ring.length, Q, B, T, self.mem_len, self.same_length, self.training,
+        # Keyed by the identity of the ring's storage object; a finalizer drops every entry of a ring when the ring
+        # dies (each epoch's `mems=None` makes a new one), so a recycled address can never match a stale graph and old
+        # entries do not pin their activations / pool blocks forever.
+        rid = id(ring.slabs)
+        key = (rid, ring.start, ring.length, Q, B, T, self.mem_len, self.same_length, self.training,
                eng.d.dropout, eng.d.dropatt, eng._param_key)
         entry = self._graphs.get(key)
         if entry is None:
+            if rid not in self._graph_rings:
+                self._graph_rings[rid] = weakref.finalize(ring.slabs, MemTransformerLM._drop_ring_graphs,
+                                                          weakref.ref(self), rid)
             entry = _GraphEntry()
             entry.ids, entry.tgt = data.clone(), target.clone()
             entry.reset = torch.zeros(B, dtype=torch.uint8, device=data.device)
             entry.dnll = torch.zeros(T * B, dtype=torch.float32, device=data.device)
             ctr = L.step_counter(data.device)
-            eng._packed_version = None  # the parameter re-pack must be part of the graph
+            eng.invalidate()  # the parameter re-pack must be part of the graph
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
@@ -315,7 +326,7 @@ class MemTransformerLM(nn.Module):
                 ctr.add_(1)
                 entry.ectx = eng.forward(entry.ids, entry.reset, ring, mem_len=self.mem_len, same_length=self.same_length,
                                          training=self.training, target=entry.tgt, n_pred=T, save_for_backward=True)
-            eng._packed_version = None
+            eng.invalidate()
             entry.fwd, entry.n_fwd = g, L.launch_count() - n0
             nm = entry.ectx.new_mems
             entry.new_mems = None if nm is None else (nm.start, nm.length)
@@ -328,8 +339,19 @@ class MemTransformerLM(nn.Module):
             entry.reset.copy_(reset_mems)
         return entry
 
+    @staticmethod
+    def _drop_ring_graphs(self_ref, rid):
+        self = self_ref()
+        if self is None:
+            return
+        self._graph_rings.pop(rid, None)
+        for k in [k for k in self._graphs if k[0] == rid]:
+            del self._graphs[k]
+
     def _run(self, mode, data, target, reset_mems, mems, temperature=None, noise=None):
         eng = self._get_engine()
+        if self.pad_type != "model":
+            reset_mems = None  # the reset mask exists only for pad_type == 'model' (mem_transformer.py:495-528)
         names = [r for r, *_ in eng.layout.reference_map()]
         pd = _param_dict(self)
         if (self.use_cuda_graphs and mode == "mle" and isinstance(mems, RingMems) and self.mem_len > 0
@@ -341,7 +363,8 @@ class MemTransformerLM(nn.Module):
                 self._graph_pending = entry
                 out = _TxlGraphFunction.apply(self, entry, names, *[pd[n] for n in names])
                 start, length = entry.new_mems
-                return out, RingMems(ring.slabs, start, length, self.d_model, kv=ring.kv)
+                ring.note_write((ring.start + ring.length) % ring.capacity, data.shape[0])  # the replay wrote the rows
+                return out, RingMems(ring.slabs, start, length, self.d_model, kv=ring.kv, shared=ring.shared)
         out = _TxlFunction.apply(self, mode, data, target, reset_mems, mems, temperature, noise, names,
                                  *[pd[n] for n in names])
         return out, self._new_mems

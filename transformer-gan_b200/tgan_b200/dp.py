@@ -104,3 +104,7 @@ class FusedClipAdam:
         L.adam_step(fp.flat, fp.grad, self.m, self.v, fp.numel(), self.lr if lr is None else lr, self.betas[0],
                     self.betas[1], self.eps, self.wd, self.steps, self.gnorm_sq, self.clip, 1.0 / self.world)
         fp.zero_grad()
+        # the kernel wrote the flat parameter buffer behind autograd's back (no version counter moved): tell every
+        # engine to re-pack its kernel-private parameter copies at the next forward
+        from .engine import notify_params_updated
+        notify_params_updated()

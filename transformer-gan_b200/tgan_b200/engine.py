@@ -69,11 +69,19 @@ class RingMems:
     The reference returns a fresh ``[n_layer+1, M, B, d_model]`` fp32 tensor per call; ``materialize()``
     produces exactly that tensor (for tests, checkpoints and the generate.py self-check)."""
 
-    def __init__(self, slabs: torch.Tensor, start: int, length: int, d_model: int, kv: Optional[dict] = None):
+    def __init__(self, slabs: torch.Tensor, start: int, length: int, d_model: int, kv: Optional[dict] = None,
+                 shared: Optional[dict] = None):
         self.slabs = slabs
         self.start = start
         self.length = length
         self.d_model = d_model
+        # State shared by every window (handle) over the same slabs: ``gen`` counts the writes into the ring and
+        # ``writes`` logs the most recent ones as (gen, position, count).  A handle remembers the generation it was
+        # produced at; it stays valid until a LATER write lands inside its window (the reference returns fresh
+        # tensors, so an old ``mems`` may legally be passed again -- here that works as long as its rows are intact,
+        # and raises instead of silently attending over overwritten rows otherwise).
+        self.shared = shared if shared is not None else {"gen": 0, "writes": []}
+        self.gen = self.shared["gen"]
         # projected-K/V cache of the ring rows (decode-sized calls only, see TxlEngine.forward): shared by every
         # RingMems window over the same slabs.  {"buf": [n_layer, capacity, B, 2*N*64], "lo", "hi": cached physical
         # rows, "tag": parameter-pack epoch the rows were projected with}
@@ -86,6 +94,31 @@ class RingMems:
     @property
     def bsz(self) -> int:
         return self.slabs.shape[2]
+
+    def check_fresh(self):
+        """Raise if a write issued after this handle was produced overwrote one of its rows."""
+        if self.length == 0:
+            return
+        C = self.capacity
+        log = self.shared["writes"]
+        if log and log[0][0] > self.gen + 1 and self.shared["gen"] - self.gen > len(log):
+            raise L.TganError("stale memory handle: older than the ring's write log (pass the most recent `new_mems`)")
+        for g, pos, cnt in log:
+            if g <= self.gen:
+                continue
+            # overlap of the circular ranges [pos, pos+cnt) and [start, start+length)
+            d = (pos - self.start) % C
+            if d < self.length or d + cnt > C:
+                raise L.TganError(
+                    "stale memory handle: rows of this `mems` were overwritten by a later forward on the same ring "
+                    "(the ring-buffer memory aliases storage; pass the most recent `new_mems`, or "
+                    "`mems.materialize()` a copy if an old memory must be kept)")
+
+    def note_write(self, pos: int, count: int) -> int:
+        sh = self.shared
+        sh["gen"] += 1
+        sh["writes"] = [w for w in sh["writes"][-63:]] + [(sh["gen"], pos, count)]
+        return sh["gen"]
 
     def segments(self, first: int, count: int) -> List[Tuple[int, int]]:
         """physical (position, count) runs covering logical rows [first, first+count)."""
@@ -212,6 +245,15 @@ class _Ctx:
     pass
 
 
+# bumped by notify_params_updated(): optimizers that write the parameter storage directly (tgan_b200.dp.FusedClipAdam
+# on a FlatParams buffer) tell every engine to re-pack at its next forward
+_PARAM_EPOCH = [0]
+
+
+def notify_params_updated() -> None:
+    _PARAM_EPOCH[0] += 1
+
+
 class TxlEngine:
     """Forward / backward of the generator stack on libtgan_b200."""
 
@@ -236,7 +278,9 @@ class TxlEngine:
         self._params: Optional[Dict[str, torch.Tensor]] = None
         self._param_key = None
         self._packed_version = None
+        self._dirty = False        # a backward ran since the last pack (an optimizer step may have followed)
         self._pack_desc = None
+        self._unpack_cache: Dict[tuple, torch.Tensor] = {}
         self._es = 2 if dtype == torch.bfloat16 else 4
         self.pack_epoch = 0        # bumped whenever the packed parameter copies are rewritten
         self.kv_cache_max_q = 8    # calls with at most this many new rows keep / reuse the projected-K/V cache
@@ -290,12 +334,24 @@ class TxlEngine:
         self.pmat.zero_()
         self.pvec.zero_()
 
+    def invalidate(self):
+        """The parameters changed behind autograd's back (``p.data.add_``, a flat-buffer optimizer, a raw copy into the
+        storage): re-pack the kernel-private copies at the next forward.  ``tgan_b200.dp`` optimizers call
+        ``notify_params_updated()``; for third-party optimizers the engine re-packs on the first forward after any
+        backward on its own (an optimizer step is always preceded by one), see ``pack``."""
+        self._packed_version = None
+
     def pack(self):
-        ver = tuple(p._version for p in self._params.values())
-        if ver == self._packed_version:
+        """Refresh the padded bf16 / fp32 parameter copies when the parameters may have changed: a version-counter
+        change (in-place autograd-visible updates, load_state_dict), an explicit invalidate(), a
+        notify_params_updated() from a flat-buffer optimizer, or any backward since the last pack (covers optimizers
+        that update through ``p.data``, e.g. the reference's lamb.py:116, which bumps no version counter)."""
+        ver = (tuple(p._version for p in self._params.values()), _PARAM_EPOCH[0])
+        if ver == self._packed_version and not self._dirty:
             return
         L.pack_params(self.pmat, self.pvec, self._pack_desc, self._pack_desc.shape[0], self._max_elems)
         self._packed_version = ver
+        self._dirty = False
         self.pack_epoch += 1
 
     def _m(self, name):  # (tensor, element offset, ld)
@@ -346,15 +402,15 @@ class TxlEngine:
         ring: RingMems = mems
         if ring.bsz != B:
             raise L.TganError(f"memory batch size {ring.bsz} != input batch size {B}")
-        w = (ring.start + ring.length) % ring.capacity
-        if ring.length > mem_len:  # reset_length shrank the memory: keep the most recent rows
-            ring.start = (ring.start + ring.length - mem_len) % ring.capacity
-            ring.length = mem_len
+        ring.check_fresh()
+        # An incoming memory longer than mem_len (reset_length shrank it between calls) is attended over in full and
+        # truncated afterwards, as the reference does (mem_transformer.py:556-575, 463-470).
+        n = ring.length
+        w = (ring.start + n) % ring.capacity
         # decode-sized calls keep [memory; new rows] physically contiguous (the projected-K/V cache and the attention
         # kernels' single K / V base pointer need it): compact just before the window would wrap
-        wraps = Q <= self.kv_cache_max_q and ring.start + ring.length + Q > ring.capacity
-        if (ring.capacity < min(ring.length, mem_len) + Q or w + Q > ring.capacity or ring.capacity < mem_len + Q
-                or wraps):
+        wraps = Q <= self.kv_cache_max_q and ring.start + n + Q > ring.capacity
+        if ring.capacity < n + Q or w + Q > ring.capacity or ring.capacity < mem_len + Q or wraps:
             # re-layout: the write position reached the end of the buffer (every capacity - mem_len decode steps) or
             # tgt_len / mem_len changed between calls
             return self._relayout(ring, Q, mem_len)
@@ -377,6 +433,7 @@ class TxlEngine:
             nb[:, :n].copy_(buf[:, ring.start:ring.start + n])
             new.kv.update(buf=nb, lo=0, hi=n, tag=self.pack_epoch)
         new.length = n
+        new.gen = new.shared["gen"]
         return new
 
     # -- forward ------------------------------------------------------------------------------------------
@@ -397,6 +454,8 @@ class TxlEngine:
         w = (ring.start + M) % C  # write position of this segment
         if w + Q > C:
             raise L.TganError("internal: ring write would wrap")
+        if mem_len > 0:
+            ring.note_write(w, Q)
         self.calls += 1
         cid = self.calls
         p_drop = d.dropout if training else 0.0
@@ -554,7 +613,7 @@ class TxlEngine:
         if mem_len > 0:
             new_len = min(M + Q, mem_len)
             new_start = (ring.start + M + Q - new_len) % C
-            ctx.new_mems = RingMems(ring.slabs, new_start, new_len, D, kv=ring.kv)
+            ctx.new_mems = RingMems(ring.slabs, new_start, new_len, D, kv=ring.kv, shared=ring.shared)
         else:
             ctx.new_mems = None
         return ctx
@@ -705,23 +764,29 @@ class TxlEngine:
             L.unpack_grads(gm, gv, desc, len(rows), self._max_elems)
             out["__desc__"] = desc  # keep the descriptor table alive until the kernel ran
         ctx.layers = None  # release activations
+        self._dirty = True  # an optimizer step may follow: the next forward re-packs (see pack)
         out.update(grads)
         return out
 
     def _stage_desc(self, rows) -> torch.Tensor:
-        """Descriptor table -> device through pinned memory (an asynchronous copy: no host synchronisation)."""
+        """Descriptor table -> device through pinned memory (an asynchronous copy: no host synchronisation).  The
+        returned device tensor carries its pinned source (``_host``) so that whoever keeps the table alive -- the
+        cache below, a captured graph's entry -- also keeps the copy's source alive."""
         host = torch.tensor(rows, dtype=torch.int64).pin_memory()
         dev = torch.empty_like(host, device=self.device)
         dev.copy_(host, non_blocking=True)
-        self._desc_keepalive = getattr(self, "_desc_keepalive", [])[-7:] + [(host, dev)]
+        dev._host = host
+        self._desc_keepalive = getattr(self, "_desc_keepalive", [])[-7:] + [dev]
         return dev
 
     def _unpack_desc_for(self, targets: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """Cached unpack table whose destinations are the given gradient tensors (rebuilt only when they move)."""
+        """Cached unpack table whose destinations are the given gradient tensors, keyed by their addresses.  Captured
+        graphs must additionally hold the returned tensor themselves (their kernels read it at every replay): the
+        cache is bounded and evicts the oldest tables."""
         key = tuple(targets[ref].data_ptr() for ref, *_ in self.layout.reference_map())
-        cache = getattr(self, "_unpack_cache", None)
-        if cache is not None and cache[0] == key:
-            return cache[1]
+        dev = self._unpack_cache.get(key)
+        if dev is not None:
+            return dev
         rows = []
         for (ref, name, kind, *_), urow in zip(self.layout.reference_map(), self._unpack_rows):
             t = targets[ref]
@@ -729,5 +794,7 @@ class TxlEngine:
                 raise L.TganError(f"gradient target for {ref} must be a contiguous fp32 tensor of the parameter's shape")
             rows.append([t.data_ptr()] + urow[1:])
         dev = self._stage_desc(rows)
-        self._unpack_cache = (key, dev)
+        while len(self._unpack_cache) >= 16:
+            self._unpack_cache.pop(next(iter(self._unpack_cache)))
+        self._unpack_cache[key] = dev
         return dev

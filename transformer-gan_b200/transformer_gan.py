@@ -59,6 +59,8 @@ class TransformerGAN(nn.Module):
         # test hooks: callables returning the uniform noise of the k-th sampling step ([1, B, V]) / the GP alphas ([B])
         self.gumbel_noise_source = None
         self.gp_alpha_source = None
+        # the injected sources return views of static device tensors (no host work): safe to capture in a CUDA graph
+        self.sources_graph_safe = False
         self.last_sampled_ids = None
         # replay the adversarial phase of forward() as one CUDA graph per (phase, batch shape); see _gan_phase_graphed
         self.use_cuda_graphs = False
@@ -182,7 +184,8 @@ class TransformerGAN(nn.Module):
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev_tf32
         try:
-            if (self.use_cuda_graphs and data.is_cuda and self.gumbel_noise_source is None and self.gp_alpha_source is None
+            injected = self.gumbel_noise_source is not None or self.gp_alpha_source is not None
+            if (self.use_cuda_graphs and data.is_cuda and (not injected or self.sources_graph_safe)
                     and self.cfg.DISCRIMINATOR.backprop_outside):
                 out.update(self._gan_phase_graphed(data, train_loss))
             else:
@@ -223,12 +226,14 @@ class TransformerGAN(nn.Module):
             names = [r for r, *_ in eng.layout.reference_map()]
             pd = dict(gen.named_parameters())
             pd.setdefault("crit.out_layers.0.weight", gen.crit.out_layers[0].weight)
-            eng._unpack_desc_for({n: pd[n].grad for n in names})  # descriptor table staged outside the capture
             entry = type("GanGraph", (), {})()
+            # descriptor table staged outside the capture; the entry owns it for the graph's lifetime (the captured
+            # unpack kernel reads it at every replay -- the engine's cache may evict its own reference)
+            entry.desc = eng._unpack_desc_for({n: pd[n].grad for n in names})
             entry.data, entry.tau = data.clone(), torch.ones(1, dtype=torch.float32, device=data.device)
             entry.grad_ptrs = tuple(t.data_ptr() for t in grads)
             ctr = L.step_counter(data.device)
-            eng._packed_version = None  # the parameter re-pack must be part of the graph
+            eng.invalidate()  # the parameter re-pack must be part of the graph
             saved_tau, self.temperature = self.temperature, entry.tau
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -239,7 +244,7 @@ class TransformerGAN(nn.Module):
                     entry.out = self._gan_phase(entry.data, train_loss)
             finally:
                 self.temperature = saved_tau
-                eng._packed_version = None
+                eng.invalidate()
             entry.graph, entry.n = g, L.launch_count() - n0
             self._gan_graphs[key] = entry
         entry = self._gan_graphs[key]
