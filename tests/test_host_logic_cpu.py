@@ -70,7 +70,10 @@ def test_reference_arm_prints_the_contract_line():
                           "--warmup", "0", "--cpu-batch", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
-    assert d["impl"] == "reference" and d["metric"] == "train tokens/sec" and d["unit"] == "tokens/s"
+    # the default workload is the metric BASELINE.json names: the experiment_spanbert.yml GAN-step cycle (step 0 of the
+    # timed region carries one discriminator + one generator update on the CPU: 123 sampling steps + HF BERT 5x768)
+    assert d["impl"] == "reference" and d["metric"] == "train tokens/sec (GAN step)" and d["unit"] == "tokens/s"
+    assert "experiment_spanbert.yml" in d["config"]["workload"]
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
