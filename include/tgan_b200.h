@@ -96,6 +96,10 @@ int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t ld, int kle
  * so the forward value is unchanged.                                                                          */
 int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
                 const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one, void* stream);
+/* same with an explicit epsilon (BERT LayerNorm: 1e-12, modeling_bert.py BertLayerNorm) */
+int tgan_ln_fwd_eps(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
+                    const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one, float eps,
+                    void* stream);
 /* dz = LN'(dy) ; dz_drop (optional) = dropmask(seed, site)(dz) / (1-p) -- the gradient entering the dropout
  * that precedes the residual add; dgamma / dbeta (fp32 [D]) are accumulated (+=).  dsum (optional, fp32 [D],
  * accumulated): column sums of dz_drop (of dz when dz_drop is NULL) = the bias gradient of the Linear whose output
@@ -125,7 +129,8 @@ int tgan_relattn_fwd(int dtype, const void* q, int64_t ldq, const void* k, const
                      void* out, int64_t ldo, float* lse, int B, int N, int Q, int M, int msl, int same_length,
                      float scale, float drop_p, uint64_t seed, uint64_t site, int impl, void* stream);
 /* Backward.  dq [Q*B, ldq], dk, dv [K*B, lddkv] (dtype) and dr (fp32 [K, lddr]) are WRITTEN;
- * du, dvb (fp32 [N,64]) are ACCUMULATED (+=); delta is an fp32 [B,N,Q] scratch buffer (row-wise dout.out). */
+ * du, dvb (fp32 [N,64]) are ACCUMULATED (+=); delta is an fp32 scratch buffer of B*N*Q floats (row-wise dout.out) --
+ * B*N*(M+1) floats when Q == 1: the fused single-token backward (csrc/relattn_decode.cu) keeps its dS row there.  */
 int tgan_relattn_bwd(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                      const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
                      const void* out, const void* dout, int64_t ldo, const float* lse, float* delta,
@@ -183,6 +188,31 @@ int tgan_sumsq(const float* x, int64_t n, float* out /* 1 float, accumulated */,
 int tgan_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* gnorm_sq, float clip,
                    float grad_scale, void* stream);
+
+/* ---- BERT discriminator encoder (transformer_gan.py:391-445 -> HuggingFace transformers ==2.5.1 modeling_bert.py:
+ * BertEmbeddings / BertSelfAttention / BertIntermediate; calc_gradient_penalty :203-230) ------------------------
+ * Dense layers are tgan_gemm; these are the remaining pieces, each as value / input-gradient / forward tangent.
+ * tgan_gelu: mode 0: out = gelu(u) (erf form); mode 1: out = t * gelu'(u) (dgrad and JVP are the same map).       */
+int tgan_gelu(int dtype, int mode, const void* u, int64_t ldu, const void* t, int64_t ldt, void* out, int64_t ldo,
+              int rows, int cols, void* stream);
+/* z[row, :cols] = (x[row] if x else E[ids[row]]) + table[row % period]   (z fp32; table fp32 [period, cols] =
+ * position_embeddings[t] + token_type_embeddings[0]; BertEmbeddings.forward with inputs_embeds)                  */
+int tgan_bert_embed_rows(int dtype, const void* x, int64_t ldx, const int64_t* ids, const void* E, int64_t lde,
+                         const float* table, int period, float* z, int64_t ldz, int rows, int cols, void* stream);
+/* LayerNorm forward tangent: yd = gamma * rstd * (zd - mean(zd) - xhat * mean(zd * xhat)), xhat = (z - mean) * rstd */
+int tgan_ln_jvp(int dtype, const float* zd, int64_t ldzd, const float* z, int64_t ldz, const float* gamma,
+                const float* mean, const float* rstd, void* yd, int64_t ldy, int rows, int D, void* stream);
+/* BertSelfAttention on qkv rows [B*T, 3*heads*dh] = [Q | K | V] (head h at columns h*dh of each third), T <= 64,
+ * dh <= 64: ctx = drop(softmax(Q K^T / sqrt(dh))) V; lse fp32 [B*heads*T] is saved.  _bwd: dqkv from dctx.
+ * _jvp: ctx tangent from the qkv tangent.  The three share (seed, site): identical dropout masks.                 */
+int tgan_bert_attn_fwd(int dtype, const void* qkv, int64_t ldq, void* ctx, int64_t ldc, float* lse, int B, int heads,
+                       int T, int dh, float drop_p, uint64_t seed, uint64_t site, void* stream);
+int tgan_bert_attn_bwd(int dtype, const void* qkv, int64_t ldq, const void* dctx, int64_t ldc, const float* lse,
+                       void* dqkv, int64_t lddq, int B, int heads, int T, int dh, float drop_p, uint64_t seed,
+                       uint64_t site, void* stream);
+int tgan_bert_attn_jvp(int dtype, const void* qkv, int64_t ldq, const void* qkvd, int64_t ldqd, const float* lse,
+                       void* ctxd, int64_t ldc, int B, int heads, int T, int dh, float drop_p, uint64_t seed,
+                       uint64_t site, void* stream);
 
 #ifdef __cplusplus
 }

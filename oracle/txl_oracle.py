@@ -124,7 +124,7 @@ def attn_mask(qlen: int, mlen: int, mem_len: int, same_length: bool,
         m = m | (j <= i - msl)                                 # tril(ones, -mask_shift_len)   :520
     m = m[None].repeat(bsz, 1, 1)
     if reset_mems is not None and mlen > 0:
-        m[reset_mems.bool(), :, :mlen] = True                  #                               :529
+        m[reset_mems.bool().cpu(), :, :mlen] = True                  #                               :529
     return m
 
 
@@ -136,8 +136,8 @@ def rel_shift_gather(bd_raw: torch.Tensor, qlen: int) -> torch.Tensor:
     Entries with j+Q-1-i >= K (always masked: j > i+M) are set to 0 instead of the reference's wrap-around
     garbage."""
     klen = bd_raw.shape[-1]
-    i = torch.arange(qlen)[:, None]
-    j = torch.arange(klen)[None, :]
+    i = torch.arange(qlen, device=bd_raw.device)[:, None]
+    j = torch.arange(klen, device=bd_raw.device)[None, :]
     src = j + qlen - 1 - i
     valid = src < klen
     src = src.clamp(max=klen - 1)
@@ -215,8 +215,9 @@ def core_forward(inp: torch.Tensor, reset_mems: Optional[torch.Tensor], mems: Op
     Q, B = x.shape[0], x.shape[1]
     M = 0 if mems is None or mems.numel() == 0 else mems.shape[1]
     K = Q + M
-    mask = attn_mask(Q, M, shape.mem_len, shape.same_length, reset_mems, B)
-    pe = positional_embedding(K, shape.d_model, shape.clamp_len, dtype=x.dtype)
+    # .to(x.device): the eager-GPU bar of bench.py runs this restatement unchanged on CUDA tensors
+    mask = attn_mask(Q, M, shape.mem_len, shape.same_length, reset_mems, B).to(x.device)
+    pe = positional_embedding(K, shape.d_model, shape.clamp_len, dtype=x.dtype).to(x.device)
     hids = [x]
     for l in range(shape.n_layer):
         pre = f"layers.{l}."

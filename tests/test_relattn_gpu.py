@@ -92,7 +92,7 @@ def test_relattn_fwd_bwd(case, dtype, impl):
     dkv = torch.empty_like(kvd)
     dr = torch.empty(K, NH, device="cuda")
     du, dvb = torch.zeros(NH, device="cuda"), torch.zeros(NH, device="cuda")
-    delta = torch.empty(B * N * Q, device="cuda")
+    delta = torch.empty(B * N * max(Q, M + 1 if Q == 1 else Q), device="cuda")
     L.relattn_bwd(qd, kvd, kvd, 2 * NH, rdv, ud, vbd, rs, out, dod, lse, delta, dq, dkv, dkv, 2 * NH, dr, du, dvb,
                   B, N, Q, M, msl, same_length, scale, 0.0, 0, 0, impl=impl, v_off=NH, dv_off=NH)
     torch.cuda.synchronize()
@@ -133,7 +133,7 @@ def test_relattn_dropout_is_consistent_between_fwd_and_bwd():
     keep_frac = 0.7
     dq, dkv = torch.empty_like(q), torch.empty_like(kv)
     dr, du, dvb = torch.empty(K, NH, device="cuda"), torch.zeros(NH, device="cuda"), torch.zeros(NH, device="cuda")
-    delta = torch.empty(B * N * Q, device="cuda")
+    delta = torch.empty(B * N * max(Q, M + 1 if Q == 1 else Q), device="cuda")
     L.relattn_bwd(q, kv, kv, 2 * NH, r, u, vb, None, out, do, lse, delta, dq, dkv, dkv, 2 * NH, dr, du, dvb, B, N, Q, M,
                   Q, False, scale, 0.3, 42, 17, v_off=NH, dv_off=NH)
     eps = 1e-2
@@ -183,7 +183,7 @@ def test_relattn_tcgen05_matches_simt_with_dropout(case):
         dq, dkv = torch.empty_like(q), torch.full_like(kv, 7.0)
         dr = torch.full((K, NH), 7.0, device="cuda")
         du, dvb = torch.zeros(NH, device="cuda"), torch.zeros(NH, device="cuda")
-        delta = torch.empty(B * N * Q, device="cuda")
+        delta = torch.empty(B * N * max(Q, M + 1 if Q == 1 else Q), device="cuda")
         # both backward passes consume the SAME forward result so only the backward kernels differ
         o_in, l_in = (out, lse) if impl == 1 else (res[1][0], res[1][1])
         L.relattn_bwd(q, kv, kv, 2 * NH, r, u, vb, rs, o_in, do, l_in, delta, dq, dkv, dkv, 2 * NH, dr, du, dvb, B, N,

@@ -144,6 +144,8 @@ static inline int tgan_set_step_ctr_local(const void* dev_ptr) {
 int tgan_set_step_ctr_gemm_simt(const void*);
 int tgan_set_step_ctr_gemm_tc(const void*);
 int tgan_set_step_ctr_relattn_simt(const void*);
+int tgan_set_step_ctr_relattn_decode(const void*);
+int tgan_set_step_ctr_bert(const void*);
 int tgan_set_step_ctr_relattn_fwd_tc(const void*);
 int tgan_set_step_ctr_relattn_bwd_tc(const void*);
 
@@ -225,6 +227,17 @@ int tgan_relattn_bwd_simt(int dtype, const void* q, int64_t ldq, const void* k, 
                           void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
                           int N, int Q, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
                           uint64_t site, cudaStream_t st);
+// single-token (Q = 1) kernels (relattn_decode.cu); scratch = fp32 [B * N * (M + 1)]
+int tgan_relattn_fwd_decode1(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                             void* out, int64_t ldo, float* lse, int B, int N, int M, int msl, int same_length, float scale,
+                             float drop_p, uint64_t seed, uint64_t site, cudaStream_t st);
+int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                             const void* out, const void* dout, int64_t ldo, const float* lse, float* scratch, void* dq,
+                             void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
+                             int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
+                             uint64_t site, cudaStream_t st);
 // tcgen05 attention (bf16 only); return -1 when the shape is not eligible
 int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out, int64_t ldo,

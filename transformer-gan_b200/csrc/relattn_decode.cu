@@ -1,0 +1,326 @@
+// Relative-position attention for single-token calls (Q = 1): every Gumbel sampling step of the GAN phase
+// (transformer_gan.py:299-334 -> mem_transformer.py:602-651) and every generated token (generate.py -> :578-600).
+// Reference arithmetic: mem_transformer.py:201-244 with qlen = 1; the rel-shift (:133-147) degenerates to
+// BD[j] = (q + r_r_bias) . R[j], the mask (:495-547) to "all keys" (minus the memory columns of a reset row).
+//
+// The work per (sequence b, head n) is one query row against K <= mem_len + 1 key rows of 64 dims: ~K * 400 bytes
+// streamed, ~K * 400 FMAs.  It is HBM-bound on the projected-K/V cache, so the kernels are organised around the byte
+// stream, not the math:
+//   * one WARP per (b, n); lane = (key group kg = lane / 8, dim chunk dc = lane % 8).  A key row (64 dims, 128 bytes in
+//     bf16) is one 16-byte load per lane of an 8-lane group -> every global access is a full, coalesced 128-byte line
+//     and a warp covers 4 key rows per step; the 4 key groups run independent online softmaxes that are merged once.
+//   * q (+ biases) lives in 16 registers per lane; scores are reduced with three shuffles inside the 8-lane group.
+//   * forward: one pass over K, R, V.  Backward (fused, replaces the three generic passes rows / keys / rel that each
+//     recomputed the scores): one pass over K, R, V producing dq, dk, dv and dS; dR (a reduction over the BATCH) is a
+//     second tiny kernel over the dS scratch instead of B*N*K*64 global atomics.
+// Dropout masks come from the same stateless hash as every other attention kernel (common.cuh: attn_drop_keep).
+#include "common.cuh"
+
+namespace {
+constexpr int HS = TGAN_HS;  // 64
+constexpr int DW = 4;        // warps per CTA (each an independent (b, n))
+
+struct DecArgs {
+    int B, N, M, K;          // Q == 1
+    int jlo0;                // first key a same_length window keeps (0 otherwise)
+    float scale, scale_log2, drop_scale;
+    uint32_t thresh, key;
+};
+
+// Sum over the 8 lanes of one key group.  `gmask` names exactly those 8 lanes: the key loop's trip count differs
+// between the groups of a warp (K is not a multiple of 4), so a full-warp mask inside the loop would wait for lanes that
+// have already left it.
+__device__ __forceinline__ float group8_sum(float v, uint32_t gmask) {
+    v += __shfl_xor_sync(gmask, v, 1);
+    v += __shfl_xor_sync(gmask, v, 2);
+    v += __shfl_xor_sync(gmask, v, 4);
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DW * 32)
+relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
+                const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
+                const uint8_t* __restrict__ reset, T* __restrict__ out, int64_t ldo, float* __restrict__ lse, DecArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bn = blockIdx.x * DW + warp;
+    if (bn >= a.B * a.N) return;
+    const int b = bn / a.N, n = bn % a.N;
+    const int kg = lane >> 3, dc = lane & 7;
+    const uint32_t gmask = 0xffu << (8 * kg);
+    const int col = n * HS + 8 * dc;
+    float qu[8], qv[8];
+    {
+        float x[8], uu[8], vv[8];
+        load8(q + (int64_t)b * ldq + col, x);
+        load8(u + col, uu);
+        load8(vb + col, vv);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { qu[t] = x[t] + uu[t]; qv[t] = x[t] + vv[t]; }
+    }
+    const int jlo = (reset && reset[b]) ? max(a.M, a.jlo0) : a.jlo0, jhi = a.K - 1;
+    const uint32_t rowkey = attn_drop_rowkey(step_fold(a.key), (uint32_t)bn);
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    const T* kbase = k + (int64_t)b * ldkv + col;
+    const T* vbase = v + (int64_t)b * ldkv + col;
+    const int64_t kstride = (int64_t)a.B * ldkv;
+#pragma unroll 2
+    for (int j = jlo + kg; j <= jhi; j += 4) {
+        float k8[8], r8[8], v8[8];
+        load8(kbase + j * kstride, k8);
+        load8(r + (int64_t)j * ldr + col, r8);
+        load8(vbase + j * kstride, v8);
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s = fmaf(qu[t], k8[t], fmaf(qv[t], r8[t], s));
+        s = group8_sum(s, gmask) * a.scale_log2;
+        const float mn = fmaxf(m, s);
+        const float corr = fast_exp2(m - mn);  // m = -inf on the first key: exp2(-inf) = 0
+        const float pe = fast_exp2(s - mn);
+        l = fmaf(l, corr, pe);
+        const float pw = (!a.thresh || attn_drop_keep(rowkey, j, a.thresh)) ? pe : 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = fmaf(pw, v8[t], acc[t] * corr);
+        m = mn;
+    }
+    __syncwarp();  // the groups leave the loop at different trip counts: reconverge before full-warp shuffles
+    // merge the 4 key groups (lanes with equal dc): max, then rescaled sums
+    float m_all = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, 16));
+    const float f = (m == -INFINITY) ? 0.f : fast_exp2(m - m_all);
+    l *= f;
+    l += __shfl_xor_sync(0xffffffffu, l, 8);
+    l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        float x = acc[t] * f;
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        acc[t] = x;
+    }
+    if (kg == 0) {
+        const float inv = l > 0.f ? a.drop_scale / l : 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] *= inv;
+        store8(out + (int64_t)b * ldo + col, acc);
+        if (dc == 0) lse[bn] = l > 0.f ? (m_all + log2f(l)) * 0.6931471805599453f : -INFINITY;
+    }
+}
+
+// Fused backward for Q = 1.  dsbuf: fp32 [B*N, K] scratch (dS already multiplied by scale), consumed by relattn_dec_dr.
+template <typename T>
+__global__ void __launch_bounds__(DW * 32, 5)
+relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
+                const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
+                const uint8_t* __restrict__ reset, const T* __restrict__ out, const T* __restrict__ dout, int64_t ldo,
+                const float* __restrict__ lse, T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv,
+                float* __restrict__ dsbuf, float* __restrict__ du, float* __restrict__ dvb, DecArgs a) {
+    __shared__ float s_du[DW][HS], s_dvb[DW][HS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bn = blockIdx.x * DW + warp;
+    const bool active = bn < a.B * a.N;
+    const int b = active ? bn / a.N : 0, n = active ? bn % a.N : 0;
+    const int kg = lane >> 3, dc = lane & 7;
+    const uint32_t gmask = 0xffu << (8 * kg);
+    const int col = n * HS + 8 * dc;
+    float dqk[8], dqr[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { dqk[t] = 0.f; dqr[t] = 0.f; }
+    if (active) {
+        float qu[8], qv[8], g8[8];
+        float delta;
+        {
+            float x[8], uu[8], vv[8], o8[8];
+            load8(q + (int64_t)b * ldq + col, x);
+            load8(u + col, uu);
+            load8(vb + col, vv);
+            load8(out + (int64_t)b * ldo + col, o8);
+            load8(dout + (int64_t)b * ldo + col, g8);
+            float d = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { qu[t] = x[t] + uu[t]; qv[t] = x[t] + vv[t]; d = fmaf(g8[t], o8[t], d); }
+            delta = group8_sum(d, gmask);
+        }
+        const float L2 = lse[bn] * 1.4426950408889634f;
+        const int jlo = (reset && reset[b]) ? max(a.M, a.jlo0) : a.jlo0, jhi = a.K - 1;
+        const uint32_t rowkey = attn_drop_rowkey(step_fold(a.key), (uint32_t)bn);
+        const T* kbase = k + (int64_t)b * ldkv + col;
+        const T* vbase = v + (int64_t)b * ldkv + col;
+        T* dkbase = dk + (int64_t)b * lddkv + col;
+        T* dvbase = dv + (int64_t)b * lddkv + col;
+        const int64_t kstride = (int64_t)a.B * ldkv, dstride = (int64_t)a.B * lddkv;
+        float* dsrow = dsbuf + (int64_t)bn * a.K;
+        // keys a reset row does not attend to: zero gradients
+        for (int j = kg; j < jlo; j += 4) {
+            float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            store8(dkbase + j * dstride, z);
+            store8(dvbase + j * dstride, z);
+            if (dc == 0) dsrow[j] = 0.f;
+        }
+#pragma unroll 2
+        for (int j = jlo + kg; j <= jhi; j += 4) {
+            float k8[8], r8[8], v8[8];
+            load8(kbase + j * kstride, k8);
+            load8(r + (int64_t)j * ldr + col, r8);
+            load8(vbase + j * kstride, v8);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                s = fmaf(qu[t], k8[t], fmaf(qv[t], r8[t], s));
+                dp = fmaf(g8[t], v8[t], dp);
+            }
+            s = group8_sum(s, gmask);
+            dp = group8_sum(dp, gmask);
+            const float pr = fast_exp2(fmaf(s, a.scale_log2, -L2));
+            const bool keep = !a.thresh || attn_drop_keep(rowkey, j, a.thresh);
+            const float pw = keep ? pr * a.drop_scale : 0.f;
+            const float ds = pr * ((keep ? dp * a.drop_scale : 0.f) - delta) * a.scale;
+            float dk8[8], dv8[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                dk8[t] = ds * qu[t];
+                dv8[t] = pw * g8[t];
+                dqk[t] = fmaf(ds, k8[t], dqk[t]);
+                dqr[t] = fmaf(ds, r8[t], dqr[t]);
+            }
+            store8(dkbase + j * dstride, dk8);
+            store8(dvbase + j * dstride, dv8);
+            if (dc == 0) dsrow[j] = ds;
+        }
+        __syncwarp();  // reconverge the key groups before the full-warp shuffles
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            float x = dqk[t], y = dqr[t];
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            y += __shfl_xor_sync(0xffffffffu, y, 8);
+            y += __shfl_xor_sync(0xffffffffu, y, 16);
+            dqk[t] = x; dqr[t] = y;
+        }
+        if (kg == 0) {
+            float s8[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) s8[t] = dqk[t] + dqr[t];
+            store8(dq + (int64_t)b * ldq + col, s8);
+        }
+    }
+    // du = column sums of the content part of dq, dvb of the position part (r_w_bias / r_r_bias are shared by all rows):
+    // warps of one CTA that serve the same head are combined in shared memory first
+    if (kg == 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { s_du[warp][8 * dc + t] = dqk[t]; s_dvb[warp][8 * dc + t] = dqr[t]; }
+    }
+    __syncthreads();
+    if (active && kg == 0) {
+        bool first = true;  // the lowest warp of each head in this CTA adds that head's partial sums
+        for (int w = 0; w < warp; ++w) {
+            const int obn = blockIdx.x * DW + w;
+            if (obn < a.B * a.N && obn % a.N == n) first = false;
+        }
+        if (first) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float su = 0.f, sv = 0.f;
+                for (int w = warp; w < DW; ++w) {
+                    const int obn = blockIdx.x * DW + w;
+                    if (obn < a.B * a.N && obn % a.N == n) { su += s_du[w][8 * dc + t]; sv += s_dvb[w][8 * dc + t]; }
+                }
+                atomicAdd(&du[col + t], su);
+                atomicAdd(&dvb[col + t], sv);
+            }
+        }
+    }
+}
+
+// dR[j, n, :] = sum_b dS[b, n, j] * (q[b, n, :] + r_r_bias[n, :])      (dS carries the 1/sqrt(d_head) factor)
+// grid (ceil(K / 8), N), 128 threads: thread = (key j0 + t / 16, dims 4 * (t % 16) .. +3); the batch loop is unrolled so
+// that 8 independent (dS, q) loads are in flight per thread.
+constexpr int DR_KEYS = 8;
+template <typename T>
+__global__ void __launch_bounds__(DR_KEYS * 16)
+relattn_dec_dr(const T* __restrict__ q, int64_t ldq, const float* __restrict__ vb, const float* __restrict__ dsbuf,
+               float* __restrict__ dr, int64_t lddr, DecArgs a) {
+    const int n = blockIdx.y;
+    const int j = blockIdx.x * DR_KEYS + (threadIdx.x >> 4);
+    const int d = 4 * (threadIdx.x & 15);
+    if (j >= a.K) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, sum = 0.f;
+    const T* qp = q + n * HS + d;
+    const float* dp = dsbuf + (int64_t)n * a.K + j;
+    const int64_t dstep = (int64_t)a.N * a.K;
+#pragma unroll 8
+    for (int b = 0; b < a.B; ++b) {
+        const float ds = dp[b * dstep];
+        const T* qr = qp + (int64_t)b * ldq;
+        float x0 = to_f(qr[0]), x1 = to_f(qr[1]), x2 = to_f(qr[2]), x3 = to_f(qr[3]);
+        acc[0] = fmaf(ds, x0, acc[0]); acc[1] = fmaf(ds, x1, acc[1]);
+        acc[2] = fmaf(ds, x2, acc[2]); acc[3] = fmaf(ds, x3, acc[3]);
+        sum += ds;
+    }
+    float* o = dr + (int64_t)j * lddr + n * HS + d;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = fmaf(sum, vb[n * HS + d + t], acc[t]);
+}
+
+DecArgs make_dec(int B, int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed, uint64_t site) {
+    DecArgs a;
+    a.B = B; a.N = N; a.M = M; a.K = M + 1;
+    a.jlo0 = same_length ? (1 - msl > 0 ? 1 - msl : 0) : 0;  // mem_transformer.py:496-503 at qlen = 1: keys j <= -msl are cut a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+    a.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    a.thresh = drop_p > 0.f ? dropout_thresh16(drop_p) : 0u;
+    a.key = dropout_key(seed, site);
+    return a;
+}
+}  // namespace
+
+int tgan_set_step_ctr_relattn_decode(const void* p) { return tgan_set_step_ctr_local(p); }
+
+// Eligibility: Q == 1, rows aligned for 16-byte (bf16) / 32-byte (fp32) vector access.
+int tgan_relattn_fwd_decode1(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                             void* out, int64_t ldo, float* lse, int B, int N, int M, int msl, int same_length, float scale,
+                             float drop_p, uint64_t seed, uint64_t site, cudaStream_t st) {
+    DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
+    const int grid = ceil_div((int64_t)B * N, DW);
+    if (dtype == TGAN_F32)
+        relattn_dec_fwd<float><<<grid, DW * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
+                                                          (const float*)r, ldr, u, vb, reset, (float*)out, ldo, lse, a);
+    else
+        relattn_dec_fwd<bf16><<<grid, DW * 32, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
+                                                         (const bf16*)r, ldr, u, vb, reset, (bf16*)out, ldo, lse, a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                             const void* out, const void* dout, int64_t ldo, const float* lse, float* scratch, void* dq,
+                             void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
+                             int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
+                             uint64_t site, cudaStream_t st) {
+    DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
+    const int grid = ceil_div((int64_t)B * N, DW);
+    if (dtype == TGAN_F32)
+        relattn_dec_bwd<float><<<grid, DW * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
+                                                          (const float*)r, ldr, u, vb, reset, (const float*)out,
+                                                          (const float*)dout, ldo, lse, (float*)dq, (float*)dk,
+                                                          (float*)dv, lddkv, scratch, du, dvb, a);
+    else
+        relattn_dec_bwd<bf16><<<grid, DW * 32, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
+                                                         (const bf16*)r, ldr, u, vb, reset, (const bf16*)out,
+                                                         (const bf16*)dout, ldo, lse, (bf16*)dq, (bf16*)dk, (bf16*)dv,
+                                                         lddkv, scratch, du, dvb, a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    dim3 g2(ceil_div(a.K, DR_KEYS), N);
+    if (dtype == TGAN_F32)
+        relattn_dec_dr<float><<<g2, DR_KEYS * 16, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
+    else
+        relattn_dec_dr<bf16><<<g2, DR_KEYS * 16, 0, st>>>((const bf16*)q, ldq, vb, scratch, dr, lddr, a);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}

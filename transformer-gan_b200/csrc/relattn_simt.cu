@@ -538,6 +538,10 @@ int tgan_relattn_fwd_simt(int dtype, const void* q, int64_t ldq, const void* k, 
                           float drop_p, uint64_t seed, uint64_t site, cudaStream_t st) {
     AttnArgs a = make_args(B, N, Q, M, msl, same_length, scale, drop_p, seed, site);
     const bool vec_ok = ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)r) & 31) == 0) && ldkv % 8 == 0 && ldr % 8 == 0;
+    if (Q == 1 && vec_ok && ((((uintptr_t)q | (uintptr_t)out | (uintptr_t)u | (uintptr_t)vb) & 31) == 0) && ldq % 8 == 0 &&
+        ldo % 8 == 0)
+        return tgan_relattn_fwd_decode1(dtype, q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, ldo, lse, B, N, M, msl,
+                                        same_length, scale, drop_p, seed, site, st);
     if (Q <= DECODE_Q && vec_ok) {
         dim3 gd(Q, B * N);
         if (dtype == TGAN_F32)
@@ -608,6 +612,14 @@ int tgan_relattn_bwd_simt(int dtype, const void* q, int64_t ldq, const void* k, 
                           void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
                           int N, int Q, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
                           uint64_t site, cudaStream_t st) {
+    const uintptr_t al = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)out | (uintptr_t)dout |
+                         (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)u | (uintptr_t)vb;
+    if (Q == 1 && (al & 31) == 0 && ldq % 8 == 0 && ldkv % 8 == 0 && ldr % 8 == 0 && ldo % 8 == 0 && lddkv % 8 == 0 &&
+        lddr % 4 == 0)
+        // `delta` doubles as the dS scratch of the fused single-token backward: B * N * (M + 1) floats (tgan_b200.h)
+        return tgan_relattn_bwd_decode1(dtype, q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq,
+                                        dk, dv, lddkv, dr, lddr, du, dvb, B, N, M, msl, same_length, scale, drop_p, seed,
+                                        site, st);
     AttnArgs a = make_args(B, N, Q, M, msl, same_length, scale, drop_p, seed, site);
     if (dtype == TGAN_F32)
         return bwd_launch<float>(q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq, dk, dv,

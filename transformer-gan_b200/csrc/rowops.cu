@@ -25,6 +25,7 @@ extern "C" unsigned long long tgan_launch_count(void) { return g_tgan_launches; 
 extern "C" int tgan_set_step_counter(const void* dev_u32) {
     int rc = tgan_set_step_ctr_local(dev_u32);
     rc |= tgan_set_step_ctr_gemm_simt(dev_u32) | tgan_set_step_ctr_gemm_tc(dev_u32) | tgan_set_step_ctr_relattn_simt(dev_u32) |
+          tgan_set_step_ctr_relattn_decode(dev_u32) | tgan_set_step_ctr_bert(dev_u32) |
           tgan_set_step_ctr_relattn_fwd_tc(dev_u32) | tgan_set_step_ctr_relattn_bwd_tc(dev_u32);
     if (rc) { tgan_set_error("tgan_set_step_counter: cudaMemcpyToSymbol failed"); return 2; }
     return 0;
@@ -147,7 +148,8 @@ __device__ __forceinline__ void store4(bf16* p, const float* v) {
 template <typename T, int MAXU>
 __global__ void ln_fwd_kernel(const float* __restrict__ z, int64_t ldz, T* __restrict__ y, int64_t ldy,
                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, int DP, int pad_one) {
+                              float* __restrict__ mean, float* __restrict__ rstd, int rows, int D, int DP, int pad_one,
+                              float eps) {
     int row = blockIdx.x * WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* zr = z + (int64_t)row * ldz;
@@ -173,7 +175,7 @@ __global__ void ln_fwd_kernel(const float* __restrict__ z, int64_t ldz, T* __res
 #pragma unroll
         for (int t = 0; t < 4; ++t) { const float d = c + t < D ? v[u][t] - mu : 0.f; q += d * d; }
     }
-    const float rs = rsqrtf(warp_sum(q) / D + 1e-5f);
+    const float rs = rsqrtf(warp_sum(q) / D + eps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
     T* yr = y + (int64_t)row * ldy;
 #pragma unroll
@@ -636,9 +638,9 @@ extern "C" int tgan_pos_emb(int dtype, const float* inv_freq, void* pe, int64_t 
     return 0;
 }
 
-extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
-                           const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one,
-                           void* stream) {
+extern "C" int tgan_ln_fwd_eps(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
+                               const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one,
+                               float eps, void* stream) {
     if (rows <= 0) return 0;
     TGAN_CHECK_ARG(DP % 8 == 0 && ldz % 4 == 0 && ldy % 8 == 0 && D <= DP, "tgan_ln_fwd: alignment");
     TGAN_CHECK_ARG(!pad_one || D < DP, "tgan_ln_fwd: pad_one needs a pad lane (D < DP)");
@@ -646,14 +648,20 @@ extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int6
                    "tgan_ln_fwd: DP <= 1024, 16-byte aligned z / gamma / beta");
     if (DP <= 512) {
         DISPATCH_T(dtype, (ln_fwd_kernel<T, 4><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
-                                                                                          mean, rstd, rows, D, DP, pad_one)));
+                                                                                          mean, rstd, rows, D, DP, pad_one, eps)));
     } else {
         DISPATCH_T(dtype, (ln_fwd_kernel<T, 8><<<ceil_div(rows, WPB), WPB * 32, 0, ST>>>(z, ldz, (T*)y, ldy, gamma, beta,
-                                                                                          mean, rstd, rows, D, DP, pad_one)));
+                                                                                          mean, rstd, rows, D, DP, pad_one, eps)));
     }
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int tgan_ln_fwd(int dtype, const float* z, int64_t ldz, void* y, int64_t ldy, const float* gamma,
+                           const float* beta, float* mean, float* rstd, int rows, int D, int DP, int pad_one,
+                           void* stream) {
+    return tgan_ln_fwd_eps(dtype, z, ldz, y, ldy, gamma, beta, mean, rstd, rows, D, DP, pad_one, 1e-5f, stream);
 }
 
 extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float* z, int64_t ldz, const float* gamma,

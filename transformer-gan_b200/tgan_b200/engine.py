@@ -704,7 +704,7 @@ class TxlEngine:
             dq = self._buf(R, NH)
             dkv = self._buf(KR, 2 * NH)
             dr32 = dr_all32[:, l * NH:(l + 1) * NH]  # view: this layer's column block
-            delta = self._buf(B * d.n_head * Q, dtype=torch.float32)
+            delta = self._buf(B * d.n_head * (Q if Q > 1 else K), dtype=torch.float32)  # Q == 1: dS scratch [B*N, K]
             L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
                           sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
                           ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,

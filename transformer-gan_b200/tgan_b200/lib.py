@@ -59,6 +59,13 @@ _SIGS = {
     "tgan_sumsq": [P, L, P, P],
     "tgan_adam_step": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P],
     "tgan_set_step_counter": [P],
+    "tgan_ln_fwd_eps": [I, P, L, P, L, P, P, P, P, I, I, I, I, F, P],
+    "tgan_gelu": [I, I, P, L, P, L, P, L, I, I, P],
+    "tgan_bert_embed_rows": [I, P, L, P, P, L, P, I, P, L, I, I, P],
+    "tgan_ln_jvp": [I, P, L, P, L, P, P, P, P, L, I, I, P],
+    "tgan_bert_attn_fwd": [I, P, L, P, L, P, I, I, I, I, F, U, U, P],
+    "tgan_bert_attn_bwd": [I, P, L, P, L, P, P, L, I, I, I, I, F, U, U, P],
+    "tgan_bert_attn_jvp": [I, P, L, P, L, P, P, L, I, I, I, I, F, U, U, P],
 }
 EXPORTS = ["tgan_last_error", "tgan_version", "tgan_has_tcgen05", "tgan_launch_count"] + list(_SIGS)
 for _name, _sig in _SIGS.items():
@@ -174,6 +181,45 @@ def pos_emb(inv_freq, pe, klen, D, DP, clamp_len, drop_p, seed, site):
 def ln_fwd(z, y, gamma, beta, mean, rstd, rows, D, DP, y_off=0, pad_one=False):
     _call("tgan_ln_fwd", dtype_code(y.dtype), z.data_ptr(), z.stride(0), y.data_ptr() + y_off * y.element_size(),
           DP, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), rows, D, DP, int(pad_one), _stream())
+
+
+def ln_fwd_eps(z, y, gamma, beta, mean, rstd, rows, D, eps):
+    """LayerNorm with an explicit epsilon over all D columns (BERT: 1e-12); z fp32 [rows, D] -> y"""
+    _call("tgan_ln_fwd_eps", dtype_code(y.dtype), z.data_ptr(), z.stride(0), y.data_ptr(), y.stride(0), _ptr(gamma),
+          _ptr(beta), _ptr(mean), _ptr(rstd), rows, D, D, 0, eps, _stream())
+
+
+def gelu(u, out, rows, cols, t=None):
+    """t is None: out = gelu(u) (erf form);  else out = t * gelu'(u)  (input gradient and forward tangent alike)"""
+    _call("tgan_gelu", dtype_code(u.dtype), 0 if t is None else 1, u.data_ptr(), u.stride(0), _ptr(t),
+          0 if t is None else t.stride(0), out.data_ptr(), out.stride(0), rows, cols, _stream())
+
+
+def bert_embed_rows(z, rows, cols, table, period, x=None, ids=None, E=None):
+    """z[row] = (x[row] | E[ids[row]]) + table[row % period]   (z fp32)"""
+    src = x if x is not None else E
+    _call("tgan_bert_embed_rows", dtype_code(src.dtype), _ptr(x), 0 if x is None else x.stride(0), _ptr(ids), _ptr(E),
+          0 if E is None else E.stride(0), _ptr(table), period, z.data_ptr(), z.stride(0), rows, cols, _stream())
+
+
+def ln_jvp(zd, z, gamma, mean, rstd, yd, rows, D):
+    _call("tgan_ln_jvp", dtype_code(yd.dtype), zd.data_ptr(), zd.stride(0), z.data_ptr(), z.stride(0), _ptr(gamma),
+          _ptr(mean), _ptr(rstd), yd.data_ptr(), yd.stride(0), rows, D, _stream())
+
+
+def bert_attn_fwd(qkv, ctx, lse, B, heads, T, dh, drop_p, seed, site):
+    _call("tgan_bert_attn_fwd", dtype_code(qkv.dtype), qkv.data_ptr(), qkv.stride(0), ctx.data_ptr(), ctx.stride(0),
+          lse.data_ptr(), B, heads, T, dh, drop_p, seed, site, _stream())
+
+
+def bert_attn_bwd(qkv, dctx, lse, dqkv, B, heads, T, dh, drop_p, seed, site):
+    _call("tgan_bert_attn_bwd", dtype_code(qkv.dtype), qkv.data_ptr(), qkv.stride(0), dctx.data_ptr(), dctx.stride(0),
+          lse.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), B, heads, T, dh, drop_p, seed, site, _stream())
+
+
+def bert_attn_jvp(qkv, qkvd, lse, ctxd, B, heads, T, dh, drop_p, seed, site):
+    _call("tgan_bert_attn_jvp", dtype_code(qkv.dtype), qkv.data_ptr(), qkv.stride(0), qkvd.data_ptr(), qkvd.stride(0),
+          lse.data_ptr(), ctxd.data_ptr(), ctxd.stride(0), B, heads, T, dh, drop_p, seed, site, _stream())
 
 
 def ln_bwd(dy, z, gamma, mean, rstd, dz, dz_drop, dgamma, dbeta, rows, D, DP, drop_p, seed, site, dy_off=0, dsum=None):

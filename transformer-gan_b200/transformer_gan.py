@@ -11,9 +11,14 @@ What runs where
     (``MemTransformerLM.forward_generate_gumbel`` -> tgan_* kernels, fused Gumbel-softmax straight-through sampler with
     device-side noise); the soft one-hot chain that carries the gradient through time (:308-320) is the engine's
     soft-input path (``tgan_gemm`` embedding + ``__dinput__`` gradient).
-  * discriminator: HuggingFace ``BertForSequenceClassification`` (third-party in the reference as well,
-    transformer_gan.py:23-30 / requirements.sh:12) with eager attention so the WGAN-GP double backward
-    (:203-230) works, or the CNN ``RelGAN_D`` (discriminator.py) -- library GEMM / conv work.
+  * discriminator (BERT): with the SHIPPED trainable set (embeddings + every encoder layer frozen, pooler +
+    classifier train; experiment_spanbert.yml ``freeze_layers``) the 5 x 768 encoder runs on the repo's own kernels
+    (``tgan_b200.bert.BertEncoderEngine``: tcgen05 GEMMs, own LayerNorm / GELU / attention kernels) in three passes --
+    value, input gradient, forward tangent -- and the WGAN-GP term (:203-230) is computed WITHOUT a double-backward
+    graph: d/dtheta ||grad_x D|| only involves the encoder through one Jacobian-vector product.  Only the 592 k-parameter
+    head stays in torch.  Any other trainable set falls back to HuggingFace ``BertForSequenceClassification``
+    (third-party in the reference as well, transformer_gan.py:23-30 / requirements.sh:12) with eager attention so that
+    autograd's double backward works.  The CNN ``RelGAN_D`` (discriminator.py) is library conv / GEMM work.
 Differences from the reference, all numerically neutral:
   * in ``"dis_loss"`` mode the sampling loop runs under ``no_grad`` (the reference builds the 123-step graph and then
     detaches it, :346-347);
@@ -66,6 +71,8 @@ class TransformerGAN(nn.Module):
         self.use_cuda_graphs = False
         self._gan_graphs, self._gan_warm = {}, set()
         self.disc_tf32 = True  # TF32 tensor-core GEMMs for the discriminator when the generator computes in bf16
+        self.use_own_bert = True   # frozen-encoder BERT discriminator on the repo's kernels (else: HuggingFace modules)
+        self._bert_engine = None
 
     # ------------------------------------------------------------------------------------------------ discriminator
     def create_bert_model(self, model_name_or_path, loss_type, model_type=None, random_weights=False):
@@ -76,7 +83,14 @@ class TransformerGAN(nn.Module):
             model = BertForSequenceClassification(config=config)
             if not random_weights:
                 lm = BertForMaskedLM.from_pretrained(model_name_or_path, config=config, cache_dir=None)
-                model.bert = lm.bert
+                # transformer_gan.py:549-553 does `model.bert = lm.bert`.  With transformers 2.5.1 (the reference's pin)
+                # BertForMaskedLM's BertModel carries a pooler; current releases build it with add_pooling_layer=False,
+                # so the wholesale assignment would drop the pooler the classification head needs: take the pretrained
+                # embeddings + encoder (+ the pooler when the checkpoint model has one) and keep the rest.
+                model.bert.embeddings = lm.bert.embeddings
+                model.bert.encoder = lm.bert.encoder
+                if getattr(lm.bert, "pooler", None) is not None:
+                    model.bert.pooler = lm.bert.pooler
         else:
             if random_weights:
                 raise NotImplementedError
@@ -111,6 +125,69 @@ class TransformerGAN(nn.Module):
         h = bert.encoder(h, attention_mask=None)
         h = h[0] if isinstance(h, (tuple, list)) else h.last_hidden_state
         return m.classifier(m.dropout(bert.pooler(h)))[:, 0]
+
+    # ------------------------------------------------------------------------------------------------ own BERT path
+    def _own_bert(self):
+        """The kernel-side encoder when it applies: BERT discriminator on CUDA, sizes the kernels cover, and nothing
+        inside embeddings / encoder trainable (the shipped configuration).  None -> HuggingFace path."""
+        if not self.use_own_bert or self.cfg.DISCRIMINATOR.type != "bert":
+            return None
+        m = self.discriminator
+        from tgan_b200.bert import BertEncoderEngine
+        if BertEncoderEngine.supported(m) is not None:
+            return None
+        dev = m.classifier.weight.device
+        if dev.type != "cuda":
+            return None
+        dt = getattr(self.generator, "compute_dtype", torch.bfloat16)
+        eng = self._bert_engine
+        if eng is None or eng.device != dev or eng.dtype != dt or eng.model is not m:
+            eng = self._bert_engine = BertEncoderEngine(m, dt, seed=torch.initial_seed())
+        return eng if eng.frozen() else None
+
+    def _bert_head(self, h0):
+        """pooler (dense + tanh on token 0) -> dropout -> classifier, logit column 0 (modeling_bert.py BertPooler /
+        BertForSequenceClassification.forward).  The trainable part: stays in torch."""
+        m = self.discriminator
+        pooled = m.bert.pooler.activation(m.bert.pooler.dense(h0))
+        return m.classifier(m.dropout(pooled))[:, 0]
+
+    def _own_logit(self, eng, *, ids=None, soft=None):
+        """D(real ids [B, T]) or D(fake rows [B, T, V+1]) with the encoder on the kernels."""
+        from tgan_b200 import bert as TB
+        training = self.discriminator.training
+        if ids is not None:
+            B, T = ids.shape
+            return self._bert_head(eng.forward(B, T, ids=ids, training=training, save=False).h0)
+        B, T, _ = soft.shape
+        if not (soft.requires_grad and torch.is_grad_enabled()):
+            x = eng.embed_onehot(soft)
+            return self._bert_head(eng.forward(B, T, x=x, training=training, save=False).h0)
+        x = TB._EmbedOneHotFn.apply(eng, soft)
+        return self._bert_head(TB.encode(eng, x, B, T, training))
+
+    def _own_gradient_penalty(self, eng, real_1h, fake_bt, LAMBDA=10):
+        """WGAN-GP (transformer_gan.py:203-230) with a frozen encoder.  With x = x^ E (the embedded interpolate the
+        reference differentiates with respect to, :211-216), h0 = Enc(x)[:, 0], D = head_theta(h0):
+            g = grad_x D = J^T a,   a = d head / d h0  (a function of theta),   J = d h0 / d x (no theta inside)
+            gp = 10 mean_b (||g_b|| - 1)^2
+        d gp / d theta flows only through a: _VjpFn's backward hands autograd J w (one forward-tangent pass of the
+        encoder) and torch differentiates a(theta) on [B, hidden] tensors.  No double-backward graph of the encoder."""
+        from tgan_b200 import bert as TB
+        B, T, _ = fake_bt.shape
+        if self.gp_alpha_source is not None:
+            alpha = self.gp_alpha_source(B).to(device=fake_bt.device, dtype=fake_bt.dtype).view(B, 1, 1)
+        else:
+            alpha = torch.rand([B, 1, 1], device=fake_bt.device, dtype=fake_bt.dtype)
+        xhat = (alpha * real_1h + (1 - alpha) * fake_bt).detach()
+        c = eng.forward(B, T, x=eng.embed_onehot(xhat), training=self.discriminator.training, save=True)
+        h0 = c.h0.detach().requires_grad_(True)
+        with torch.enable_grad():
+            d = self._bert_head(h0)
+            (a,) = torch.autograd.grad(d, h0, grad_outputs=torch.ones_like(d), create_graph=True)
+            g = TB._VjpFn.apply(eng, c, a)
+            slopes = torch.sqrt(g.reshape(B, -1).pow(2).sum(1) + 1e-12)
+            return ((slopes - 1.0) ** 2).mean() * LAMBDA
 
     def calc_gradient_penalty(self, real_data, fake_data, LAMBDA=10):
         """WGAN-GP on interpolated one-hot rows (transformer_gan.py:203-230).  real / fake: [B, T, V'] float."""
@@ -291,9 +368,14 @@ class TransformerGAN(nn.Module):
                 if dcfg.type == "bert":
                     # BERT's vocabulary has one extra (MASK) id: pad the sampled rows with a zero column (:396-399)
                     fake_bt = torch.cat([fake_bt, fake_bt.new_zeros(*fake_bt.shape[:-1], 1)], -1)
-                    E = self._bert_embedding_matrix()
-                    d_real = self._bert_logit(E[real])
-                    d_fake = self._bert_logit(torch.einsum("ve,bcv->bce", E, fake_bt))
+                    own = self._own_bert()
+                    if own is not None:
+                        d_real = self._own_logit(own, ids=real)
+                        d_fake = self._own_logit(own, soft=fake_bt)
+                    else:
+                        E = self._bert_embedding_matrix()
+                        d_real = self._bert_logit(E[real])
+                        d_fake = self._bert_logit(torch.einsum("ve,bcv->bce", E, fake_bt))
                     real_1h = None
                     if use_gp:
                         real_1h = torch.zeros(*real.shape, self.ntokens + 1, device=real.device).scatter_(-1, real[..., None], 1.0)
@@ -302,7 +384,10 @@ class TransformerGAN(nn.Module):
                     d_real = self.discriminator(real_1h)
                     d_fake = self.discriminator(fake_bt)
                 g_loss, d_loss = get_losses(d_real, d_fake, dtype_cfg.loss_type)
-                gp = self.calc_gradient_penalty(real_1h, fake_bt) if use_gp else None
+                if use_gp and dcfg.type == "bert" and self._own_bert() is not None:
+                    gp = self._own_gradient_penalty(self._own_bert(), real_1h, fake_bt)
+                else:
+                    gp = self.calc_gradient_penalty(real_1h, fake_bt) if use_gp else None
                 keep = (lambda t: t.detach()) if dcfg.backprop_outside else (lambda t: t)
                 g_total = g_total + keep(g_loss)
                 d_total = d_total + keep(d_loss)
