@@ -214,6 +214,16 @@ int tgan_bert_attn_jvp(int dtype, const void* qkv, int64_t ldq, const void* qkvd
                        void* ctxd, int64_t ldc, int B, int heads, int T, int dh, float drop_p, uint64_t seed,
                        uint64_t site, void* stream);
 
+/* ---- batched generation post-processing: generate.py:228-304 for every sequence in one launch ----
+ * logits fp32 [rows, ldl] -> ids int64 [rows].  exclude_bos drops token 0; suppress_empty[row] != 0 drops `empty_token`;
+ * temperature 0 = argmax; mode 0 "random", 1 "topk" (keep the topk most probable, renormalise), 2 "nucleus" (keep the
+ * sorted prefix whose exclusive cumulative probability is < top_p).  The categorical draw is the inverse CDF of
+ * u[row] in [0, 1) (injected) or of a Philox4x32-10 uniform keyed by (seed, site, row) when u == NULL -- torch.multinomial's
+ * stream cannot be reproduced.  probs_out (optional, fp32 [rows, ldp]): the filtered, renormalised distribution.     */
+int tgan_sample_tokens(const float* logits, int64_t ldl, const float* u, const uint8_t* suppress_empty, int64_t* ids,
+                       float* probs_out, int64_t ldp, int rows, int V, int exclude_bos, int empty_token, int mode,
+                       int topk, float top_p, float temperature, uint64_t seed, uint64_t site, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

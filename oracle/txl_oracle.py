@@ -439,3 +439,62 @@ def relgan_d_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_rep: int 
     feat = gate * F.relu(hw) + (1.0 - gate) * feat
     out = feat @ sd["feature2out.weight"].t() + sd["feature2out.bias"]               # dropout is identity in eval
     return (out @ sd["out2logits.weight"].t() + sd["out2logits.bias"]).squeeze(1)     # :116-117
+
+
+# ----------------------------------------------------------------------------------------------
+# f1  generation post-processing                                generate.py:228-304
+# ----------------------------------------------------------------------------------------------
+def generation_probs(logits: torch.Tensor, *, temperature: float, technique: str, topk: Optional[int] = 32, p: float = 0.0,
+                     exclude_bos: bool = True, suppress_empty: bool = False, empty_bar_token: int = -1) -> torch.Tensor:
+    """The distribution generate.py samples the next token from, for ONE sequence: logits [V] -> probs [V].
+    Restates generate.py:231-296 step by step (slice out the excluded entries, temperature, softmax, pad them back as
+    zeros, then the topk / nucleus filter with renormalisation)."""
+    lg = logits.clone()
+    if exclude_bos:                                                                  # :232-233
+        lg = lg[1:]
+    if suppress_empty:                                                               # :235-247
+        e = empty_bar_token - 1 if exclude_bos else empty_bar_token
+        lg = torch.cat([lg[:e], lg[e + 1:]], 0)
+    if temperature == 0:                                                             # :250-253
+        probs = torch.zeros_like(lg)
+        probs[lg.argmax()] = 1.0
+    else:
+        probs = F.softmax(lg / temperature, dim=-1)                                  # :255-259
+    if exclude_bos:                                                                  # :261-262
+        probs = F.pad(probs, [1, 0])
+    if suppress_empty:                                                               # :264-266
+        probs = torch.cat([probs[:empty_bar_token], F.pad(probs[empty_bar_token:], [1, 0])], 0)
+    if technique in ("topk", "random"):                                              # :268-275
+        if technique == "topk" and topk is not None:
+            _, top_idx = torch.topk(probs, topk)
+            mask = torch.zeros_like(probs)
+            mask[top_idx] = 1.0
+            probs = probs * mask
+            probs = probs / probs.sum()
+    elif technique == "nucleus":                                                     # :277-296
+        if p > 0:
+            sorted_probs, sorted_indices = torch.sort(probs, descending=True)
+            cumulative = torch.cumsum(sorted_probs, dim=0)
+            remove = cumulative >= p
+            remove[1:] = remove[:-1].clone()
+            remove[0] = False
+            to_remove = remove.scatter(dim=0, index=sorted_indices, src=remove)
+            probs = probs.clone()
+            probs[to_remove] = 0
+            probs = probs / probs.sum()
+    else:
+        raise NotImplementedError(technique)
+    return probs
+
+
+def categorical_from_uniform(probs: torch.Tensor, u: float):
+    """torch.multinomial(probs, 1) (generate.py:302) with its RNG replaced by an injected uniform: the inverse CDF.
+    Returns (token, margin) where margin = distance of u * total to the nearest CDF step (ids of a lower-precision
+    implementation may differ only when that margin is inside its rounding)."""
+    c = torch.cumsum(probs.double(), 0)
+    target = u * c[-1]
+    nz = probs > 0
+    idx = int(torch.nonzero((c > target) & nz)[0]) if bool(((c > target) & nz).any()) else int(torch.nonzero(nz)[-1])
+    steps = torch.cat([torch.zeros(1, dtype=torch.float64), c])
+    margin = float((steps - target).abs().min())
+    return idx, margin

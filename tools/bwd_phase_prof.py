@@ -32,14 +32,14 @@ buf = (ctypes.c_longlong * 32)()
 L._lib.tgan_debug_bwd_prof.argtypes = [ctypes.c_void_p]
 L._lib.tgan_debug_bwd_prof.restype = ctypes.c_int
 rc = L._lib.tgan_debug_bwd_prof(buf)
-names = ["prologue", "g_pull", "pairA", "s_wait+ld", "ring+exp", "pairB", "dp_wait+ld", "compute", "flush_keys", "flush_dr",
-         "publish", "epilogue", "wait kdone", "wait rdone"]
+names = ["prologue", "g_pull", "pairA", "s_wait+ld", "ring+exp", "pairB", "dp_wait+ld", "compute", "(unused)", "wait rdone",
+         "wait ks_empty+publish", "epilogue", "-", "-"]
 tot = sum(buf[:12])  # 12, 13 are sub-intervals of flush_keys / flush_dr
 print("rc", rc, "total clk", tot, "(warp 0 lane 0 of CTA 200; 18 tiles)")
 for n, v in zip(names, buf):
     print(f"{n:12s} {v:9d} {100.0*v/tot:5.1f}%   per tile {v/18:8.0f}")
 
-mn = ["issue/other", "k_full", "s_empty", "v_full", "dp_empty", "rg_full", "g_empty", "p_full", "rd_full", "dr_empty"]
+mn = ["issue/other", "k_full", "s_empty", "v_full", "dp_empty", "rg_full", "g_empty", "p_full(+kd_empty)", "rd_full", "dr_empty"]
 tot2 = sum(buf[16:26])
 print("MMA thread: total clk", tot2)
 for n, v in zip(mn, buf[16:26]):

@@ -367,11 +367,10 @@ BertAttnArgs make_bargs(int B, int heads, int T, int dh, float drop_p, uint64_t 
     a.key = dropout_key(seed, site);
     return a;
 }
+// not a stream operation: safe under graph capture.  (No "set once" cache keyed on the kernel's TYPE: the dgrad and JVP
+// kernels have identical signatures.)
 template <typename K>
-int set_smem(K kernel, int bytes) {  // once per kernel instantiation (not a stream operation: safe under graph capture)
-    static bool done = false;
-    if (done) return 0;
-    done = true;
+int set_smem(K kernel, int bytes) {
     return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 int grid_for(int64_t n, int threads) {

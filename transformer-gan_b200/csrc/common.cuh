@@ -146,6 +146,7 @@ int tgan_set_step_ctr_gemm_tc(const void*);
 int tgan_set_step_ctr_relattn_simt(const void*);
 int tgan_set_step_ctr_relattn_decode(const void*);
 int tgan_set_step_ctr_bert(const void*);
+int tgan_set_step_ctr_sampling(const void*);
 int tgan_set_step_ctr_relattn_fwd_tc(const void*);
 int tgan_set_step_ctr_relattn_bwd_tc(const void*);
 

@@ -267,7 +267,9 @@ relattn_dec_dr(const T* __restrict__ q, int64_t ldq, const float* __restrict__ v
 DecArgs make_dec(int B, int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed, uint64_t site) {
     DecArgs a;
     a.B = B; a.N = N; a.M = M; a.K = M + 1;
-    a.jlo0 = same_length ? (1 - msl > 0 ? 1 - msl : 0) : 0;  // mem_transformer.py:496-503 at qlen = 1: keys j <= -msl are cut a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+    // mem_transformer.py:496-503 at qlen = 1: keys j <= -msl are cut
+    a.jlo0 = same_length ? (1 - msl > 0 ? 1 - msl : 0) : 0;
+    a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
     a.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     a.thresh = drop_p > 0.f ? dropout_thresh16(drop_p) : 0u;
     a.key = dropout_key(seed, site);

@@ -1,13 +1,17 @@
 // tcgen05 relative-position attention BACKWARD for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 // Reference: autograd of mem_transformer.py:201-244 (+ _rel_shift :133-147, mask :495-547); SURVEY.md section 9.
 //
-// One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.  4*SPLIT + 5 warps:
+// One CTA per (b, n); requires Q <= 128 (one query tile) so dK / dV tiles are complete per CTA.  4*SPLIT + 8 warps:
 //   row warps   (4*SPLIT of them) thread = (query row = TMEM lane, column slice): warp w owns lane quarter w & 3 and
 //               the CW = 64/SPLIT-column slice w >> 2 of every 64-wide tile, so each query row is served by SPLIT
-//               threads (SPLIT = 4: 16 row warps -- the row work is latency-bound, more resident warps hide it).
-//   then one warp each: tcgen05.mma issuer; K / V tile loads (TMA); R chunks for the G product; R chunks for dqR;
-//               dK / dV tile stores (TMA): the tiles are staged in shared memory and written by the copy engine, so
-//               the 1.3 MB-strided key rows never go through the SIMT load/store pipe
+//               threads.  They do ONLY the per-score work: G ring, P, dS, publish.
+//   drain warps (4, one per TMEM lane quarter): move the finished key-side results out of tensor memory -- dK / dV
+//               tiles (scaled, bf16, staged for the TMA store) and dR chunks (red.global.add over the batch).  In
+//               round 1 the row warps did this between their own phases: 37 % of their tile time (profiles/
+//               r1 bwd phase log: flush_keys 1979 + flush_dr 730 of ~7250 clk) sat on the critical path.
+//               The dK / dV tiles are staged in shared memory and written by the copy engine (TMA store issued by one
+//               drain thread), so the 1.3 MB-strided key rows never go through the SIMT load/store pipe.
+//   then one warp each: tcgen05.mma issuer; K / V tile loads (TMA); R chunks for the G product; R chunks for dqR
 // Per 64-key tile t (TMEM columns in brackets):
 //     S  [0]   = (q+u) K_t^T          G [64]  = (q+v) R_c^T (ring, as in the forward)     dP [128] = dO' V_t^T
 //   row threads:  P = exp2(S2 - lse2),  dS = P (keep(dP) - delta),  P~ = keep(P)   -> bf16 tiles in shared memory;
@@ -33,12 +37,14 @@ constexpr int BQ = 128;      // query rows per CTA
 constexpr int BJ = 64;       // keys per tile
 constexpr int RING_COLS = 192;
 #ifndef TGAN_BWD_SPLIT
-#define TGAN_BWD_SPLIT 4
+#define TGAN_BWD_SPLIT 2
 #endif
 constexpr int SPLIT = TGAN_BWD_SPLIT;   // threads per query row (2 or 4): each owns CW columns of every 64-wide tile
 constexpr int CW = BJ / SPLIT;
 constexpr int ROW_WARPS = 4 * SPLIT;
-constexpr int NTHREADS = 32 * (ROW_WARPS + 5);
+constexpr int DRAIN0 = ROW_WARPS;          // drain warps DRAIN0 .. DRAIN0 + 3 (DRAIN0 % 4 == 0: warp w reads lane quarter w & 3)
+constexpr int MMA_WARP = ROW_WARPS + 4;
+constexpr int NTHREADS = 32 * (ROW_WARPS + 8);
 static_assert(SPLIT == 2 || SPLIT == 4, "row split");
 
 constexpr int B_OFF_QU = 0;
@@ -55,7 +61,7 @@ constexpr int B_OFF_DRING = B_OFF_GRING + RING_COLS * BQ * 2; // bf16 [16 row gr
 constexpr int DR_GROUP = RING_COLS * 16 + 32;                 // byte stride between 8-row groups (+32: bank spread)
 constexpr int DRING_BYTES = 16 * DR_GROUP;
 constexpr int B_OFF_BAR = B_OFF_DRING + DRING_BYTES;
-constexpr int B_NUM_BARS = 26;
+constexpr int B_NUM_BARS = 28;
 constexpr int BWD_SMEM = B_OFF_BAR + B_NUM_BARS * 8 + 16 + 1024;
 static_assert(BWD_SMEM <= 232448, "shared memory budget");
 constexpr int TB_S = 0, TB_G = 64, TB_DP = 128, TB_DQK = 192, TB_DQR = 256, TB_DK = 320, TB_DV = 384, TB_DR = 448;
@@ -120,8 +126,10 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                    rg_full = v_empty + 8, rg_empty = rg_full + 16, rd_full = rg_empty + 16, rd_empty = rd_full + 8,
                    s_full = rd_empty + 8, s_empty = s_full + 8, dp_full = s_empty + 8, dp_empty = dp_full + 8,
                    g_full = dp_empty + 8, g_empty = g_full + 8, p_full = g_empty + 8, kdone = p_full + 8,
-                   dr_empty = kdone + 8, rdone = dr_empty + 8, ks_full = rdone + 8, ks_empty = ks_full + 8;
-    const uint32_t sTmemPtr = ks_empty + 8;
+                   dr_empty = kdone + 8, rdone = dr_empty + 8, ks_full = rdone + 8, ks_empty = ks_full + 8,
+                   kd_empty = ks_empty + 8,  // the drain warps have read dK / dV of a tile out of tensor memory
+                   fin = kd_empty + 8;       // single use: every tcgen05 op of the CTA has completed
+    const uint32_t sTmemPtr = fin + 8;
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + (sTmemPtr - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,11 +154,11 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         mbar_init(s_full, 1); mbar_init(s_empty, ROW_WARPS);
         mbar_init(dp_full, 1); mbar_init(dp_empty, ROW_WARPS);
         mbar_init(g_full, 1); mbar_init(g_empty, ROW_WARPS);
-        mbar_init(p_full, ROW_WARPS); mbar_init(kdone, 1); mbar_init(dr_empty, ROW_WARPS); mbar_init(rdone, 1);
-        mbar_init(ks_full, ROW_WARPS); mbar_init(ks_empty, 1);
+        mbar_init(p_full, ROW_WARPS); mbar_init(kdone, 1); mbar_init(dr_empty, 4); mbar_init(rdone, 1);
+        mbar_init(ks_full, 1); mbar_init(ks_empty, 1); mbar_init(kd_empty, 4); mbar_init(fin, 1);
         fence_barrier_init();
     }
-    if (warp == ROW_WARPS) tmem_alloc(sTmemPtr, TM_COLS);
+    if (warp == MMA_WARP) tmem_alloc(sTmemPtr, TM_COLS);
 
     // row-thread identity
     const int quarter = warp & 3, part = (warp >> 2) & (SPLIT - 1);
@@ -214,7 +222,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     }
     PROF(0)
 
-    if (warp == ROW_WARPS + 1) {
+    if (warp == MMA_WARP + 1) {
         // =========================== K / V producer ===========================
         if (lane == 0) {
             for (int tt = 0; tt < nt; ++tt) {
@@ -227,7 +235,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 tma_load_3d(sV, &tmV, v_full, n * HS, b, (t_lo + tt) * BJ);
             }
         }
-    } else if (warp == ROW_WARPS + 2) {
+    } else if (warp == MMA_WARP + 2) {
         // =========================== R chunks feeding G = (q+v) R^T ===========================
         if (lane == 0) {
             for (int cc = 0; cc < nc; ++cc) {
@@ -237,7 +245,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 tma_load_2d(sRG + st * 8192, &tmR, rg_full + 8 * st, n * HS, P0 + BJ * cc);
             }
         }
-    } else if (warp == ROW_WARPS + 3) {
+    } else if (warp == MMA_WARP + 3) {
         // =========================== R chunks feeding dqR += dG R ===========================
         if (lane == 0) {
             for (int cc = 0; cc < nc; ++cc) {
@@ -246,20 +254,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                 tma_load_2d(sRD, &tmR, rd_full, n * HS, P0 + BJ * cc);
             }
         }
-    } else if (warp == ROW_WARPS + 4) {
-        // =========================== dK / dV tile stores ===========================
-        if (lane == 0) {
-            for (int tt = 0; tt < nt; ++tt) {
-                mbar_wait(ks_full, tt & 1);  // all row warps have staged tile tt's dK (PT + 0) and dV (PT + 8 KB)
-                tma_store_3d(&tmDK, sPT, n * HS, b, (t_lo + tt) * BJ);
-                tma_store_3d(&tmDV, sPT + 8192, n * HS, b, (t_lo + tt) * BJ);
-                tma_store_commit();
-                tma_store_wait_read();
-                mbar_arrive(ks_empty);
-            }
-            tma_store_wait_all();
-        }
-    } else if (warp == ROW_WARPS) {
+    } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================
         // The whole warp runs the schedule (converged barrier waits); one elected lane issues the tcgen05 ops.
         // Descriptors are built once and advanced by adding to their start-address field (16-byte units).
@@ -331,6 +326,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             PROF(0)
             mbar_wait(p_full, tt & 1);
             PROF(7)
+            if (tt > 0) mbar_wait(kd_empty, (tt - 1) & 1);  // dK / dV of tile tt-1 have left tensor memory
             tcgen05_fence_after();
             if (elect_one()) {
                 const uint64_t dkn = n_k0 + (uint64_t)(((tt & 1) * 8192) >> 4);
@@ -377,8 +373,77 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             mma_rel(tt);
         }
         for (int cc = nt; cc < nc; ++cc) mma_rel(cc);
+        if (elect_one()) umma_commit(fin);
+        __syncwarp();
         PROF(0)
         if (lane == 0) { PROF_DUMP_MMA() }
+    } else if (warp >= DRAIN0) {
+        // =========================== drain warps: key-side results out of tensor memory ===========================
+        // dK / dV of tile tk and dR of chunk cc sit in TMEM in the M = 64 layout: row r = 16 * quarter + lane, lanes 0..15.
+        const int dq_ = warp & 3;
+        const uint32_t lane_off = (uint32_t)(32 * dq_) << 16;
+        const int r = 16 * dq_ + lane;
+        auto flush_dr = [&](int cc) {
+            mbar_wait(rdone, cc & 1);
+            tcgen05_fence_after();
+            uint32_t v[64];
+            tmem_ld32(tmem_base + TB_DR + lane_off, v);
+            tmem_ld32(tmem_base + TB_DR + 32 + lane_off, v + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dr_empty);
+            const int pr = P0 + BJ * cc + r;
+            if (lane < 16 && pr >= 0 && pr < p.K) {
+                float* dst = p.dr + (int64_t)pr * p.lddr + n * HS;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    red_add_v4(dst + 4 * c, __uint_as_float(v[4 * c]) * p.scale, __uint_as_float(v[4 * c + 1]) * p.scale,
+                               __uint_as_float(v[4 * c + 2]) * p.scale, __uint_as_float(v[4 * c + 3]) * p.scale);
+            }
+        };
+        // -> bf16 tiles staged in the P~ buffer (free between the key MMAs of tile tk and the publication of tile tk+1),
+        // in the swizzled layout the TMA store expects; the store warp writes them out
+        auto stage_keys = [&](int tk) {
+            mbar_wait(kdone, tk & 1);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {  // m = 0: dK (scaled), m = 1: dV
+                uint32_t a[64];
+                tmem_ld32(tmem_base + (m ? TB_DV : TB_DK) + lane_off, a);
+                tmem_ld32(tmem_base + (m ? TB_DV : TB_DK) + 32 + lane_off, a + 32);
+                tmem_ld_wait();
+                const float mul = m ? 1.f : p.scale;
+                if (lane < 16) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * mul;
+                        store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + 8192 * m + sw128_off(r, c)), f);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(kd_empty);  // the next tile's key MMAs may overwrite dK / dV
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 5, 128;" ::: "memory");  // all four drain warps have staged their 16 key rows
+            if (warp == DRAIN0 && lane == 0) {
+                tma_store_3d(&tmDK, sPT, n * HS, b, (t_lo + tk) * BJ);
+                tma_store_3d(&tmDV, sPT + 8192, n * HS, b, (t_lo + tk) * BJ);
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(ks_empty);  // the P~ buffer may be overwritten (tile tk+1's publication)
+            }
+            __syncwarp();
+        };
+        for (int tt = 0; tt < nt; ++tt) {
+            stage_keys(tt);
+            flush_dr(tt);
+        }
+        for (int cc = nt; cc < nc; ++cc) flush_dr(cc);
+        if (warp == DRAIN0 && lane == 0) tma_store_wait_all();
     } else {
         // =========================== row warps ===========================
         const bool live = ii < rows_here;
@@ -388,63 +453,6 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const uint32_t th_hi = p.drop_thresh << 16;
         int consumed = 0;
         uint8_t* drow = gbase + B_OFF_DRING + (ii >> 3) * DR_GROUP + (ii & 7) * 2;  // ring entry (p, ii) at drow + 16 p
-        // dR chunk cc (64 relative positions x 64 lanes) sits in TMEM in the M = 64 layout: row r = 16 * quarter + lane
-        auto flush_dr = [&](int cc) {
-            PROF(15)
-            mbar_wait(rdone, cc & 1);
-            PROF(13)
-            tcgen05_fence_after();
-            uint32_t v[CW];
-            tmem_ld_cw(tmem_base + TB_DR + hc + lane_off, v);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dr_empty);
-            const int pr = P0 + BJ * cc + 16 * quarter + lane;
-            if (lane < 16 && pr >= 0 && pr < p.K) {
-                float* dst = p.dr + (int64_t)pr * p.lddr + n * HS + hc;
-#pragma unroll
-                for (int c = 0; c < CW / 4; ++c)
-                    red_add_v4(dst + 4 * c, __uint_as_float(v[4 * c]) * p.scale, __uint_as_float(v[4 * c + 1]) * p.scale,
-                               __uint_as_float(v[4 * c + 2]) * p.scale, __uint_as_float(v[4 * c + 3]) * p.scale);
-            }
-        };
-        // key-side results of tile tk (M = 64 layout: row r = 16 * quarter + lane, lanes 0..15) -> bf16 tiles staged in
-        // the (currently free) P~ buffer, in the swizzled layout the TMA store expects; warp 12 writes them out
-        auto stage_keys = [&](int tk) {
-            PROF(15)
-            mbar_wait(kdone, tk & 1);
-            PROF(12)
-            tcgen05_fence_after();
-            uint32_t a[CW];
-            const int r = 16 * quarter + lane;
-            tmem_ld_cw(tmem_base + TB_DK + hc + lane_off, a);
-            tmem_ld_wait();
-            if (lane < 16) {
-#pragma unroll
-                for (int c = 0; c < CW / 8; ++c) {
-                    float f[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]) * p.scale;
-                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + sw128_off(r, (CW / 8) * part + c)), f);
-                }
-            }
-            tmem_ld_cw(tmem_base + TB_DV + hc + lane_off, a);
-            tmem_ld_wait();
-            if (lane < 16) {
-#pragma unroll
-                for (int c = 0; c < CW / 8; ++c) {
-                    float f[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(a[8 * c + t]);
-                    store8(reinterpret_cast<bf16*>(gbase + B_OFF_PT + 8192 + sw128_off(r, (CW / 8) * part + c)), f);
-                }
-            }
-            tcgen05_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ks_full);
-        };
 #pragma unroll 1
         for (int tt = 0; tt < nt; ++tt) {
             // 1. new G chunks (tile tt reads chunks tt .. tt+2): this thread converts its CW-column slice.  The ring third
@@ -518,8 +526,6 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(dp_empty);
             PROF(6)
-            // the previous tile's dK / dV leave through the P~ buffer (free until this tile publishes) and the copy engine
-            if (tt > 0) stage_keys(tt - 1);
             PROF(8)
             // 4. P~ = keep(P), dS = P (keep(dP) - delta), packed to bf16 pairs in registers
             uint32_t ptw[CW / 2], dsw[CW / 2];
@@ -542,12 +548,14 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
                     dsw[c] = *reinterpret_cast<uint32_t*>(&d);
                 }
             }
-            // 5. drain the previous tile's dR chunk (frees the ring third that this tile's scatter is about to reuse)
+            // 5. the ring third this tile's scatter is about to reuse must have been consumed (dqR / dR MMAs of chunk
+            //    tt-1), and the P~ buffer must be free again (the drain warps staged tile tt-1's dK / dV in it and the
+            //    TMA store has finished reading them)
             PROF(7)
             if (tt > 0) {
-                flush_dr(tt - 1);
+                mbar_wait(rdone, (tt - 1) & 1);
                 PROF(9)
-                mbar_wait(ks_empty, (tt - 1) & 1);  // the TMA store has finished reading the P~ buffer
+                mbar_wait(ks_empty, (tt - 1) & 1);
             }
             if (tt + 2 >= nt) {
                 // chunk tt+2 is one of the two tail chunks whose upper positions are never written: clear this thread's
@@ -579,9 +587,10 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
             if (lane == 0) mbar_arrive(p_full);
             PROF(10)
         }
-        stage_keys(nt - 1);
-        for (int cc = nt - 1; cc < nc; ++cc) flush_dr(cc);
-        // dq = (dqK + dqR) / sqrt(d); du / dvb = column sums over the query rows
+        // dq = (dqK + dqR) / sqrt(d); du / dvb = column sums over the query rows.  `fin` is committed after the last
+        // MMA (a parity wait on `rdone` would be ambiguous here: the row warps are up to three phases behind it).
+        mbar_wait(fin, 0);
+        tcgen05_fence_after();
         {
             uint32_t a[CW], c2[CW];
             tmem_ld_cw(tmem_base + TB_DQK + hc + lane_off, a);
@@ -615,7 +624,7 @@ relattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == ROW_WARPS) {
+    if (warp == MMA_WARP) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TM_COLS);
     }

@@ -25,7 +25,7 @@ extern "C" unsigned long long tgan_launch_count(void) { return g_tgan_launches; 
 extern "C" int tgan_set_step_counter(const void* dev_u32) {
     int rc = tgan_set_step_ctr_local(dev_u32);
     rc |= tgan_set_step_ctr_gemm_simt(dev_u32) | tgan_set_step_ctr_gemm_tc(dev_u32) | tgan_set_step_ctr_relattn_simt(dev_u32) |
-          tgan_set_step_ctr_relattn_decode(dev_u32) | tgan_set_step_ctr_bert(dev_u32) |
+          tgan_set_step_ctr_relattn_decode(dev_u32) | tgan_set_step_ctr_bert(dev_u32) | tgan_set_step_ctr_sampling(dev_u32) |
           tgan_set_step_ctr_relattn_fwd_tc(dev_u32) | tgan_set_step_ctr_relattn_bwd_tc(dev_u32);
     if (rc) { tgan_set_error("tgan_set_step_counter: cudaMemcpyToSymbol failed"); return 2; }
     return 0;

@@ -271,7 +271,12 @@ class _EncodeFn(torch.autograd.Function):
         ctx.eng, ctx.c = eng, c
         if holder is not None:
             holder.append(c)
-        return c.h0
+        # The returned tensor becomes an autograd output of this node: it must not ALSO live inside ctx (node -> ctx.c ->
+        # h0 -> grad_fn = node is a reference cycle that keeps the whole graph -- and the AccumulateGrad nodes bound to the
+        # stream it was built on -- alive until the garbage collector runs; a later CUDA-graph capture on another stream
+        # then trips over them: "dependency created on uncaptured work in another stream").
+        h0, c.h0 = c.h0, None
+        return h0
 
     @staticmethod
     def backward(ctx, dh0):

@@ -66,6 +66,7 @@ _SIGS = {
     "tgan_bert_attn_fwd": [I, P, L, P, L, P, I, I, I, I, F, U, U, P],
     "tgan_bert_attn_bwd": [I, P, L, P, L, P, P, L, I, I, I, I, F, U, U, P],
     "tgan_bert_attn_jvp": [I, P, L, P, L, P, P, L, I, I, I, I, F, U, U, P],
+    "tgan_sample_tokens": [P, L, P, P, P, P, L, I, I, I, I, I, I, F, F, U, U, P],
 }
 EXPORTS = ["tgan_last_error", "tgan_version", "tgan_has_tcgen05", "tgan_launch_count"] + list(_SIGS)
 for _name, _sig in _SIGS.items():
@@ -309,3 +310,13 @@ def sumsq(x, n, out):
 def adam_step(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq, clip, grad_scale):
     _call("tgan_adam_step", param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, beta1, beta2, eps,
           weight_decay, step, _ptr(gnorm_sq), clip, grad_scale, _stream())
+
+
+def sample_tokens(logits, ids, V, *, u=None, suppress_empty=None, probs_out=None, exclude_bos=True, empty_token=-1,
+                  mode=1, topk=32, top_p=0.0, temperature=1.0, seed=0, site=0):
+    """generate.py:228-304 for a batch of rows in one launch: logits fp32 [rows, >= V] -> ids int64 [rows].
+    mode 0 random / 1 topk / 2 nucleus; u: optional injected uniforms [rows] (default: device Philox)."""
+    rows = ids.numel()
+    _call("tgan_sample_tokens", logits.data_ptr(), logits.stride(0), _ptr(u), _ptr(suppress_empty), ids.data_ptr(),
+          _ptr(probs_out), 0 if probs_out is None else probs_out.stride(0), rows, V, int(exclude_bos), empty_token, mode,
+          topk, top_p, temperature, seed, site, _stream())

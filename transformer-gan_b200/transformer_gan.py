@@ -312,6 +312,8 @@ class TransformerGAN(nn.Module):
             ctr = L.step_counter(data.device)
             eng.invalidate()  # the parameter re-pack must be part of the graph
             saved_tau, self.temperature = self.temperature, entry.tau
+            import gc
+            gc.collect()  # no autograd graph of the eager warm-up call (built on another stream) may survive into the capture
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
