@@ -18,7 +18,8 @@
 
 namespace {
 constexpr int HS = TGAN_HS;  // 64
-constexpr int DW = 4;        // warps per CTA (each an independent (b, n))
+constexpr int DW_MAX = 16;   // warps per CTA = heads of ONE sequence when N <= 16 (else 4 consecutive (b, n) pairs): per key row
+                             // the CTA then touches N * 128 contiguous bytes of K and of V instead of isolated 128-byte lines
 
 struct DecArgs {
     int B, N, M, K;          // Q == 1
@@ -38,11 +39,12 @@ __device__ __forceinline__ float group8_sum(float v, uint32_t gmask) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(DW * 32)
+__global__ void __launch_bounds__(DW_MAX * 32)
 relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
                 const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
                 const uint8_t* __restrict__ reset, T* __restrict__ out, int64_t ldo, float* __restrict__ lse, DecArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int DW = blockDim.x >> 5;
     const int bn = blockIdx.x * DW + warp;
     if (bn >= a.B * a.N) return;
     const int b = bn / a.N, n = bn % a.N;
@@ -109,16 +111,18 @@ relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
     }
 }
 
-// Fused backward for Q = 1.  dsbuf: fp32 [B*N, K] scratch (dS already multiplied by scale), consumed by relattn_dec_dr.
+// Fused backward for Q = 1.  dsbuf: fp32 [N, K, B] scratch (dS already multiplied by scale; batch index contiguous so
+// that the batch reduction of relattn_dec_dr reads it coalesced).
 template <typename T>
-__global__ void __launch_bounds__(DW * 32, 5)
+__global__ void __launch_bounds__(DW_MAX * 32, 1)
 relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
                 const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
                 const uint8_t* __restrict__ reset, const T* __restrict__ out, const T* __restrict__ dout, int64_t ldo,
                 const float* __restrict__ lse, T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv,
                 float* __restrict__ dsbuf, float* __restrict__ du, float* __restrict__ dvb, DecArgs a) {
-    __shared__ float s_du[DW][HS], s_dvb[DW][HS];
+    __shared__ float s_du[DW_MAX][HS], s_dvb[DW_MAX][HS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int DW = blockDim.x >> 5;
     const int bn = blockIdx.x * DW + warp;
     const bool active = bn < a.B * a.N;
     const int b = active ? bn / a.N : 0, n = active ? bn % a.N : 0;
@@ -151,13 +155,13 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
         T* dkbase = dk + (int64_t)b * lddkv + col;
         T* dvbase = dv + (int64_t)b * lddkv + col;
         const int64_t kstride = (int64_t)a.B * ldkv, dstride = (int64_t)a.B * lddkv;
-        float* dsrow = dsbuf + (int64_t)bn * a.K;
+        float* dsrow = dsbuf + (int64_t)n * a.K * a.B + b;  // entry j at dsrow[j * B]
         // keys a reset row does not attend to: zero gradients
         for (int j = kg; j < jlo; j += 4) {
             float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             store8(dkbase + j * dstride, z);
             store8(dvbase + j * dstride, z);
-            if (dc == 0) dsrow[j] = 0.f;
+            if (dc == 0) dsrow[(int64_t)j * a.B] = 0.f;
         }
 #pragma unroll 2
         for (int j = jlo + kg; j <= jhi; j += 4) {
@@ -187,7 +191,7 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
             }
             store8(dkbase + j * dstride, dk8);
             store8(dvbase + j * dstride, dv8);
-            if (dc == 0) dsrow[j] = ds;
+            if (dc == 0) dsrow[(int64_t)j * a.B] = ds;
         }
         __syncwarp();  // reconverge the key groups before the full-warp shuffles
 #pragma unroll
@@ -234,34 +238,36 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
     }
 }
 
-// dR[j, n, :] = sum_b dS[b, n, j] * (q[b, n, :] + r_r_bias[n, :])      (dS carries the 1/sqrt(d_head) factor)
-// grid (ceil(K / 8), N), 128 threads: thread = (key j0 + t / 16, dims 4 * (t % 16) .. +3); the batch loop is unrolled so
-// that 8 independent (dS, q) loads are in flight per thread.
-constexpr int DR_KEYS = 8;
+// dR[j, n, :] = sum_b dS[n, j, b] * (q[b, n, :] + r_r_bias[n, :])      (dS carries the 1/sqrt(d_head) factor)
+// One CTA per (key j, head n), 256 threads = 4 batch phases x 64 dims: thread (bq, d) sums b = bq, bq + 4, ...; the dS
+// value of a (b) step is one broadcast load per warp, the q row one coalesced 128-byte (bf16) line.  The four partial
+// sums meet in shared memory.  (Round 2's first version walked the batch with one thread per (j, 4 dims): 512
+// dependent-latency steps on uncoalesced 4-byte reads, 199 us per launch = a third of the generator update.)
+constexpr int DR_THREADS = 256;
 template <typename T>
-__global__ void __launch_bounds__(DR_KEYS * 16)
+__global__ void __launch_bounds__(DR_THREADS)
 relattn_dec_dr(const T* __restrict__ q, int64_t ldq, const float* __restrict__ vb, const float* __restrict__ dsbuf,
                float* __restrict__ dr, int64_t lddr, DecArgs a) {
-    const int n = blockIdx.y;
-    const int j = blockIdx.x * DR_KEYS + (threadIdx.x >> 4);
-    const int d = 4 * (threadIdx.x & 15);
-    if (j >= a.K) return;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, sum = 0.f;
+    __shared__ float s_acc[4][HS], s_sum[4];
+    const int j = blockIdx.x, n = blockIdx.y;
+    const int d = threadIdx.x & 63, bq = threadIdx.x >> 6;
+    const float* ds = dsbuf + ((int64_t)n * a.K + j) * a.B;
     const T* qp = q + n * HS + d;
-    const float* dp = dsbuf + (int64_t)n * a.K + j;
-    const int64_t dstep = (int64_t)a.N * a.K;
+    float acc = 0.f, sum = 0.f;
 #pragma unroll 8
-    for (int b = 0; b < a.B; ++b) {
-        const float ds = dp[b * dstep];
-        const T* qr = qp + (int64_t)b * ldq;
-        float x0 = to_f(qr[0]), x1 = to_f(qr[1]), x2 = to_f(qr[2]), x3 = to_f(qr[3]);
-        acc[0] = fmaf(ds, x0, acc[0]); acc[1] = fmaf(ds, x1, acc[1]);
-        acc[2] = fmaf(ds, x2, acc[2]); acc[3] = fmaf(ds, x3, acc[3]);
-        sum += ds;
+    for (int b = bq; b < a.B; b += 4) {
+        const float w = ds[b];
+        acc = fmaf(w, to_f(qp[(int64_t)b * ldq]), acc);
+        sum += w;
     }
-    float* o = dr + (int64_t)j * lddr + n * HS + d;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] = fmaf(sum, vb[n * HS + d + t], acc[t]);
+    s_acc[bq][d] = acc;
+    if (d == 0) s_sum[bq] = sum;
+    __syncthreads();
+    if (bq == 0) {
+        const float tot = s_acc[0][d] + s_acc[1][d] + s_acc[2][d] + s_acc[3][d];
+        const float st = s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3];
+        dr[(int64_t)j * lddr + n * HS + d] = fmaf(st, vb[n * HS + d], tot);
+    }
 }
 
 DecArgs make_dec(int B, int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed, uint64_t site) {
@@ -285,6 +291,7 @@ int tgan_relattn_fwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                              void* out, int64_t ldo, float* lse, int B, int N, int M, int msl, int same_length, float scale,
                              float drop_p, uint64_t seed, uint64_t site, cudaStream_t st) {
     DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
+    const int DW = N <= DW_MAX ? N : 4;
     const int grid = ceil_div((int64_t)B * N, DW);
     if (dtype == TGAN_F32)
         relattn_dec_fwd<float><<<grid, DW * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
@@ -304,6 +311,7 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                              int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
                              uint64_t site, cudaStream_t st) {
     DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
+    const int DW = N <= DW_MAX ? N : 4;
     const int grid = ceil_div((int64_t)B * N, DW);
     if (dtype == TGAN_F32)
         relattn_dec_bwd<float><<<grid, DW * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
@@ -317,11 +325,11 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                                                          lddkv, scratch, du, dvb, a);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
-    dim3 g2(ceil_div(a.K, DR_KEYS), N);
+    dim3 g2(a.K, N);
     if (dtype == TGAN_F32)
-        relattn_dec_dr<float><<<g2, DR_KEYS * 16, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
+        relattn_dec_dr<float><<<g2, DR_THREADS, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
     else
-        relattn_dec_dr<bf16><<<g2, DR_KEYS * 16, 0, st>>>((const bf16*)q, ldq, vb, scratch, dr, lddr, a);
+        relattn_dec_dr<bf16><<<g2, DR_THREADS, 0, st>>>((const bf16*)q, ldq, vb, scratch, dr, lddr, a);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
