@@ -14,8 +14,12 @@ BASELINE.json's metric is "train tokens/sec (GAN step)".  A "step" is one iterat
 cycles); the timed region starts on a cycle boundary.  `extras.mle_only` keeps round 1's headline (the MLE step of
 experiment_baseline.yml alone).
 
-One process per GPU; N > 1 shards the batch columns (data parallel, global batch fixed = strong scaling as in
-train.py:226-227) and all-reduces the flat gradient buffers over NCCL.  Prints ONE JSON line on rank 0.
+One process per GPU.  N > 1 is data parallel over sequences: every rank runs the configuration's batch (512 sequences
+per GPU: WEAK scaling, global batch 512 x N; `--scaling strong` keeps the global batch at 512 and divides it as
+train.py:226-227 does) on its own token stream (seed + 1000 x rank, train.py:224).  The only exchange is the gradient
+all-reduce: the MLE gradients go bucket by bucket (one per layer, last layer first) through tgan_allreduce_bucket on a
+side stream inside the backward (captured in its CUDA graph), the two adversarial updates all-reduce their flat
+gradient buffer once.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -54,7 +58,11 @@ def parse():
     ap.add_argument("--workload", default="gan", choices=["gan", "mle"],
                     help="gan: experiment_spanbert.yml cycle (the BASELINE metric); mle: experiment_baseline.yml MLE step only")
     ap.add_argument("--batch-chunk", type=int, default=1, help="micro-batches per step (reference yml: 16; native: 1)")
-    ap.add_argument("--global-batch", type=int, default=WORK["global_batch"])
+    ap.add_argument("--global-batch", type=int, default=WORK["global_batch"],
+                    help="sequences per optimizer step: per GPU under weak scaling, in total under strong scaling")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-buckets", action="store_true", help="N > 1: one flat all-reduce after the backward instead of "
+                    "per-layer buckets overlapped with it")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -179,13 +187,17 @@ def workload_config(args, world):
     name = ("experiment_spanbert.yml Transformer-XL + GAN training cycle: every iteration an MLE optimizer step, every 5th "
             "iteration one discriminator update + one generator update (123 Gumbel-softmax sampling steps, BERT 5x768 "
             "discriminator, WGAN-GP)") if gan else "experiment_baseline.yml Transformer-XL MLE training step"
+    per_gpu = args.global_batch if args.scaling == "weak" else args.global_batch // world
     return {"workload": name + " (6 layers, 10 heads, d_model 500, d_inner 1000, vocab 310, tgt_len 128, mem_len 1024, "
                         "dropout 0.1), synthetic MAESTRO-vocab tokens",
-            "global_batch": args.global_batch, "seq_len": WORK["tgt_len"], "mem_len": WORK["mem_len"],
+            "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "seq_len": WORK["tgt_len"], "mem_len": WORK["mem_len"],
+            "all_reduce": None if world == 1 else ("one flat NCCL all-reduce per optimizer step" if args.no_buckets else
+                          "MLE: 7 buckets (6 layers + shared tensors) via tgan_allreduce_bucket on a side stream inside "
+                          "backward; dis / gen updates: one flat NCCL all-reduce each"),
             "batch_chunk": args.batch_chunk, "parallelism": f"dp{world}",
             "gan": {"dis_tgt_len": 128, "dis_mem_len": 128, "context_len": 5, "sample_chunks_mem": 2, "freq": 5,
                     "discriminator": "BERT 5x768, shipped trainable set (pooler + classifier), wgan-gp",
-                    "dis_batch": args.global_batch} if gan else None,
+                    "dis_batch": per_gpu * world} if gan else None,
             "launch": "host launches" if args.no_graphs else
                       "CUDA graphs (MLE: one forward + one backward graph per ring phase; one graph per adversarial phase)",
             "l2": "per-step working set (activations + recurrence memory, several GB) is far larger than the 126 MB L2"}
@@ -286,8 +298,8 @@ def run_reference(args):
         "impl": "reference", "metric": "train tokens/sec (GAN step)" if gan else "train tokens/sec", "value": v,
         "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(1, int(os.environ.get("WORLD_SIZE", "1")))),
         "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -305,7 +317,7 @@ class Cycle:
         self.L, self.dp, self.args, self.dev, self.world = L, dp, args, dev, world
         self.gan = args.workload == "gan"
         Q, V = WORK["tgt_len"], WORK["n_token"]
-        self.B = args.global_batch // world            # sequences on this rank
+        self.B = args.global_batch if args.scaling == "weak" else args.global_batch // world   # sequences on this rank
         self.n_chunks = args.batch_chunk
         self.Bc = self.B // self.n_chunks
         bert_dir = synth_bert_checkpoint() if self.gan else None
@@ -323,7 +335,11 @@ class Cycle:
         # one flat parameter / gradient buffer per optimizer group: all-reduce, clip and Adam are one call each
         self.fp = dp.FlatParams(gen.parameters())
         lr = WORK["lr"] / world  # train.py:392 divides lr by the GPU count
-        self.opt = dp.FusedClipAdam(self.fp, lr, clip=WORK["clip"], world=world)       # `optimizer` (MLE)
+        self.reducer = None
+        if world > 1 and not args.no_buckets:
+            self.reducer = gen.grad_reducer = dp.BucketReducer(world, rank, dev)
+        self.opt = dp.FusedClipAdam(self.fp, lr, clip=WORK["clip"], world=world,       # `optimizer` (MLE)
+                                    reduce=self.reducer is None)
         self.gen_opt = dp.FusedClipAdam(self.fp, lr, clip=WORK["clip"], world=world)   # `gen_optimizer` (train.py:1085-1090)
         self.dis_opt = self.dfp = None
         if self.gan:
@@ -576,8 +592,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from tgan_b200 import lib as L
 
-    if args.global_batch % (world * args.batch_chunk):
-        raise SystemExit("global batch must divide by gpus * batch_chunk")
+    if (args.global_batch if args.scaling == "weak" else args.global_batch // world) % args.batch_chunk or \
+            (args.scaling == "strong" and args.global_batch % world):
+        raise SystemExit("batch must divide by gpus (strong scaling) and batch_chunk")
     Q = WORK["tgt_len"]
     cyc = Cycle(args, dev, world, rank)
     freq = WORK["gan_freq"]
@@ -626,7 +643,8 @@ def main():
     h2d, d2h = cyc.h2d / args.steps, cyc.d2h / args.steps
     torch.cuda.synchronize()
     final_loss = [float(x) for x in cyc.loss_host]
-    tokens = Q * args.global_batch * args.steps
+    global_batch = args.global_batch * world if args.scaling == "weak" else args.global_batch
+    tokens = Q * global_batch * args.steps
     value = tokens / (ms_dev / 1e3)
     e2e_value = tokens / (ms_e2e / 1e3)
     gan_updates = len([i for i in range(args.steps) if i % freq == 0]) if cyc.gan else 0
@@ -662,7 +680,7 @@ def main():
             "warmup": args.warmup, "untimed_steps": untimed, "ms_per_step": ms_dev / args.steps,
             "gan_updates_in_timed_region": {"dis": gan_updates, "gen": gan_updates},
             "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "final_losses_mle_dis_gen": final_loss},

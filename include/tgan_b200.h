@@ -224,6 +224,17 @@ int tgan_sample_tokens(const float* logits, int64_t ldl, const float* u, const u
                        float* probs_out, int64_t ldp, int rows, int V, int exclude_bos, int empty_token, int mode,
                        int topk, float top_p, float temperature, uint64_t seed, uint64_t site, void* stream);
 
+/* ---- data-parallel gradient all-reduce: replaces DistributedDataParallel's implicit all-reduce,
+ * train.py:649-655 / :904.  The library binds libnccl.so.2 at run time (tgan_nccl_load, optional explicit path).
+ * tgan_nccl_unique_id: 128-byte id created on one rank, distributed by the caller; tgan_nccl_init: collective, current
+ * device = this rank's GPU; tgan_allreduce_bucket: in-place SUM of `count` elements on `stream` (stream-ordered,
+ * capturable: the buckets of a captured backward live inside its CUDA graph, on a side stream).                     */
+int tgan_nccl_load(const char* lib_path);
+int tgan_nccl_unique_id(void* id128);
+int tgan_nccl_init(const void* id128, int nranks, int rank, void** comm_out);
+int tgan_allreduce_bucket(void* comm, void* buf, int64_t count, int dtype, void* stream);
+int tgan_nccl_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

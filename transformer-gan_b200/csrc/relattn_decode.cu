@@ -28,18 +28,56 @@ struct DecArgs {
     uint32_t thresh, key;
 };
 
-// Sum over the 8 lanes of one key group.  `gmask` names exactly those 8 lanes: the key loop's trip count differs
-// between the groups of a warp (K is not a multiple of 4), so a full-warp mask inside the loop would wait for lanes that
-// have already left it.
-__device__ __forceinline__ float group8_sum(float v, uint32_t gmask) {
-    v += __shfl_xor_sync(gmask, v, 1);
-    v += __shfl_xor_sync(gmask, v, 2);
-    v += __shfl_xor_sync(gmask, v, 4);
+// 8 consecutive elements kept in their storage format (bf16: one 16-byte register quad) until they are consumed: the
+// loads of the next key row are issued before the current row's arithmetic and cost 12 registers, not 24.
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+    uint4 v;
+    __device__ __forceinline__ void ld(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void get(float* o) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void ld(const float* p) {
+        a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+    }
+    __device__ __forceinline__ void get(float* o) const {
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+};
+
+// Per-lane FIFO of key rows in shared memory, filled with cp.async: a lane copies ITS 8 elements of the k / r / v rows
+// of a key and later reads back exactly those bytes, so no other thread is involved -- cp.async.wait_group is the only
+// synchronisation.  PF stages deep: a warp keeps PF key quartets in flight without spending registers on them.  A warp
+// walks ~K/4 iterations; with the one-deep register prefetch each one cost a full DRAM round trip (~1 us) and the
+// kernel ran at 2.4 TB/s in two unbalanced waves; the FIFO hides the latency behind PF iterations.
+constexpr int PF = 4;
+template <typename T>
+__device__ __forceinline__ void cp_row8(uint32_t dst, const T* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    if constexpr (sizeof(T) == 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Sum over the 8 lanes of one key group.  Called with the FULL warp converged: the key loops below run the same trip
+// count on every lane (lanes whose key index is past the end are predicated off around the shuffles, not out of the
+// loop).  A per-group member mask also works but costs ~4x: a lane-dependent mask sends every shuffle through the
+// compiler's divergent-mask slow path (REDUX.OR + BRA.DIV loop over the distinct masks).
+__device__ __forceinline__ float group8_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(DW_MAX * 32)
+__global__ void __launch_bounds__(DW_MAX * 32, 2)
 relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
                 const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
                 const uint8_t* __restrict__ reset, T* __restrict__ out, int64_t ldo, float* __restrict__ lse, DecArgs a) {
@@ -49,7 +87,6 @@ relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
     if (bn >= a.B * a.N) return;
     const int b = bn / a.N, n = bn % a.N;
     const int kg = lane >> 3, dc = lane & 7;
-    const uint32_t gmask = 0xffu << (8 * kg);
     const int col = n * HS + 8 * dc;
     float qu[8], qv[8];
     {
@@ -68,25 +105,65 @@ relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
     const T* kbase = k + (int64_t)b * ldkv + col;
     const T* vbase = v + (int64_t)b * ldkv + col;
     const int64_t kstride = (int64_t)a.B * ldkv;
-#pragma unroll 2
-    for (int j = jlo + kg; j <= jhi; j += 4) {
-        float k8[8], r8[8], v8[8];
-        load8(kbase + j * kstride, k8);
-        load8(r + (int64_t)j * ldr + col, r8);
-        load8(vbase + j * kstride, v8);
+    // FIFO slot (stage st, tensor x) of this thread: fifo + ((st * 3 + x) * blockDim.x + threadIdx.x) * CH
+    extern __shared__ __align__(16) uint8_t fifo_raw[];
+    constexpr int CH = 8 * sizeof(T);
+    uint8_t* fifo = fifo_raw + threadIdx.x * CH;
+    const uint32_t fifo_s = (uint32_t)__cvta_generic_to_shared(fifo);
+    const uint32_t slot = blockDim.x * CH;
+    // running pointers (one 64-bit add per row and step instead of an index * stride multiply chain -- the first
+    // version of this loop spent 45 % of its instructions on address arithmetic)
+    const int64_t kstep = 4 * kstride, rstep = 4 * ldr;
+    int j = jlo + kg;
+    const T* kp = kbase + j * kstride;          // prefetch cursors: row of key jp
+    const T* rp = r + (int64_t)j * ldr + col;
+    const T* vp = vbase + j * kstride;
+    int jp = j;
+    uint32_t wr = fifo_s;                       // FIFO write / read cursors (stage = 3 * slot bytes)
+    const uint32_t fifo_end = fifo_s + PF * 3 * slot;
+    auto issue = [&]() {
+        if (jp <= jhi) {
+            cp_row8(wr, kp);
+            cp_row8(wr + slot, rp);
+            cp_row8(wr + 2 * slot, vp);
+        }
+        cp_commit();  // one group per stage, empty past the end: wait_group counts stay uniform
+        kp += kstep; rp += rstep; vp += kstep; jp += 4;
+        wr += 3 * slot;
+        if (wr == fifo_end) wr = fifo_s;
+    };
+#pragma unroll
+    for (int st = 0; st < PF - 1; ++st) issue();
+    const uint8_t* rd = fifo;
+    const uint8_t* rd_end = fifo + PF * 3 * slot;
+#pragma unroll 1
+    for (int j0 = jlo; j0 <= jhi; j0 += 4, j += 4) {  // same trip count on all 32 lanes; j = j0 + kg
+        issue();
+        cp_wait<PF - 1>();  // the group of the stage at `rd` has landed
+        const bool valid = j <= jhi;
+        float k8[8], r8[8];
+        load8(reinterpret_cast<const T*>(rd), k8);
+        load8(reinterpret_cast<const T*>(rd + slot), r8);
         float s = 0.f;
 #pragma unroll
         for (int t = 0; t < 8; ++t) s = fmaf(qu[t], k8[t], fmaf(qv[t], r8[t], s));
-        s = group8_sum(s, gmask) * a.scale_log2;
-        const float mn = fmaxf(m, s);
-        const float corr = fast_exp2(m - mn);  // m = -inf on the first key: exp2(-inf) = 0
-        const float pe = fast_exp2(s - mn);
-        l = fmaf(l, corr, pe);
-        const float pw = (!a.thresh || attn_drop_keep(rowkey, j, a.thresh)) ? pe : 0.f;
+        s = group8_sum(s) * a.scale_log2;  // (stale FIFO bytes on lanes past the end: discarded below)
+        if (valid) {
+            const float mn = fmaxf(m, s);
+            const float corr = fast_exp2(m - mn);  // m = -inf on the first key: exp2(-inf) = 0
+            const float pe = fast_exp2(s - mn);
+            l = fmaf(l, corr, pe);
+            const float pw = (!a.thresh || attn_drop_keep(rowkey, j, a.thresh)) ? pe : 0.f;
+            float v8[8];
+            load8(reinterpret_cast<const T*>(rd + 2 * slot), v8);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = fmaf(pw, v8[t], acc[t] * corr);
-        m = mn;
+            for (int t = 0; t < 8; ++t) acc[t] = fmaf(pw, v8[t], acc[t] * corr);
+            m = mn;
+        }
+        rd += 3 * slot;
+        if (rd == rd_end) rd = fifo;
     }
+    cp_wait<0>();
     __syncwarp();  // the groups leave the loop at different trip counts: reconverge before full-warp shuffles
     // merge the 4 key groups (lanes with equal dc): max, then rescaled sums
     float m_all = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
@@ -114,20 +191,18 @@ relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
 // Fused backward for Q = 1.  dsbuf: fp32 [N, K, B] scratch (dS already multiplied by scale; batch index contiguous so
 // that the batch reduction of relattn_dec_dr reads it coalesced).
 template <typename T>
-__global__ void __launch_bounds__(DW_MAX * 32, 1)
+__global__ void __launch_bounds__(128, 5)
 relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
                 const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
                 const uint8_t* __restrict__ reset, const T* __restrict__ out, const T* __restrict__ dout, int64_t ldo,
                 const float* __restrict__ lse, T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv,
                 float* __restrict__ dsbuf, float* __restrict__ du, float* __restrict__ dvb, DecArgs a) {
-    __shared__ float s_du[DW_MAX][HS], s_dvb[DW_MAX][HS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int DW = blockDim.x >> 5;
     const int bn = blockIdx.x * DW + warp;
     const bool active = bn < a.B * a.N;
     const int b = active ? bn / a.N : 0, n = active ? bn % a.N : 0;
     const int kg = lane >> 3, dc = lane & 7;
-    const uint32_t gmask = 0xffu << (8 * kg);
     const int col = n * HS + 8 * dc;
     float dqk[8], dqr[8];
 #pragma unroll
@@ -145,7 +220,7 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
             float d = 0.f;
 #pragma unroll
             for (int t = 0; t < 8; ++t) { qu[t] = x[t] + uu[t]; qv[t] = x[t] + vv[t]; d = fmaf(g8[t], o8[t], d); }
-            delta = group8_sum(d, gmask);
+            delta = group8_sum(d);
         }
         const float L2 = lse[bn] * 1.4426950408889634f;
         const int jlo = (reset && reset[b]) ? max(a.M, a.jlo0) : a.jlo0, jhi = a.K - 1;
@@ -163,36 +238,76 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
             store8(dvbase + j * dstride, z);
             if (dc == 0) dsrow[(int64_t)j * a.B] = 0.f;
         }
-#pragma unroll 2
-        for (int j = jlo + kg; j <= jhi; j += 4) {
+        extern __shared__ __align__(16) uint8_t fifo_raw[];
+        constexpr int CH = 8 * sizeof(T);
+        uint8_t* fifo = fifo_raw + threadIdx.x * CH;
+        const uint32_t fifo_s = (uint32_t)__cvta_generic_to_shared(fifo);
+        const uint32_t slot = blockDim.x * CH;
+        const int64_t kstep = 4 * kstride, rstep = 4 * ldr, dstep = 4 * dstride, sstep = 4 * (int64_t)a.B;
+        int j = jlo + kg;
+        const T* kp = kbase + j * kstride;
+        const T* rp = r + (int64_t)j * ldr + col;
+        const T* vp = vbase + j * kstride;
+        T* dkp = dkbase + j * dstride;
+        T* dvp = dvbase + j * dstride;
+        float* dsp = dsrow + (int64_t)j * a.B;
+        int jp = j;
+        uint32_t wr = fifo_s;
+        const uint32_t fifo_end = fifo_s + PF * 3 * slot;
+        auto issue = [&]() {
+            if (jp <= jhi) {
+                cp_row8(wr, kp);
+                cp_row8(wr + slot, rp);
+                cp_row8(wr + 2 * slot, vp);
+            }
+            cp_commit();
+            kp += kstep; rp += rstep; vp += kstep; jp += 4;
+            wr += 3 * slot;
+            if (wr == fifo_end) wr = fifo_s;
+        };
+#pragma unroll
+        for (int st = 0; st < PF - 1; ++st) issue();
+        const uint8_t* rd = fifo;
+        const uint8_t* rd_end = fifo + PF * 3 * slot;
+#pragma unroll 1
+        for (int j0 = jlo; j0 <= jhi; j0 += 4, j += 4) {  // same trip count on all 32 lanes; j = j0 + kg
+            issue();
+            cp_wait<PF - 1>();
+            const bool valid = j <= jhi;
             float k8[8], r8[8], v8[8];
-            load8(kbase + j * kstride, k8);
-            load8(r + (int64_t)j * ldr + col, r8);
-            load8(vbase + j * kstride, v8);
+            load8(reinterpret_cast<const T*>(rd), k8);
+            load8(reinterpret_cast<const T*>(rd + slot), r8);
+            load8(reinterpret_cast<const T*>(rd + 2 * slot), v8);
+            rd += 3 * slot;
+            if (rd == rd_end) rd = fifo;
             float s = 0.f, dp = 0.f;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 s = fmaf(qu[t], k8[t], fmaf(qv[t], r8[t], s));
                 dp = fmaf(g8[t], v8[t], dp);
             }
-            s = group8_sum(s, gmask);
-            dp = group8_sum(dp, gmask);
-            const float pr = fast_exp2(fmaf(s, a.scale_log2, -L2));
-            const bool keep = !a.thresh || attn_drop_keep(rowkey, j, a.thresh);
-            const float pw = keep ? pr * a.drop_scale : 0.f;
-            const float ds = pr * ((keep ? dp * a.drop_scale : 0.f) - delta) * a.scale;
-            float dk8[8], dv8[8];
+            s = group8_sum(s);
+            dp = group8_sum(dp);
+            if (valid) {  // (after the shuffles: every lane took part in them)
+                const float pr = fast_exp2(fmaf(s, a.scale_log2, -L2));
+                const bool keep = !a.thresh || attn_drop_keep(rowkey, j, a.thresh);
+                const float pw = keep ? pr * a.drop_scale : 0.f;
+                const float ds = pr * ((keep ? dp * a.drop_scale : 0.f) - delta) * a.scale;
+                float dk8[8], dv8[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                dk8[t] = ds * qu[t];
-                dv8[t] = pw * g8[t];
-                dqk[t] = fmaf(ds, k8[t], dqk[t]);
-                dqr[t] = fmaf(ds, r8[t], dqr[t]);
+                for (int t = 0; t < 8; ++t) {
+                    dk8[t] = ds * qu[t];
+                    dv8[t] = pw * g8[t];
+                    dqk[t] = fmaf(ds, k8[t], dqk[t]);
+                    dqr[t] = fmaf(ds, r8[t], dqr[t]);
+                }
+                store8(dkp, dk8);
+                store8(dvp, dv8);
+                if (dc == 0) *dsp = ds;
             }
-            store8(dkbase + j * dstride, dk8);
-            store8(dvbase + j * dstride, dv8);
-            if (dc == 0) dsrow[(int64_t)j * a.B] = ds;
+            dkp += dstep; dvp += dstep; dsp += sstep;
         }
+        cp_wait<0>();
         __syncwarp();  // reconverge the key groups before the full-warp shuffles
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -211,29 +326,13 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
         }
     }
     // du = column sums of the content part of dq, dvb of the position part (r_w_bias / r_r_bias are shared by all rows):
-    // warps of one CTA that serve the same head are combined in shared memory first
-    if (kg == 0) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { s_du[warp][8 * dc + t] = dqk[t]; s_dvb[warp][8 * dc + t] = dqr[t]; }
-    }
-    __syncthreads();
+    // 128 float atomics per warp onto N * 128 addresses.  (A first version merged the warps of a CTA in shared memory
+    // first; its head-matching loops with integer modulo cost more instructions than the whole key loop of short rows.)
     if (active && kg == 0) {
-        bool first = true;  // the lowest warp of each head in this CTA adds that head's partial sums
-        for (int w = 0; w < warp; ++w) {
-            const int obn = blockIdx.x * DW + w;
-            if (obn < a.B * a.N && obn % a.N == n) first = false;
-        }
-        if (first) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                float su = 0.f, sv = 0.f;
-                for (int w = warp; w < DW; ++w) {
-                    const int obn = blockIdx.x * DW + w;
-                    if (obn < a.B * a.N && obn % a.N == n) { su += s_du[w][8 * dc + t]; sv += s_dvb[w][8 * dc + t]; }
-                }
-                atomicAdd(&du[col + t], su);
-                atomicAdd(&dvb[col + t], sv);
-            }
+        for (int t = 0; t < 8; ++t) {
+            atomicAdd(&du[col + t], dqk[t]);
+            atomicAdd(&dvb[col + t], dqr[t]);
         }
     }
 }
@@ -293,11 +392,18 @@ int tgan_relattn_fwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
     DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
     const int DW = N <= DW_MAX ? N : 4;
     const int grid = ceil_div((int64_t)B * N, DW);
+    const size_t sm_f32 = (size_t)PF * 3 * DW * 32 * 32, sm_bf16 = (size_t)PF * 3 * DW * 32 * 16;
+    static bool attr = false;
+    if (!attr) {
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_dec_fwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF * 3 * DW_MAX * 32 * 32));
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_dec_fwd<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF * 3 * DW_MAX * 32 * 16));
+        attr = true;
+    }
     if (dtype == TGAN_F32)
-        relattn_dec_fwd<float><<<grid, DW * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
+        relattn_dec_fwd<float><<<grid, DW * 32, sm_f32, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
                                                           (const float*)r, ldr, u, vb, reset, (float*)out, ldo, lse, a);
     else
-        relattn_dec_fwd<bf16><<<grid, DW * 32, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
+        relattn_dec_fwd<bf16><<<grid, DW * 32, sm_bf16, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
                                                          (const bf16*)r, ldr, u, vb, reset, (bf16*)out, ldo, lse, a);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
@@ -311,15 +417,21 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                              int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
                              uint64_t site, cudaStream_t st) {
     DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
-    const int DW = N <= DW_MAX ? N : 4;
+    const int DW = 4;  // <= 96 registers x 128 threads: 5 CTAs (20 warps) per SM; 10-warp CTAs at 128 registers fit only once
     const int grid = ceil_div((int64_t)B * N, DW);
+    const size_t sm_f32 = (size_t)PF * 3 * DW * 32 * 32, sm_bf16 = (size_t)PF * 3 * DW * 32 * 16;
+    static bool attr = false;
+    if (!attr) {  // fp32: 48 KB of FIFO + the static du / dvb staging exceeds the default 48 KB window
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_dec_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF * 3 * 128 * 32));
+        attr = true;
+    }
     if (dtype == TGAN_F32)
-        relattn_dec_bwd<float><<<grid, DW * 32, 0, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
+        relattn_dec_bwd<float><<<grid, DW * 32, sm_f32, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
                                                           (const float*)r, ldr, u, vb, reset, (const float*)out,
                                                           (const float*)dout, ldo, lse, (float*)dq, (float*)dk,
                                                           (float*)dv, lddkv, scratch, du, dvb, a);
     else
-        relattn_dec_bwd<bf16><<<grid, DW * 32, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
+        relattn_dec_bwd<bf16><<<grid, DW * 32, sm_bf16, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
                                                          (const bf16*)r, ldr, u, vb, reset, (const bf16*)out,
                                                          (const bf16*)dout, ldo, lse, (bf16*)dq, (bf16*)dk, (bf16*)dv,
                                                          lddkv, scratch, du, dvb, a);

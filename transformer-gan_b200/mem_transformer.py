@@ -142,7 +142,8 @@ class _TxlFunction(torch.autograd.Function):
                 prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
             targets[n] = prm.grad
         if mode == "mle":
-            grads = eng.backward(ectx, dnll=gout, need_dinput=ctx.soft_in, grad_targets=targets)
+            grads = eng.backward(ectx, dnll=gout, need_dinput=ctx.soft_in, grad_targets=targets,
+                                 reducer=model.grad_reducer)
         else:
             g = gout.view(T * B, V)
             if mode == "gumbel":
@@ -202,7 +203,8 @@ class _TxlGraphFunction(torch.autograd.Function):
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(g, pool=eng.graph_pool()):
-                eng.backward(entry.ectx, dnll=entry.dnll, grad_targets=entry.staged, accumulate=False)
+                eng.backward(entry.ectx, dnll=entry.dnll, grad_targets=entry.staged, accumulate=False,
+                             reducer=model.grad_reducer)
             entry.bwd, entry.n_bwd = g, L.launch_count() - n0
             # eng.backward dropped the activations: their pool blocks may now be reused by the next key's capture
             # (graphs that share the pool are replayed strictly one after the other).  The entry must not keep the
@@ -264,6 +266,9 @@ class MemTransformerLM(nn.Module):
         # replay each steady-state MLE segment (forward, backward) as CUDA graphs instead of ~180 launches; see
         # _TxlGraphFunction.  Off by default: it pins the input / gradient buffers of the captured shapes.
         self.use_cuda_graphs = False
+        # data parallel: tgan_b200.dp.BucketReducer that all-reduces the MLE gradients bucket by bucket inside backward
+        # (None: single process, or the caller reduces the flat gradient itself)
+        self.grad_reducer = None
         self._graphs = {}
         self._graph_rings = {}
         self._graph_pending = None

@@ -82,15 +82,55 @@ def allreduce_gradients(flat_grad: torch.Tensor, world: int, average: bool = Fal
         flat_grad.mul_(1.0 / world)
 
 
+class BucketReducer:
+    """The data-parallel gradient exchange of the MLE step through the C-ABI (``tgan_allreduce_bucket``): the padded
+    gradient buffers of the engine are all-reduced layer by layer, in the order the backward finishes them (last layer
+    first), on a SIDE stream -- each bucket's NCCL kernel overlaps the backward of the layers below it.  NCCL
+    operations are stream-ordered and capturable, so under ``use_cuda_graphs`` the buckets are nodes of the captured
+    backward graph.  Replaces DistributedDataParallel (train.py:649-655), whose hooks do the same per autograd bucket;
+    unlike DDP there is one exchange per optimizer step when ``batch_chunk`` is 1 (the reference re-reduces every
+    micro-batch).  Pair it with ``FusedClipAdam(..., reduce=False)``."""
+
+    def __init__(self, world: int, rank: int, device):
+        from . import lib as L
+        import torch.distributed as dist
+        self.L, self.world = L, world
+        uid = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(L.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)  # the torch process group only carries the 128-byte id
+        self.comm = L.nccl_init(bytes(uid.cpu().tolist()), world, rank)
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending = False
+        self.buckets = 0
+
+    def reduce(self, t: torch.Tensor, offset: int, count: int):
+        """enqueue the in-place SUM all-reduce of t.view(-1)[offset : offset + count]; everything enqueued so far on the
+        current stream is ordered before it"""
+        if count <= 0:
+            return
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self.L.allreduce_bucket(self.comm, t, count, offset, stream=self.stream.cuda_stream)
+        self.pending = True
+        self.buckets += 1
+
+    def join(self):
+        """the current stream waits for every bucket enqueued so far"""
+        if self.pending:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.pending = False
+
+
 class FusedClipAdam:
     """``clip_grad_norm_(max_norm)`` + Adam (no weight decay by default) on flat buffers through the CUDA library
     (tgan_sumsq + tgan_adam_step).  CUDA only -- there is no host fallback."""
 
     def __init__(self, fp: FlatParams, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 clip: float = 0.0, world: int = 1):
+                 clip: float = 0.0, world: int = 1, reduce: bool = True):
         from . import lib as L
         self.L = L
         self.fp, self.lr, self.betas, self.eps, self.wd, self.clip, self.world = fp, lr, betas, eps, weight_decay, clip, world
+        self.reduce = reduce  # False: the gradients arrive already summed over the ranks (BucketReducer)
         self.m, self.v = torch.zeros_like(fp.flat), torch.zeros_like(fp.flat)
         self.gnorm_sq = torch.zeros(1, device=fp.flat.device)
         self.steps = 0
@@ -98,7 +138,8 @@ class FusedClipAdam:
     def step(self, lr: Optional[float] = None):
         fp, L = self.fp, self.L
         self.steps += 1
-        allreduce_gradients(fp.grad, self.world)
+        if self.reduce:
+            allreduce_gradients(fp.grad, self.world)
         self.gnorm_sq.zero_()
         L.sumsq(fp.grad, fp.grad.numel(), self.gnorm_sq)
         L.adam_step(fp.flat, fp.grad, self.m, self.v, fp.numel(), self.lr if lr is None else lr, self.betas[0],

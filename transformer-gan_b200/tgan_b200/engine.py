@@ -621,12 +621,15 @@ class TxlEngine:
     # -- backward -----------------------------------------------------------------------------------------
     def backward(self, ctx: _Ctx, dnll: Optional[torch.Tensor] = None, dlogits32: Optional[torch.Tensor] = None,
                  need_dinput: bool = False, grad_targets: Optional[Dict[str, torch.Tensor]] = None,
-                 accumulate: bool = True) -> Dict[str, torch.Tensor]:
+                 accumulate: bool = True, reducer=None) -> Dict[str, torch.Tensor]:
         """Gradients (reference layout, fp32) of sum(nll * dnll) [+ sum(logits * dlogits32)] w.r.t. every
         generator parameter.  With ``grad_targets`` ({state_dict name: fp32 tensor}, e.g. the parameters' ``.grad``)
         the gradients are ACCUMULATED into (``accumulate=False``: written to) those tensors by one kernel (no per-tensor
         allocation, no autograd accumulate nodes); otherwise fresh tensors are returned.  With need_dinput the gradient w.r.t. the soft
-        one-hot input rows is returned under the key '__dinput__' (fp32 [Q*B, VP])."""
+        one-hot input rows is returned under the key '__dinput__' (fp32 [Q*B, VP]).
+        ``reducer`` (tgan_b200.dp.BucketReducer): data-parallel runs all-reduce each layer's padded gradient block on a
+        side stream as soon as that layer's backward has been enqueued (last layer first), overlapping the exchange with
+        the layers below; the shared tensors (embedding, r_net, biases) follow at the end, before the unpack."""
         d, lay, dt = self.d, self.layout, self.dtype
         DP, NH, DIP, VP, D = d.DP, d.NH, d.DIP, d.VP, d.d_model
         Q, B, M, K, cid = ctx.Q, ctx.B, ctx.M, ctx.K, ctx.cid
@@ -723,6 +726,11 @@ class TxlEngine:
             dx = self._buf(R, DP)
             L.gemm(dkv, self.pmat, dx, M=R, N=DP, K=2 * NH, lda=2 * NH, ldb=wtld, a_off=M * B * 2 * NH,
                    b_off=wtoff + NH, aux=t, ldaux=DP, flags=L.EPI_ADD_AUX, impl=impl)
+            if reducer is not None:  # this layer's weight / bias / LayerNorm gradients are final: exchange them now
+                m0, m1 = lay.gmat[p + "Wqkv"][0], lay.gmat[p + "W2"][0] + lay.gmat[p + "W2"][1] * lay.gmat[p + "W2"][2]
+                v0, v1 = lay.vec[p + "b1"][0], lay.vec[p + "ln2_b"][0] + lay.vec[p + "ln2_b"][1]
+                reducer.reduce(gm, m0, m1 - m0)
+                reducer.reduce(gv, v0, v1 - v0)
         # ---- r_net weight gradients of all layers: dWr_all = dR_all^T pos_emb
         NL = d.n_layer * NH
         if dt == torch.float32:
@@ -748,6 +756,10 @@ class TxlEngine:
                 dsoft = self._buf(R, VP, dtype=torch.float32)
                 L.gemm(dx, self.pmat, dsoft, M=R, N=d.n_token, K=DP, ldb=eld, b_off=eoff, alpha=math.sqrt(D), impl=impl)
                 out["__dinput__"] = dsoft
+        if reducer is not None:  # shared tensors: embedding, r_net of every layer, r_w_bias / r_r_bias, output bias
+            reducer.reduce(gm, 0, lay.gmat["l0.Wqkv"][0])
+            reducer.reduce(gv, 0, lay.vec["l0.b1"][0])
+            reducer.join()
         # ---- unpack to reference-layout gradients
         if grad_targets is not None:
             desc = self._unpack_desc_for(grad_targets)

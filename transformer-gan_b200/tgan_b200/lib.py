@@ -67,6 +67,11 @@ _SIGS = {
     "tgan_bert_attn_bwd": [I, P, L, P, L, P, P, L, I, I, I, I, F, U, U, P],
     "tgan_bert_attn_jvp": [I, P, L, P, L, P, P, L, I, I, I, I, F, U, U, P],
     "tgan_sample_tokens": [P, L, P, P, P, P, L, I, I, I, I, I, I, F, F, U, U, P],
+    "tgan_nccl_load": [c_char_p],
+    "tgan_nccl_unique_id": [P],
+    "tgan_nccl_init": [P, I, I, P],
+    "tgan_allreduce_bucket": [P, P, L, I, P],
+    "tgan_nccl_destroy": [P],
 }
 EXPORTS = ["tgan_last_error", "tgan_version", "tgan_has_tcgen05", "tgan_launch_count"] + list(_SIGS)
 for _name, _sig in _SIGS.items():
@@ -320,3 +325,36 @@ def sample_tokens(logits, ids, V, *, u=None, suppress_empty=None, probs_out=None
     _call("tgan_sample_tokens", logits.data_ptr(), logits.stride(0), _ptr(u), _ptr(suppress_empty), ids.data_ptr(),
           _ptr(probs_out), 0 if probs_out is None else probs_out.stride(0), rows, V, int(exclude_bos), empty_token, mode,
           topk, top_p, temperature, seed, site, _stream())
+
+
+def nccl_load(path=None):
+    """Bind libnccl.so.2 (default: the copy torch ships / has already loaded)."""
+    if path is None:
+        cand = os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2")
+        path = cand if os.path.exists(cand) else ""
+    _call("tgan_nccl_load", path.encode() if path else None)
+
+
+def nccl_unique_id() -> bytes:
+    nccl_load()
+    buf = ctypes.create_string_buffer(128)
+    _call("tgan_nccl_unique_id", buf)
+    return buf.raw
+
+
+def nccl_init(uid: bytes, nranks: int, rank: int) -> int:
+    nccl_load()
+    comm = c_void_p()
+    _call("tgan_nccl_init", ctypes.c_char_p(uid), nranks, rank, ctypes.byref(comm))
+    return comm.value
+
+
+def allreduce_bucket(comm: int, t: torch.Tensor, count=None, offset=0, stream=None):
+    """in-place SUM all-reduce of t.view(-1)[offset : offset + count] on `stream` (raw handle; default: current stream)"""
+    n = t.numel() - offset if count is None else count
+    _call("tgan_allreduce_bucket", comm, t.data_ptr() + offset * t.element_size(), n, dtype_code(t.dtype),
+          _stream() if stream is None else stream)
+
+
+def nccl_destroy(comm: int):
+    _call("tgan_nccl_destroy", comm)
