@@ -43,13 +43,20 @@ def run(mode, graphs, world, rank, dev, data, target):
         cols = slice(rank * per, (rank + 1) * per)
         scale = 1.0  # each rank's loss.mean() over its shard; Adam's 1/world averages the summed gradient
     mems = None
+    first_grad = None
     for s in range(data.shape[0]):
         d, t = data[s][:, cols].contiguous().to(dev), target[s][:, cols].contiguous().to(dev)
         loss, mems = model(d, t, None, mems)
         (loss.mean() * scale).backward()
+        if s == 0:  # gradient of the first step (identical parameters in every mode), summed over the ranks
+            first_grad = fp.grad.clone()
+            if mode == "flat":
+                dist.all_reduce(first_grad)
+            elif mode == "single":
+                first_grad *= world  # mean over the whole batch = average of the shard means: x world = their sum
         opt.step()
     torch.cuda.synchronize()
-    return fp.flat.clone(), (0 if reducer is None else reducer.buckets)
+    return fp.flat.clone(), (0 if reducer is None else reducer.buckets), first_grad
 
 
 def main():
@@ -63,16 +70,25 @@ def main():
     target = torch.randint(2, 310, (steps, Q, B), generator=g)
     ok = True
     for graphs in (False, True):
-        flat, _ = run("flat", graphs, world, rank, dev, data, target)
-        buck, nb = run("bucket", graphs, world, rank, dev, data, target)
-        single, _ = run("single", graphs, world, rank, dev, data, target)
-        e1 = (flat - buck).abs().max().item()
-        e2 = (flat - single).abs().max().item() / single.abs().max().item()
-        same = torch.tensor([e1], device=dev)
-        dist.all_reduce(same, op=dist.ReduceOp.MAX)
+        flat, _, g_flat = run("flat", graphs, world, rank, dev, data, target)
+        flat2, _, g_flat2 = run("flat", graphs, world, rank, dev, data, target)
+        buck, nb, g_buck = run("bucket", graphs, world, rank, dev, data, target)
+        single, _, g_single = run("single", graphs, world, rank, dev, data, target)
+        rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+        # the exchanged gradient itself: bucketed == flat to fp32 rounding; both == the single-process gradient up to the
+        # bf16 effects of a different batch split (GEMM row counts / split-K partitions differ)
+        gb, gs, noise = rel(g_buck, g_flat), rel(g_flat, g_single), rel(g_flat2, g_flat)
+        # parameters after 6 clipped Adam steps: Adam divides by sqrt(v), so rounding-level gradient differences of
+        # near-zero entries grow; the run-to-run floor (flat vs flat: fp32 atomics order) is the yardstick
+        p_noise, p_buck = (flat2 - flat).abs().max().item(), (buck - flat).abs().max().item()
+        p_single = rel(flat, single)
+        stats = torch.tensor([gb, gs, noise, p_noise, p_buck, p_single], device=dev)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        gb, gs, noise, p_noise, p_buck, p_single = stats.tolist()
         if rank == 0:
-            print(f"graphs={graphs} buckets={nb} |flat - bucket|={same.item():.3e} rel |flat - single|={e2:.3e}", flush=True)
-        ok = ok and same.item() < 1e-6 and e2 < 2e-2 and nb > 0
+            print(f"graphs={graphs} buckets={nb} grad: |bucket-flat|={gb:.2e} |flat-flat'|={noise:.2e} |flat-single|={gs:.2e}  "
+                  f"params: |flat-flat'|={p_noise:.2e} |bucket-flat|={p_buck:.2e} rel |flat-single|={p_single:.2e}", flush=True)
+        ok = ok and nb > 0 and gb <= max(5 * noise, 1e-5) and gs < 2e-2 and p_buck <= max(5 * p_noise, 1e-5) and p_single < 0.1
     dist.destroy_process_group()
     if rank == 0:
         print("DP_WORKER_OK" if ok else "DP_WORKER_FAIL", flush=True)
