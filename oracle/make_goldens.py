@@ -166,21 +166,79 @@ def run_gan_case(name, shape: O.TxlShape, seed, B, dis_type, loss_type, dis_tgt_
     print("wrote", name, {k: float(v) for k, v in out.items() if k.endswith("_loss")})
 
 
+def run_gan_ppo_case(name, shape: O.TxlShape, seed, B, dis_tgt_len=16, context_len=5, chunks=2, temperature=0.8):
+    """The PPO variant of the GAN step (transformer_gan.py:184-201, :350-388) on the UNMODIFIED reference: BERT
+    discriminator with loss_type 'ppo-gp', density-ratio classifier ``dis_D`` = RelGAN_D with one representation
+    (PPO.dis_D_type 'cnn'; the reference's 'bert' branch reads self.discriminator before it exists, :140).  Calls, in
+    train.py's order (:1037-1052): "classifier_loss" (P0 initialised), "gen_loss" with update_D0, "gen_loss" without,
+    "dis_loss"."""
+    import tempfile
+    V = shape.n_token
+    bert_dir = ref_harness.tiny_bert_config_dir(os.path.join(tempfile.mkdtemp(), "bert"), V + 1)
+    cfg = ref_harness.make_gan_cfg(shape, dis_tgt_len, shape.mem_len, "bert", dis_tgt_len, shape.mem_len, context_len,
+                                   chunks, "ppo-gp", bert_path=bert_dir)
+    cfg.PPO.dis_D_type = "cnn"
+    params = O.init_params(shape, seed, dtype=torch.float32)
+    torch.manual_seed(seed)
+    model = ref_harness.build_reference_gan(cfg, V, params, dtype=torch.float32)
+    model.discriminator.load_state_dict(O.seeded_state(model.discriminator, seed + 1), strict=False)
+    model.dis_D.load_state_dict(O.seeded_state(model.dis_D, seed + 3), strict=False)
+    model.dis_D.dropout.p = 0.0  # RelGAN_D hard-codes dropout 0.25: off for a fixture
+    model.temperature = temperature
+    g = torch.Generator().manual_seed(seed + 2)
+    data = token_stream(B, dis_tgt_len, offset=555)[:dis_tgt_len].contiguous()
+    n_steps = dis_tgt_len - context_len
+    U = [torch.rand(1, B, V, generator=g) for _ in range(n_steps)]
+    alphas = [torch.rand(B, 1, 1, generator=g) for _ in range(chunks)]
+    out = {"seed": seed, "B": B, "dis_type": "bert", "loss_type": "ppo-gp", "dis_tgt_len": dis_tgt_len,
+           "context_len": context_len, "chunks": chunks, "temperature": temperature, "data": data.numpy(),
+           "U": torch.cat(U, 0).numpy(), "alpha": torch.cat(alphas, 0).view(chunks, B).numpy(), "clip": cfg.PPO.clip_param,
+           "shape": np.array([shape.n_layer, shape.n_head, shape.d_model, shape.d_inner, shape.n_token,
+                              shape.mem_len, int(shape.same_length), shape.clamp_len, int(shape.pre_lnorm)])}
+    calls = [("classifier_loss", "classifier_loss", False), ("gen_loss_d0", "gen_loss", True),
+             ("gen_loss", "gen_loss", False), ("dis_loss", "dis_loss", False)]
+    for tag, mode, upd in calls:
+        model.zero_grad()
+        with ref_harness.injected_uniform(U, alphas):
+            r = model(data, None, None, mode, update_D0=upd)
+        for k in ("dis_loss", "gen_loss", "gp_loss"):
+            if r.get(k) is not None:
+                out[f"{tag}.{k}"] = np.array(float(r[k]))
+        out[f"{tag}.P0"] = model.P0.numpy().copy()
+        owner = {"classifier_loss": model.dis_D, "dis_loss": model.discriminator}.get(mode, model.generator)
+        for k, prm in owner.named_parameters():
+            if prm.grad is not None and prm.numel() <= 40000:
+                out[f"{tag}.grad.{k}"] = prm.grad.numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, {k: float(v) for k, v in out.items() if k.endswith("_loss")})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]  # optional: regenerate just the named fixtures
     tiny = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=16)
-    run_mle_case("mle_tiny", tiny, seed=11, Q=8, B=3, nseg=4, reset_at=(2, 1))
     tiny_sl = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=12, same_length=True,
                          clamp_len=15)
-    run_mle_case("mle_tiny_samelen", tiny_sl, seed=12, Q=8, B=2, nseg=4, reset_at=(1, 0))
     real = O.TxlShape(n_layer=6, n_head=10, d_model=500, d_inner=1000, n_token=310, mem_len=24)
-    run_mle_case("mle_real", real, seed=13, Q=16, B=2, nseg=3, reset_at=(2, 1), full_mems=False)
+    # Q = 32 is the smallest segment the tcgen05 attention kernels take: this fixture drives them (and the wrap of the
+    # 64 + 32 ring) from the model-level golden test
+    real_q32 = O.TxlShape(n_layer=6, n_head=10, d_model=500, d_inner=1000, n_token=310, mem_len=64)
     gen = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=64, same_length=True)
-    run_generate_case("generate_tiny", gen, seed=14, B=2, T=12, temperature=0.7)
     gan = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=16)
-    run_gan_case("gan_bert_tiny", gan, seed=15, B=3, dis_type="bert", loss_type="wgan-gp")
-    run_gan_case("gan_cnn_tiny", gan, seed=16, B=2, dis_type="cnn", loss_type="rsgan")
+    cases = {
+        "mle_tiny": lambda n: run_mle_case(n, tiny, seed=11, Q=8, B=3, nseg=4, reset_at=(2, 1)),
+        "mle_tiny_samelen": lambda n: run_mle_case(n, tiny_sl, seed=12, Q=8, B=2, nseg=4, reset_at=(1, 0)),
+        "mle_real": lambda n: run_mle_case(n, real, seed=13, Q=16, B=2, nseg=3, reset_at=(2, 1), full_mems=False),
+        "mle_real_q32": lambda n: run_mle_case(n, real_q32, seed=18, Q=32, B=2, nseg=4, reset_at=(3, 1), full_mems=False),
+        "generate_tiny": lambda n: run_generate_case(n, gen, seed=14, B=2, T=12, temperature=0.7),
+        "gan_bert_tiny": lambda n: run_gan_case(n, gan, seed=15, B=3, dis_type="bert", loss_type="wgan-gp"),
+        "gan_cnn_tiny": lambda n: run_gan_case(n, gan, seed=16, B=2, dis_type="cnn", loss_type="rsgan"),
+        "gan_ppo_tiny": lambda n: run_gan_ppo_case(n, gan, seed=17, B=3),
+    }
+    for name, fn in cases.items():
+        if not only or name in only:
+            fn(name)
 
 
 if __name__ == "__main__":

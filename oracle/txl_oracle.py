@@ -279,7 +279,7 @@ def generate_gumbel(data, temperature, mems, p, shape: TxlShape, U: torch.Tensor
 # ----------------------------------------------------------------------------------------------
 def sample_fake_chunks(data: torch.Tensor, p, shape_gen: TxlShape, temperature: float, noise: List[torch.Tensor],
                        tgt_len: int, context_len: int, sample_chunks_mem: int, truncate_backprop: bool = False,
-                       margins: Optional[List[torch.Tensor]] = None):
+                       margins: Optional[List[torch.Tensor]] = None, hard_inputs: bool = False):
     """Replays the generator side of one 'gen_loss'/'dis_loss' call.  ``shape_gen.mem_len`` must be
     DISCRIMINATOR.mem_len (the call runs under reset_length(1, mem_len), transformer_gan.py:251).
     ``noise[k]`` is the uniform tensor [1,B,V] consumed by the k-th forward_generate_gumbel call.
@@ -300,7 +300,7 @@ def sample_fake_chunks(data: torch.Tensor, p, shape_gen: TxlShape, temperature: 
             if ind < context_len:
                 seq.append(F.one_hot(data[ind], V).to(p["r_w_bias"].dtype))             # :304-306
                 continue
-            if truncate_backprop or ind == cs:
+            if truncate_backprop or ind == cs or hard_inputs:   # :311 ('classifier' feeds hard ids)
                 inp = seq[-1].argmax(-1)[None, :].detach()                            # :315
             else:
                 inp = seq[-1][None]                                                   # :319
@@ -328,6 +328,9 @@ def adv_losses(d_real: torch.Tensor, d_fake: torch.Tensor, loss_type: str):
     if "rsgan" in loss_type:                                            # experiment_cnn.yml default
         bce = F.binary_cross_entropy_with_logits
         return bce(d_fake - d_real, torch.ones_like(d_fake)), bce(d_real - d_fake, torch.ones_like(d_real))
+    if "ppo" in loss_type:                                              # 'ppo' / 'ppo-gp', utils/helpers.py:131-136
+        W = (d_fake.shape[0] * F.softmax(d_fake.detach(), dim=0)).detach()
+        return -d_fake.mean(), (W * d_fake - d_real).mean()
     raise NotImplementedError(loss_type)
 
 
@@ -354,30 +357,60 @@ def gradient_penalty(disc_on_onehot, real_1h: torch.Tensor, fake: torch.Tensor, 
 def gan_step(mode: str, data: torch.Tensor, p, shape_gen: TxlShape, disc_on_onehot, extra_col: int, loss_type: str,
              temperature: float, noise: List[torch.Tensor], alphas: List[torch.Tensor], tgt_len: int, context_len: int,
              sample_chunks_mem: int, batch_chunk: int = 1, gen_loss_factor: float = 1.0, dis_loss_factor: float = 1.0,
-             embed=None, disc_on_embeds=None):
+             embed=None, disc_on_embeds=None, ppo: Optional[dict] = None):
     """One ``"dis_loss"`` or ``"gen_loss"`` call of TransformerGAN.forward with ``backprop_outside`` (the shipped
     setting): samples ``sample_chunks_mem`` chunks with the generator, scores real / fake with ``disc_on_onehot``
     ([B, T, V + extra_col] -> logits [B or B*rep]), back-propagates each chunk's scaled loss immediately
     (:487-502) and returns the detached sums exactly as the reference does (:515-531).
-    ``extra_col`` = 1 for the BERT discriminator (its vocabulary has one more id, :396-399), 0 for the CNN one."""
+    ``extra_col`` = 1 for the BERT discriminator (its vocabulary has one more id, :396-399), 0 for the CNN one.
+
+    PPO variants (loss_type 'ppo' / 'ppo-gp'; :184-201, :350-388): ``ppo`` = {"dis_D": callable on sequence-major
+    [T, B] ids or [T, B, V] rows -> logits (``dis_D_forward``), "P0": tensor or None (the module's ``self.P0``
+    state; updated in place under the key), "update_D0": bool, "clip": PPO.clip_param}.  ``mode`` may then also be
+    ``"classifier_loss"``: the density-ratio classifier's BCE update on real / sampled chunks (hard-id inputs, :311)."""
     V = shape_gen.n_token
     share = batch_chunk * sample_chunks_mem
     margins: List[torch.Tensor] = []
     chunks = sample_fake_chunks(data, p, shape_gen, temperature, noise, tgt_len, context_len, sample_chunks_mem,
-                                margins=margins)
+                                margins=margins, hard_inputs="classifier" in mode)
     g_sum = d_sum = gp_sum = 0.0
     ids = []
+
+    def d0_ratio(fake_chunk):                                                              # :351-354 / :377-380
+        with torch.no_grad():
+            D0 = torch.sigmoid(ppo["dis_D"](fake_chunk))
+            return (1.0 - D0) / torch.clamp(D0, min=1e-7)
+
     for k, (cs, fake) in enumerate(chunks):
         T = fake.shape[0]
         if mode == "dis_loss":
             fake = fake.detach()
         ids.append(fake.detach().argmax(-1))
+        if "classifier" in mode:                                                           # :350-372
+            if ppo["P0"] is None:
+                ppo["P0"] = d0_ratio(fake)
+            n = ppo["P0"].shape[0]
+            err = F.binary_cross_entropy(torch.sigmoid(ppo["dis_D"](data[cs:cs + T])), fake.new_ones(n)) + \
+                F.binary_cross_entropy(torch.sigmoid(ppo["dis_D"](fake.detach())), fake.new_zeros(n))
+            (err / share).backward()
+            continue
+        ratio = None
+        if mode == "gen_loss" and ppo is not None and "ppo" in loss_type:                  # :375-388
+            if ppo["P0"] is None or ppo.get("update_D0", False):
+                ppo["P0"] = d0_ratio(fake)
+            D1 = torch.sigmoid(ppo["dis_D"](fake))
+            ratio = (1.0 - D1) / torch.clamp(D1 * ppo["P0"], min=1e-7)
+            ratio_clipped = torch.clamp(ratio, 1.0 - ppo["clip"], 1.0 + ppo["clip"])
         real = data[cs:cs + T].transpose(0, 1)                                            # [B, T]
         fake_bt = fake.transpose(0, 1)
         if extra_col:
             fake_bt = torch.cat([fake_bt, fake_bt.new_zeros(*fake_bt.shape[:-1], extra_col)], -1)
         real_1h = F.one_hot(real, V + extra_col).to(fake_bt.dtype)
-        g_loss, d_loss = adv_losses(disc_on_onehot(real_1h), disc_on_onehot(fake_bt), loss_type)
+        d_real, d_fake = disc_on_onehot(real_1h), disc_on_onehot(fake_bt)
+        if ratio is not None:                                                              # :419-424 / :456-461
+            surr1, surr2 = ratio * d_fake, ratio_clipped * d_fake
+            d_fake = torch.where(d_fake > 0, torch.min(surr1, surr2), torch.max(surr1, surr2))
+        g_loss, d_loss = adv_losses(d_real, d_fake, loss_type)
         g_sum += g_loss.detach()
         d_sum += d_loss.detach()
         if mode == "dis_loss":
@@ -389,6 +422,8 @@ def gan_step(mode: str, data: torch.Tensor, p, shape_gen: TxlShape, disc_on_oneh
         else:
             (g_loss * gen_loss_factor / share).backward()
     out = {"ids": torch.cat(ids, 0), "margins": torch.stack(margins, 0) if margins else None}
+    if "classifier" in mode:
+        return out
     if mode == "dis_loss":
         out["dis_loss"] = dis_loss_factor * d_sum / sample_chunks_mem
         if "gp" in loss_type:
