@@ -44,8 +44,11 @@ def _cfg(shape, z, bert_dir):
               PPO=ns(dis_D_type="bert", dis_D_num_rep=1, clip_param=0.4))
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("name", ["gan_bert_tiny", "gan_cnn_tiny"])
-def test_gan_step_matches_reference_golden(name, tmp_path):
+def test_gan_step_matches_reference_golden(name, lanes, tmp_path):
+    """lanes = 2: the sampling chain split into two concurrent column lanes (separate streams / engines, lane-private
+    gradient staging folded into .grad) must give the same ids, losses and gradients as the single chain."""
     import transformer_gan as TG
     z, shape = GU.load(name)
     V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
@@ -63,6 +66,7 @@ def test_gan_step_matches_reference_golden(name, tmp_path):
     model = model.cuda().train()
     model.generator.compute_dtype = torch.float32  # fp32 parity mode (1e-4)
     model.temperature = float(z["temperature"])
+    model.sample_lanes, model.sample_lane_min_batch = lanes, 1
     data = torch.from_numpy(z["data"]).cuda()
     U = torch.from_numpy(z["U"]).cuda()
     alpha = torch.from_numpy(z["alpha"]).cuda()
@@ -144,6 +148,7 @@ def test_gan_step_bf16_eager_and_graphed_match_reference(name, tmp_path):
     UNMODIFIED reference's goldens; sampled ids equal to the oracle's along every sequence up to the first step whose
     top-2 (logit + g) margin is inside the tolerance; the graph replay reproduces the eager bf16 call."""
     model, z, shape = _build_gan(name, tmp_path, torch.bfloat16)
+    model.sample_lanes, model.sample_lane_min_batch = 2, 1  # the benchmarked path: two concurrent sampling lanes
     V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
     data = torch.from_numpy(z["data"]).cuda()
     U = torch.from_numpy(z["U"]).cuda()
@@ -206,3 +211,79 @@ def test_gan_step_bf16_eager_and_graphed_match_reference(name, tmp_path):
                 err = (g_g[k] - want).norm().item()
                 assert err <= 2e-2 * want.norm().item() + 1e-6, (mode, rep, k, err, want.norm().item())
         assert any(k[0] == mode for k in model._gan_graphs), "the adversarial phase was not captured"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gan_ppo_variant_matches_reference_golden(dtype, tmp_path):
+    """The PPO variant (loss type 'ppo-gp', density-ratio classifier dis_D = RelGAN_D): 'classifier_loss', 'gen_loss'
+    with and without update_D0, 'dis_loss' -- against the golden of the UNMODIFIED reference (transformer_gan.py:133-153,
+    :184-201, :350-388).  fp32 mode at 1e-3; bf16 at 1e-2 when the sampled ids coincide."""
+    import transformer_gan as TG
+    from test_gan_golden import PPO_CALLS
+    z, shape = GU.load("gan_ppo_tiny")
+    V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
+    bert_dir = str(tmp_path / "bert")
+    os.makedirs(bert_dir, exist_ok=True)
+    json.dump(dict(O.TINY_BERT, vocab_size=V + 1), open(os.path.join(bert_dir, "config.json"), "w"))
+    cfg = _cfg(shape, z, bert_dir)
+    cfg.PPO.dis_D_type, cfg.PPO.clip_param = "cnn", float(z["clip"])
+    torch.manual_seed(0)
+    model = TG.TransformerGAN(cfg, _Vocab(V))
+    sd = {k: v.clone() for k, v in O.init_params(shape, int(z["seed"])).items()}
+    sd["crit.out_layers.0.weight"] = sd["word_emb.emb_layers.0.weight"]
+    model.generator.load_state_dict(sd, strict=False)
+    model.discriminator.load_state_dict(O.seeded_state(model.discriminator, int(z["seed"]) + 1), strict=False)
+    model.dis_D.load_state_dict(O.seeded_state(model.dis_D, int(z["seed"]) + 3), strict=False)
+    model.dis_D.dropout.p = 0.0
+    model = model.cuda().train()
+    model.generator.compute_dtype = dtype
+    model.temperature = float(z["temperature"])
+    model.use_cuda_graphs = True  # must be ignored for the PPO variants (host-side P0 / update_D0 state)
+    data = torch.from_numpy(z["data"]).cuda()
+    U = torch.from_numpy(z["U"]).cuda()
+    alpha = torch.from_numpy(z["alpha"]).cuda()
+    chunk_of = {"k": 0}
+    model.gumbel_noise_source = lambda step, shp: U[step:step + 1]
+
+    def alpha_src(b):
+        a = alpha[chunk_of["k"] % chunks]
+        chunk_of["k"] += 1
+        return a
+    model.gp_alpha_source = alpha_src
+    fp32 = dtype == torch.float32
+    tol = 1e-3 if fp32 else 1e-2
+    ids_ref = None
+    for tag, mode, upd in PPO_CALLS:
+        model.zero_grad(set_to_none=True)
+        chunk_of["k"] = 0
+        r = model(data, None, None, mode, update_D0=upd)
+        torch.cuda.synchronize()
+        if ids_ref is None:
+            ids_ref = model.last_sampled_ids.clone()  # same noise, same weights: every call samples the same ids
+        same_ids = torch.equal(model.last_sampled_ids, ids_ref)
+        assert same_ids or not fp32
+        if mode == "classifier_loss":
+            assert all(r[k] is None for k in ("mle", "gen_loss", "dis_loss"))
+        if not same_ids:
+            continue
+        want_P0 = torch.from_numpy(z[f"{tag}.P0"]).cuda()
+        assert torch.allclose(model.P0.float(), want_P0, rtol=10 * tol, atol=1e-4), (tag, model.P0, want_P0)
+        for key in ("dis_loss", "gen_loss", "gp_loss"):
+            if f"{tag}.{key}" in z.files:
+                want, got = float(z[f"{tag}.{key}"]), float(r[key])
+                assert abs(got - want) <= tol * max(1.0, abs(want)), (tag, key, got, want)
+        owner = {"classifier_loss": model.dis_D, "dis_loss": model.discriminator}.get(mode, model.generator)
+        named = dict(owner.named_parameters())
+        checked = 0
+        for k in z.files:
+            pre = f"{tag}.grad."
+            if not k.startswith(pre) or k[len(pre):] == "crit.out_layers.0.weight":
+                continue
+            want = torch.from_numpy(z[k]).double()
+            g = named[k[len(pre):]].grad
+            got = g.detach().cpu().double() if g is not None else torch.zeros_like(want)
+            err = (got - want).norm().item()
+            assert err <= (2e-2 if fp32 else 0.15) * want.norm().item() + 2e-6, (tag, k, err, want.norm().item())
+            checked += 1
+        assert checked >= 5
+    assert not model._gan_graphs

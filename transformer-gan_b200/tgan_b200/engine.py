@@ -284,6 +284,12 @@ class TxlEngine:
         self._es = 2 if dtype == torch.bfloat16 else 4
         self.pack_epoch = 0        # bumped whenever the packed parameter copies are rewritten
         self.kv_cache_max_q = 8    # calls with at most this many new rows keep / reuse the projected-K/V cache
+        # Calls with at most this many query rows (the single-token steps of the sampling chain: R = batch) are a
+        # string of launch-latency-bound kernels on a fraction of the SMs: their weight-gradient GEMMs (off the
+        # backward's critical path) and the K/V projection of the forward run on a side stream, concurrently with the
+        # dgrad chain.  Captured in a CUDA graph the fork / join events become plain dependency edges.
+        self.side_stream_max_rows = 8192
+        self._side = None
 
     # -- parameters ---------------------------------------------------------------------------------------
     def bind_params(self, params: Dict[str, torch.Tensor]):
@@ -370,6 +376,11 @@ class TxlEngine:
         if getattr(self, "_graph_pool", None) is None:
             self._graph_pool = torch.cuda.graph_pool_handle()
         return self._graph_pool
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def _site(self, call_id: int, local: int) -> int:
         return call_id * 256 + local
@@ -534,12 +545,20 @@ class TxlEngine:
             q = self._buf(R, NH)
             r = r_all[:, l * NH:(l + 1) * NH]  # view: row pitch n_layer * NH
             x_base = l * slab_elems
-            L.gemm(slabs, self.pmat, q, M=R, N=NH, K=DP, lda=DP, ldb=wld, a_off=cur_off[l], b_off=woff, impl=self.impl)
             if use_cache:
                 kv, kv_off = ring.kv["buf"], (l * C + ctx.x_segs[0][0]) * B * 2 * NH
-                L.gemm(slabs, self.pmat, kv, M=(w + Q - kv_from) * B, N=2 * NH, K=DP, lda=DP, ldb=wld, ldc=2 * NH,
-                       a_off=x_base + kv_from * B * DP, b_off=woff + NH * wld, c_off=(l * C + kv_from) * B * 2 * NH,
-                       impl=self.impl)
+                side = self._side_stream() if R <= self.side_stream_max_rows else None
+                main = torch.cuda.current_stream()
+                if side is not None:  # the K/V projection of the new rows runs beside the Q projection
+                    side.wait_stream(main)
+                with torch.cuda.stream(side if side is not None else main):
+                    L.gemm(slabs, self.pmat, kv, M=(w + Q - kv_from) * B, N=2 * NH, K=DP, lda=DP, ldb=wld, ldc=2 * NH,
+                           a_off=x_base + kv_from * B * DP, b_off=woff + NH * wld, c_off=(l * C + kv_from) * B * 2 * NH,
+                           impl=self.impl)
+            L.gemm(slabs, self.pmat, q, M=R, N=NH, K=DP, lda=DP, ldb=wld, a_off=cur_off[l], b_off=woff, impl=self.impl)
+            if use_cache:
+                if side is not None:
+                    main.wait_stream(side)
             else:
                 kv, kv_off = self._buf(KR, 2 * NH), 0
                 row = 0
@@ -646,11 +665,22 @@ class TxlEngine:
         gv.zero_()
         gm.zero_()
 
+        # small calls: weight-gradient GEMMs on the side stream (see side_stream_max_rows); their operands are kept
+        # alive in `keep` until the join at the end -- the caching allocator would otherwise hand a freed block to the
+        # next allocation on the main stream while the side stream still reads it
+        side = self._side_stream() if (R <= self.side_stream_max_rows and reducer is None) else None
+        main = torch.cuda.current_stream()
+        keep = []
+
         def wgrad(name, dY, X, rows, n_out, k_in, *, dy_off=0, x_off=0, ldy=None, ldx=None, row_off=0):
             """gmat[name][row_off : row_off+n_out, :k_in] (+)= dY^T X"""
             goff, _, gld = lay.gmat[name]
-            L.gemm(dY, X, gm, transA=True, transB=False, M=n_out, N=k_in, K=rows, lda=ldy, ldb=ldx, ldc=gld,
-                   a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld, flags=L.EPI_ACCUM, impl=impl)
+            if side is not None:
+                side.wait_stream(main)  # everything enqueued so far (the producers of dY, the zeroing of gm)
+                keep.append((dY, X))
+            with torch.cuda.stream(side if side is not None else main):
+                L.gemm(dY, X, gm, transA=True, transB=False, M=n_out, N=k_in, K=rows, lda=ldy, ldb=ldx, ldc=gld,
+                       a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld, flags=L.EPI_ACCUM, impl=impl)
 
         # ---- loss head
         dl = self._buf(RT, VP)
@@ -731,6 +761,9 @@ class TxlEngine:
                 v0, v1 = lay.vec[p + "b1"][0], lay.vec[p + "ln2_b"][0] + lay.vec[p + "ln2_b"][1]
                 reducer.reduce(gm, m0, m1 - m0)
                 reducer.reduce(gv, v0, v1 - v0)
+        if side is not None:
+            main.wait_stream(side)
+            keep.clear()
         # ---- r_net weight gradients of all layers: dWr_all = dR_all^T pos_emb
         NL = d.n_layer * NH
         if dt == torch.float32:

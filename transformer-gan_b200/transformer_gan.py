@@ -24,9 +24,13 @@ Differences from the reference, all numerically neutral:
     detaches it, :346-347);
   * Gumbel noise comes from the device-side counter RNG unless ``gumbel_noise_source`` is set (parity tests inject the
     reference's uniform draws); the GP interpolation weights likewise honour ``gp_alpha_source``.
-The PPO variants (``dis_D``, ``"classifier"`` loss, :184-201, :351-388) are listed as "next" in SURVEY.md section 8f and
-raise ``NotImplementedError`` here.
+The PPO variants (loss type 'ppo' / 'ppo-gp': the density-ratio classifier ``dis_D``, the ``"classifier_loss"`` phase, the
+clipped-ratio generator target, :133-153, :184-201, :350-388) keep their host-side state (``P0``, ``update_D0``) and
+are therefore launched from the host rather than replayed as a graph; their arithmetic is torch on [B]-sized tensors
+plus the same generator / discriminator kernels.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -47,8 +51,11 @@ class TransformerGAN(nn.Module):
         self.ntokens = len(vocab)
         self.generator = MemTransformerLM(cfg, self.ntokens, vocab.vec_len)
         dcfg = cfg.DISCRIMINATOR
-        if "ppo" in dcfg.CNN.loss_type or "ppo" in dcfg.BERT.loss_type:
-            raise NotImplementedError("PPO discriminator variants are not part of the accelerated path yet")
+        self.cfg = cfg
+        self.ppo = "ppo" in dcfg.CNN.loss_type or "ppo" in dcfg.BERT.loss_type
+        if self.ppo:  # density-ratio classifier of the PPO variants (transformer_gan.py:133-153), registered before
+            self.dis_D = self._create_dis_D(cfg)  # the discriminator like the reference does (state_dict order)
+            self.P0 = None
         if dcfg.type == "bert":
             self.discriminator = self.create_bert_model(dcfg.BERT.model_path, dcfg.BERT.loss_type, dcfg.BERT.model_type,
                                                         dcfg.BERT.random_weights)
@@ -73,6 +80,11 @@ class TransformerGAN(nn.Module):
         self.disc_tf32 = True  # TF32 tensor-core GEMMs for the discriminator when the generator computes in bf16
         self.use_own_bert = True   # frozen-encoder BERT discriminator on the repo's kernels (else: HuggingFace modules)
         self._bert_engine = None
+        # the sampling chain runs as this many concurrent column lanes (see _lane_slices); lanes narrower than
+        # sample_lane_min_batch sequences are not worth a stream
+        self.sample_lanes = 2
+        self.sample_lane_min_batch = 64
+        self._lane_stream_objs = []
 
     # ------------------------------------------------------------------------------------------------ discriminator
     def create_bert_model(self, model_name_or_path, loss_type, model_type=None, random_weights=False):
@@ -97,11 +109,41 @@ class TransformerGAN(nn.Module):
             model = BertForSequenceClassification.from_pretrained(model_name_or_path, config=config, cache_dir=None)
         return model.bert if loss_type == "mmd" else model
 
-    def calculate_unfreeze_idx(self, cfg):
+    def _create_dis_D(self, cfg):
+        """transformer_gan.py:133-149.  (For dis_D_type 'bert' the reference computes the unfreeze list from
+        ``self.discriminator`` before that attribute exists, :140; here it is computed on dis_D itself.)"""
+        dcfg = cfg.DISCRIMINATOR
+        if cfg.PPO.dis_D_type == "bert":
+            dis_D = self.create_bert_model(dcfg.BERT.model_path, dcfg.BERT.loss_type, dcfg.BERT.model_type)
+            dis_D.unfreeze_idx = self.calculate_unfreeze_idx(cfg, dis_D)
+            return dis_D
+        if cfg.PPO.dis_D_type == "cnn":
+            return RelGAN_D(dcfg.CNN.embed_dim, dcfg.tgt_len, cfg.PPO.dis_D_num_rep, self.ntokens, 1, cfg=cfg)
+        raise NotImplementedError(cfg.PPO.dis_D_type)
+
+    def dis_D_forward(self, data):
+        """Logits of the density-ratio classifier on a sequence-major chunk: [T, B] ids or [T, B, V] one-hot-ish rows
+        (transformer_gan.py:184-201).  The BERT variant looks hard ids up (argmax: no gradient to the generator), the
+        CNN variant consumes the rows themselves (the PPO ratio is differentiable w.r.t. the samples)."""
+        data = data.transpose(0, 1)
+        if self.cfg.PPO.dis_D_type == "bert":
+            if data.dim() == 3:
+                data = data.argmax(dim=-1)
+            return self._bert_logit(self.dis_D.bert.embeddings.word_embeddings.weight[data], self.dis_D)
+        if data.dim() == 2:
+            data = self._one_hot(data)
+        return self.dis_D(data)
+
+    def _ppo_P0(self, fake):
+        with torch.no_grad():
+            D0 = torch.sigmoid(self.dis_D_forward(fake))
+            return (1.0 - D0) / torch.clamp(D0, min=1e-7)
+
+    def calculate_unfreeze_idx(self, cfg, module=None):
         """Indices (in ``named_parameters`` order) of the discriminator tensors that train (transformer_gan.py:568-585)."""
         frozen_layers = cfg.DISCRIMINATOR.BERT.freeze_layers
         idx, layers = [], []
-        for i, (name, _) in enumerate(self.discriminator.named_parameters()):
+        for i, (name, _) in enumerate((module if module is not None else self.discriminator).named_parameters()):
             in_layer = name.startswith("bert.encoder.layer")
             if in_layer:
                 layers.append(name.split(".")[3])
@@ -115,11 +157,11 @@ class TransformerGAN(nn.Module):
     def _bert_embedding_matrix(self):
         return self.discriminator.bert.embeddings.word_embeddings.weight
 
-    def _bert_logit(self, inputs_embeds):
+    def _bert_logit(self, inputs_embeds, m=None):
         """Logit column 0 of BertForSequenceClassification(inputs_embeds=...) (transformer_gan.py:403-416), calling the
         sub-modules directly: with no padding the all-ones attention mask HuggingFace builds adds exactly 0.0 to every
         score, and its construction (a host scalar copied to the device) cannot be captured in a CUDA graph."""
-        m = self.discriminator
+        m = self.discriminator if m is None else m
         bert = m.bert
         h = bert.embeddings(inputs_embeds=inputs_embeds)
         h = bert.encoder(h, attention_mask=None)
@@ -212,49 +254,116 @@ class TransformerGAN(nn.Module):
     def _one_hot(self, ids):
         return torch.zeros(*ids.shape, self.ntokens, dtype=torch.float32, device=ids.device).scatter_(-1, ids[..., None], 1.0)
 
+    def _lane_slices(self, B):
+        """Batch-column ranges of the sampling lanes.  The single-token steps of the chain are launch-latency-bound
+        kernels on a fraction of the SMs, and sequences are independent: with ``sample_lanes`` > 1 the batch is cut
+        into that many column ranges whose chains run on separate streams (separate engines: private scratch, K/V cache
+        and noise stream), so their kernels overlap -- in a captured graph as parallel branches."""
+        n = max(1, min(int(self.sample_lanes), B // max(1, int(self.sample_lane_min_batch))))
+        per = (B + n - 1) // n
+        return [(lo, min(B, lo + per)) for lo in range(0, B, per)]
+
+    def _lane_streams(self, n, device):
+        while len(self._lane_stream_objs) < n - 1:
+            self._lane_stream_objs.append(torch.cuda.Stream(device=device))
+        return [None] + self._lane_stream_objs[:n - 1]  # lane 0 runs on the caller's stream
+
     def _sample_chunks(self, data, with_grad):
         """Yields ``(chunk_start, chunk_end, fake_chunk [len, B, V])`` for each of the ``sample_chunks_mem`` pieces of
         the ``DISCRIMINATOR.tgt_len`` sequence (transformer_gan.py:273-349).  The first chunk starts with the
         ``context_len`` real tokens as one-hot rows; the gradient chain inside a chunk is the soft one-hot fed back as
         the next input, and each chunk's first generated token restarts from a hard id."""
         dcfg, gen = self.cfg.DISCRIMINATOR, self.generator
-        mems = None
+        B = data.shape[1]
+        lanes = self._lane_slices(B) if data.is_cuda else [(0, B)]
+        nl = len(lanes)
+        streams = self._lane_streams(nl, data.device) if nl > 1 else [None]
+        main = torch.cuda.current_stream() if data.is_cuda else None
+        cols = [data[:, lo:hi] for lo, hi in lanes]
+        mems = [None] * nl
+
+        def on_lane(k):
+            return torch.cuda.stream(streams[k]) if streams[k] is not None else contextlib.nullcontext()
+
+        def fork():
+            for st in streams[1:]:
+                st.wait_stream(main)
+
+        def join():
+            for st in streams[1:]:
+                main.wait_stream(st)
+
+        fork()
         if dcfg.context_len > 1:
             with torch.no_grad():
-                _, mems = gen.forward_generate(data[:dcfg.context_len - 1], mems)
+                for k in range(nl):
+                    with on_lane(k):
+                        _, mems[k] = gen.forward_generate(cols[k][:dcfg.context_len - 1], mems[k], lane=k)
         chunk = dcfg.tgt_len // dcfg.sample_chunks_mem
-        seq, ids, step = [], [], 0
+        seq = [[] for _ in range(nl)]
+        ids, step = [], 0
         for cs in range(0, dcfg.tgt_len, chunk):
             ce = min(cs + chunk, dcfg.tgt_len)
             for pos in range(cs, ce):
                 if pos < dcfg.context_len:
-                    seq.append(self._one_hot(data[pos]))
+                    for k in range(nl):
+                        with on_lane(k):
+                            seq[k].append(self._one_hot(cols[k][pos]))
                     continue
-                prev = seq[-1]
-                hard = prev.argmax(dim=-1)[None, :].detach()
-                inp = hard if (dcfg.truncate_backprop or pos == cs or not with_grad) else prev[None]
-                noise = None if self.gumbel_noise_source is None else self.gumbel_noise_source(step, (1,) + tuple(prev.shape))
-                st, mems = gen.forward_generate_gumbel(inp, self.temperature, mems, noise=noise)
-                seq.append(st[0])
-                ids.append(st[0].detach().argmax(dim=-1))
+                noise = None
+                if self.gumbel_noise_source is not None:
+                    noise = self.gumbel_noise_source(step, (1, B, self.ntokens))
+                    if nl > 1:
+                        join()   # whatever produced the injected noise ran on the caller's stream
+                        fork()
+                step_ids = []
+                for k, (lo, hi) in enumerate(lanes):  # lanes alternate step by step: their launches (and, in the
+                    with on_lane(k):                  # backward, their autograd nodes) interleave
+                        prev = seq[k][-1]
+                        hard = prev.argmax(dim=-1)[None, :].detach()
+                        inp = hard if (dcfg.truncate_backprop or pos == cs or not with_grad) else prev[None]
+                        st, mems[k] = gen.forward_generate_gumbel(inp, self.temperature, mems[k],
+                                                                  noise=None if noise is None else noise[:, lo:hi],
+                                                                  lane=k)
+                        seq[k].append(st[0])
+                        step_ids.append(st[0].detach().argmax(dim=-1))
+                ids.append(step_ids)
                 step += 1
-            if len(seq) == chunk + 1:  # later chunks carry the previous chunk's last token only as the seed
-                seq = seq[1:]
-            yield cs, ce, torch.stack(seq, 0)
-            seq = [seq[-1].detach()]
-        self.last_sampled_ids = torch.stack(ids, 0) if ids else None
+            parts = []
+            for k in range(nl):
+                with on_lane(k):
+                    if len(seq[k]) == chunk + 1:  # later chunks carry the previous chunk's last token only as the seed
+                        seq[k] = seq[k][1:]
+                    part = torch.stack(seq[k], 0)
+                    if streams[k] is not None:
+                        part.record_stream(main)
+                    parts.append(part)
+                    seq[k] = [seq[k][-1].detach()]
+            join()
+            yield cs, ce, (parts[0] if nl == 1 else torch.cat(parts, 1))
+            fork()
+        join()
+        if ids:
+            for row in ids:
+                for k, t in enumerate(row):
+                    if streams[k] is not None:
+                        t.record_stream(main)
+            self.last_sampled_ids = torch.stack([r[0] if nl == 1 else torch.cat(r, 0) for r in ids], 0)
+        else:
+            self.last_sampled_ids = None
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, data, target, reset_mems, train_loss, mems=None, status_vec=None, update_D0=False):
         out = {"mle": None, "gen_loss": None, "dis_loss": None, "mems": None}
         if status_vec is not None or self.cfg.TRAIN.append_note_status:
             raise NotImplementedError("append_note_status is off in every shipped config and not accelerated")
-        if "classifier" in train_loss:
-            raise NotImplementedError("the PPO 'classifier' phase is not part of the accelerated path yet")
+        if "classifier" in train_loss and not self.ppo:
+            raise AttributeError("'classifier' phase without a PPO loss type: the model has no dis_D")
         if "mle" in train_loss:
             out["mle"], out["mems"] = self.generator(data, target, reset_mems, mems)
-        if "gen" not in train_loss and "dis" not in train_loss:
+        if "gen" not in train_loss and "dis" not in train_loss and "classifier" not in train_loss:
             return out
+        self._update_D0 = bool(update_D0)
         # In bf16 mode the discriminator's GEMMs (HuggingFace BERT / RelGAN_D: library code, fp32 tensors) run on the
         # tensor cores as TF32 -- more mantissa than the generator's own bf16 operands; fp32 mode keeps them exact.
         tf32 = self.disc_tf32 and gen_is_bf16(self.generator)
@@ -262,8 +371,9 @@ class TransformerGAN(nn.Module):
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev_tf32
         try:
             injected = self.gumbel_noise_source is not None or self.gp_alpha_source is not None
+            # the PPO variants carry host-side state between calls (P0, update_D0): launched from the host
             if (self.use_cuda_graphs and data.is_cuda and (not injected or self.sources_graph_safe)
-                    and self.cfg.DISCRIMINATOR.backprop_outside):
+                    and self.cfg.DISCRIMINATOR.backprop_outside and not self.ppo):
                 out.update(self._gan_phase_graphed(data, train_loss))
             else:
                 out.update(self._gan_phase(data, train_loss))
@@ -307,10 +417,14 @@ class TransformerGAN(nn.Module):
             # descriptor table staged outside the capture; the entry owns it for the graph's lifetime (the captured
             # unpack kernel reads it at every replay -- the engine's cache may evict its own reference)
             entry.desc = eng._unpack_desc_for({n: pd[n].grad for n in names})
+            # ... and so are the tables of the concurrent lanes' engines (created by the eager warm-up call)
+            entry.lane_descs = [e._unpack_desc_for(gen._lane_grads[k]["t"]) for k, e in gen._lane_engines.items()
+                                if k in gen._lane_grads]
             entry.data, entry.tau = data.clone(), torch.ones(1, dtype=torch.float32, device=data.device)
             entry.grad_ptrs = tuple(t.data_ptr() for t in grads)
             ctr = L.step_counter(data.device)
-            eng.invalidate()  # the parameter re-pack must be part of the graph
+            for e in gen._all_engines():
+                e.invalidate()  # the parameter re-pack (of every lane's engine) must be part of the graph
             saved_tau, self.temperature = self.temperature, entry.tau
             import gc
             gc.collect()  # no autograd graph of the eager warm-up call (built on another stream) may survive into the capture
@@ -323,7 +437,8 @@ class TransformerGAN(nn.Module):
                     entry.out = self._gan_phase(entry.data, train_loss)
             finally:
                 self.temperature = saved_tau
-                eng.invalidate()
+                for e in gen._all_engines():
+                    e.invalidate()
             entry.graph, entry.n = g, L.launch_count() - n0
             self._gan_graphs[key] = entry
         entry = self._gan_graphs[key]
@@ -334,7 +449,8 @@ class TransformerGAN(nn.Module):
         entry.tau.fill_(float(self.temperature))
         entry.graph.replay()
         L.note_graph_replay(entry.n)
-        eng.pack_epoch += 1
+        for e in gen._all_engines():
+            e.pack_epoch += 1
         return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in entry.out.items()}
 
     def _gan_phase(self, data, train_loss):
@@ -346,6 +462,8 @@ class TransformerGAN(nn.Module):
             raise NotImplementedError(dcfg.type)
         train_dis = "dis" in train_loss
         train_gen = "gen" in train_loss and not train_dis
+        train_cls = "classifier" in train_loss
+        ppo_gen = train_gen and self.ppo  # :375 (either discriminator's loss type switches the ratio on)
         use_gp = train_dis and "gp" in dtype_cfg.loss_type
         share = dcfg.batch_chunk * dcfg.sample_chunks_mem
         cached = (gen.tgt_len, gen.mem_len)
@@ -353,7 +471,7 @@ class TransformerGAN(nn.Module):
         gen.detach_mems_grad = False
         g_total = d_total = gp_total = 0
         try:
-            sampler = self._sample_chunks(data, with_grad=train_gen)
+            sampler = self._sample_chunks(data, with_grad=train_gen and not train_cls)  # 'classifier': hard ids, :311
             while True:
                 if train_gen:
                     item = next(sampler, None)
@@ -365,6 +483,22 @@ class TransformerGAN(nn.Module):
                 cs, ce, fake = item
                 if train_dis:
                     fake = fake.detach()
+                if train_cls:  # BCE update of the density-ratio classifier on real / sampled chunks (:350-372)
+                    if self.P0 is None:
+                        self.P0 = self._ppo_P0(fake)
+                    n = self.P0.shape[0]
+                    bce = torch.nn.functional.binary_cross_entropy
+                    err = bce(torch.sigmoid(self.dis_D_forward(data[cs:ce])), self.P0.new_ones(n)) + \
+                        bce(torch.sigmoid(self.dis_D_forward(fake.detach())), self.P0.new_zeros(n))
+                    (err.float().mean() / share).backward()
+                    continue
+                ratio = None
+                if ppo_gen:  # clipped density ratio of the current samples under dis_D (:375-388)
+                    if self.P0 is None or self._update_D0:
+                        self.P0 = self._ppo_P0(fake)
+                    D1 = torch.sigmoid(self.dis_D_forward(fake))
+                    ratio = (1.0 - D1) / torch.clamp(D1 * self.P0, min=1e-7)
+                    ratio_clipped = torch.clamp(ratio, 1.0 - self.cfg.PPO.clip_param, 1.0 + self.cfg.PPO.clip_param)
                 real = data[cs:ce].transpose(0, 1)          # [B, len] ids
                 fake_bt = fake.transpose(0, 1)              # [B, len, V]
                 if dcfg.type == "bert":
@@ -385,6 +519,9 @@ class TransformerGAN(nn.Module):
                     real_1h = self._one_hot(real)
                     d_real = self.discriminator(real_1h)
                     d_fake = self.discriminator(fake_bt)
+                if ratio is not None and "ppo" in dtype_cfg.loss_type:  # PPO surrogate target (:419-424, :456-461)
+                    surr1, surr2 = ratio * d_fake, ratio_clipped * d_fake
+                    d_fake = torch.where(d_fake > 0, torch.min(surr1, surr2), torch.max(surr1, surr2))
                 g_loss, d_loss = get_losses(d_real, d_fake, dtype_cfg.loss_type)
                 if use_gp and dcfg.type == "bert" and self._own_bert() is not None:
                     gp = self._own_gradient_penalty(self._own_bert(), real_1h, fake_bt)
@@ -405,6 +542,9 @@ class TransformerGAN(nn.Module):
         finally:
             gen.detach_mems_grad = True
             gen.reset_length(*cached)
+        gen.fold_lane_grads()
+        if train_cls:
+            return out
         if train_dis:
             out["dis_loss"] = dcfg.dis_loss_factor * d_total / dcfg.sample_chunks_mem
             if use_gp:
