@@ -138,6 +138,20 @@ int tgan_relattn_bwd(int dtype, const void* q, int64_t ldq, const void* k, const
                      int B, int N, int Q, int M, int msl, int same_length, float scale,
                      float drop_p, uint64_t seed, uint64_t site, int impl, void* stream);
 
+/* The single-token case (Q == 1: every step of the GAN sampling chain, transformer_gan.py:299-334) in two launches,
+ * so that the caller can keep the half that only weight gradients need off the chain's critical path:
+ *   phase 1 (query side):  dq, du / dvb (+=), dk / dv of the CURRENT row (j == M), and the scratch rows
+ *                          dS[n, j, b], P~[n, j, b] (scratch: fp32 [2 * N * (M+1) * B]);
+ *   phase 2 (memory side): dk / dv of the rows j < M (outer products of the scratch with q + u / dout) and dr.
+ * The memory rows are detached (mem_transformer.py:461-475): their dk / dv feed only dW_kv.  Phase 2 must be ordered
+ * after phase 1 (same stream or an event).  Same arguments as tgan_relattn_bwd otherwise.                        */
+int tgan_relattn_bwd_step(int phase, int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                          const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
+                          const void* out, const void* dout, int64_t ldo, const float* lse, float* scratch,
+                          void* dq, void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb,
+                          int B, int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
+                          uint64_t site, void* stream);
+
 /* ---- logits -> NLL: proj_adaptive_softmax.py:75-84 ------------------------------------------------------
  * logits fp32 [rows, ldl] (first V columns valid); nll = lse - logits[target]; lse saved for the backward. */
 int tgan_ce_fwd(const float* logits, int64_t ldl, const int64_t* target, float* nll, float* lse, int rows, int V,

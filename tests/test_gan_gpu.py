@@ -44,11 +44,8 @@ def _cfg(shape, z, bert_dir):
               PPO=ns(dis_D_type="bert", dis_D_num_rep=1, clip_param=0.4))
 
 
-@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("name", ["gan_bert_tiny", "gan_cnn_tiny"])
-def test_gan_step_matches_reference_golden(name, lanes, tmp_path):
-    """lanes = 2: the sampling chain split into two concurrent column lanes (separate streams / engines, lane-private
-    gradient staging folded into .grad) must give the same ids, losses and gradients as the single chain."""
+def test_gan_step_matches_reference_golden(name, tmp_path):
     import transformer_gan as TG
     z, shape = GU.load(name)
     V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
@@ -66,7 +63,6 @@ def test_gan_step_matches_reference_golden(name, lanes, tmp_path):
     model = model.cuda().train()
     model.generator.compute_dtype = torch.float32  # fp32 parity mode (1e-4)
     model.temperature = float(z["temperature"])
-    model.sample_lanes, model.sample_lane_min_batch = lanes, 1
     data = torch.from_numpy(z["data"]).cuda()
     U = torch.from_numpy(z["U"]).cuda()
     alpha = torch.from_numpy(z["alpha"]).cuda()
@@ -148,7 +144,6 @@ def test_gan_step_bf16_eager_and_graphed_match_reference(name, tmp_path):
     UNMODIFIED reference's goldens; sampled ids equal to the oracle's along every sequence up to the first step whose
     top-2 (logit + g) margin is inside the tolerance; the graph replay reproduces the eager bf16 call."""
     model, z, shape = _build_gan(name, tmp_path, torch.bfloat16)
-    model.sample_lanes, model.sample_lane_min_batch = 2, 1  # the benchmarked path: two concurrent sampling lanes
     V, B, T, ctx, chunks = shape.n_token, int(z["B"]), int(z["dis_tgt_len"]), int(z["context_len"]), int(z["chunks"])
     data = torch.from_numpy(z["data"]).cuda()
     U = torch.from_numpy(z["U"]).cuda()
@@ -283,7 +278,9 @@ def test_gan_ppo_variant_matches_reference_golden(dtype, tmp_path):
             g = named[k[len(pre):]].grad
             got = g.detach().cpu().double() if g is not None else torch.zeros_like(want)
             err = (got - want).norm().item()
-            assert err <= (2e-2 if fp32 else 0.15) * want.norm().item() + 2e-6, (tag, k, err, want.norm().item())
+            # (key-bias gradients are mathematically zero -- softmax shift invariance: absolute floor; TF32 / bf16
+            # rounding leaves ~1e-4 there)
+            assert err <= (2e-2 if fp32 else 0.15) * want.norm().item() + (2e-6 if fp32 else 5e-4), (tag, k, err, want.norm().item())
             checked += 1
         assert checked >= 5
     assert not model._gan_graphs

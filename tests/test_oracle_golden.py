@@ -8,7 +8,7 @@ import golden_util as GU
 import txl_oracle as O
 
 
-@pytest.mark.parametrize("name", ["mle_tiny", "mle_tiny_samelen", "mle_real"])
+@pytest.mark.parametrize("name", ["mle_tiny", "mle_tiny_samelen", "mle_real", "mle_real_q32"])
 def test_mle_matches_reference(name):
     z, shape = GU.load(name)
     p = O.init_params(shape, int(z["seed"]), dtype=torch.float64)

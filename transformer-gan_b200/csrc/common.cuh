@@ -238,7 +238,7 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                              const void* out, const void* dout, int64_t ldo, const float* lse, float* scratch, void* dq,
                              void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
                              int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
-                             uint64_t site, cudaStream_t st);
+                             uint64_t site, cudaStream_t st, int phase);
 // tcgen05 attention (bf16 only); return -1 when the shape is not eligible
 int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out, int64_t ldo,

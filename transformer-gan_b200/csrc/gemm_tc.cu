@@ -821,9 +821,11 @@ int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const
     }
     const int waste256 = ceil_div(N, 256) * 256 - N, waste128 = ceil_div(N, 128) * 128 - N;
     int BN = (waste256 <= waste128) ? 256 : 128;
-    // few tiles and a short K loop (decode-sized GEMMs; long-K weight gradients fill the SMs through split-K instead):
-    // narrower tiles occupy more SMs
-    if (ceil_div(M, BM) * ceil_div(N, 256) * 2 <= sm_count() && ceil_div(K, BK) < 16) BN = 128;
+    // few tiles (decode-sized GEMMs: a single-token step of the sampling chain has 4 row tiles): narrower tiles occupy
+    // more SMs and halve each CTA's K loop, which is what bounds these launch-latency-sized kernels.  Long-K weight
+    // gradients (plain fp32 output) keep the wide tile: they fill the SMs through split-K instead.
+    const bool splittable = dtype_c == TGAN_F32 && (flags & ~(TGAN_EPI_ACCUM | TGAN_EPI_AUX_F32)) == 0;
+    if (ceil_div(M, BM) * ceil_div(N, 256) * 2 <= sm_count() && (ceil_div(K, BK) < 16 || !splittable)) BN = 128;
     CUtensorMap tmA, tmB;
     int rc;
     if (!transA) rc = tc::make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);

@@ -26,6 +26,7 @@ struct DecArgs {
     int jlo0;                // first key a same_length window keeps (0 otherwise)
     float scale, scale_log2, drop_scale;
     uint32_t thresh, key;
+    int split;               // backward: 1 = query side only (dk / dv of the memory rows are left to relattn_dec_keys)
 };
 
 // 8 consecutive elements kept in their storage format (bf16: one 16-byte register quad) until they are consumed: the
@@ -231,12 +232,18 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
         T* dvbase = dv + (int64_t)b * lddkv + col;
         const int64_t kstride = (int64_t)a.B * ldkv, dstride = (int64_t)a.B * lddkv;
         float* dsrow = dsbuf + (int64_t)n * a.K * a.B + b;  // entry j at dsrow[j * B]
+        const int64_t pw_off = (int64_t)a.N * a.K * a.B;    // split mode: the dropped weights P~ follow the dS block
         // keys a reset row does not attend to: zero gradients
         for (int j = kg; j < jlo; j += 4) {
-            float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            store8(dkbase + j * dstride, z);
-            store8(dvbase + j * dstride, z);
-            if (dc == 0) dsrow[(int64_t)j * a.B] = 0.f;
+            if (!a.split) {
+                float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                store8(dkbase + j * dstride, z);
+                store8(dvbase + j * dstride, z);
+            }
+            if (dc == 0) {
+                dsrow[(int64_t)j * a.B] = 0.f;
+                if (a.split) dsrow[(int64_t)j * a.B + pw_off] = 0.f;
+            }
         }
         extern __shared__ __align__(16) uint8_t fifo_raw[];
         constexpr int CH = 8 * sizeof(T);
@@ -301,9 +308,16 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
                     dqk[t] = fmaf(ds, k8[t], dqk[t]);
                     dqr[t] = fmaf(ds, r8[t], dqr[t]);
                 }
-                store8(dkp, dk8);
-                store8(dvp, dv8);
-                if (dc == 0) *dsp = ds;
+                // split mode: only the current row (the one whose dk / dv the dgrad chain needs) is written here;
+                // the memory rows are outer products of the saved (dS, P~) with (q + u, dO): relattn_dec_keys
+                if (!a.split || j == jhi) {
+                    store8(dkp, dk8);
+                    store8(dvp, dv8);
+                }
+                if (dc == 0) {
+                    *dsp = ds;
+                    if (a.split) dsp[pw_off] = pw;
+                }
             }
             dkp += dstep; dvp += dstep; dsp += sstep;
         }
@@ -369,8 +383,37 @@ relattn_dec_dr(const T* __restrict__ q, int64_t ldq, const float* __restrict__ v
     }
 }
 
+// Memory-row half of the split backward: dk[j, b, n, :] = dS[n, j, b] (q + r_w_bias)[b, n, :],
+// dv[j, b, n, :] = P~[n, j, b] dO[b, n, :] for the rows j < M.  These rows feed only the K/V weight gradient (the memory
+// is detached, mem_transformer.py:461-475), so the kernel runs OFF the sampling chain's critical path, on a side
+// stream.  Pure write stream: one thread per 8 dims, a CTA per (key row, 32 sequences).
+template <typename T>
+__global__ void __launch_bounds__(320)
+relattn_dec_keys(const T* __restrict__ q, int64_t ldq, const float* __restrict__ u, const T* __restrict__ dout, int64_t ldo,
+                 const float* __restrict__ dsbuf, T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv, int NC, DecArgs a) {
+    const int j = blockIdx.x;
+    const int64_t pw_off = (int64_t)a.N * a.K * a.B;
+    for (int e = threadIdx.x; e < 32 * NC; e += blockDim.x) {
+        const int b = blockIdx.y * 32 + e / NC, c = e % NC;
+        if (b >= a.B) break;
+        const int n = c >> 3, col = 8 * c;
+        const float* sp = dsbuf + ((int64_t)n * a.K + j) * a.B + b;
+        const float ds = sp[0], pw = sp[pw_off];
+        float x[8], uu[8], g8[8], dk8[8], dv8[8];
+        load8(q + (int64_t)b * ldq + col, x);
+        load8(u + col, uu);
+        load8(dout + (int64_t)b * ldo + col, g8);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { dk8[t] = ds * (x[t] + uu[t]); dv8[t] = pw * g8[t]; }
+        const int64_t row = ((int64_t)j * a.B + b) * lddkv + col;
+        store8(dk + row, dk8);
+        store8(dv + row, dv8);
+    }
+}
+
 DecArgs make_dec(int B, int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed, uint64_t site) {
     DecArgs a;
+    a.split = 0;
     a.B = B; a.N = N; a.M = M; a.K = M + 1;
     // mem_transformer.py:496-503 at qlen = 1: keys j <= -msl are cut
     a.jlo0 = same_length ? (1 - msl > 0 ? 1 - msl : 0) : 0;
@@ -410,13 +453,38 @@ int tgan_relattn_fwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
     return 0;
 }
 
+// phase 0: the whole backward on `st`.  phase 1: query side only (dq, du / dvb, dk / dv of the current row, the dS / P~
+// scratch); phase 2: memory side (dk / dv of the rows j < M from the scratch, dR) -- see tgan_relattn_bwd_step.
 int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const void* r, int64_t ldr, const float* u, const float* vb, const uint8_t* reset,
                              const void* out, const void* dout, int64_t ldo, const float* lse, float* scratch, void* dq,
                              void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
                              int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
-                             uint64_t site, cudaStream_t st) {
+                             uint64_t site, cudaStream_t st, int phase) {
     DecArgs a = make_dec(B, N, M, msl, same_length, scale, drop_p, seed, site);
+    a.split = phase != 0;
+    if (phase == 2) {
+        if (M > 0) {
+            const int NC = N * (HS / 8);
+            dim3 gk(M, ceil_div(B, 32));
+            if (dtype == TGAN_F32)
+                relattn_dec_keys<float><<<gk, 320, 0, st>>>((const float*)q, ldq, u, (const float*)dout, ldo, scratch,
+                                                            (float*)dk, (float*)dv, lddkv, NC, a);
+            else
+                relattn_dec_keys<bf16><<<gk, 320, 0, st>>>((const bf16*)q, ldq, u, (const bf16*)dout, ldo, scratch,
+                                                           (bf16*)dk, (bf16*)dv, lddkv, NC, a);
+            TGAN_COUNT_LAUNCH();
+            TGAN_LAUNCH_OK();
+        }
+        dim3 g2(a.K, N);
+        if (dtype == TGAN_F32)
+            relattn_dec_dr<float><<<g2, DR_THREADS, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
+        else
+            relattn_dec_dr<bf16><<<g2, DR_THREADS, 0, st>>>((const bf16*)q, ldq, vb, scratch, dr, lddr, a);
+        TGAN_COUNT_LAUNCH();
+        TGAN_LAUNCH_OK();
+        return 0;
+    }
     const int DW = 4;  // <= 96 registers x 128 threads: 5 CTAs (20 warps) per SM; 10-warp CTAs at 128 registers fit only once
     const int grid = ceil_div((int64_t)B * N, DW);
     const size_t sm_f32 = (size_t)PF * 3 * DW * 32 * 32, sm_bf16 = (size_t)PF * 3 * DW * 32 * 16;
@@ -437,6 +505,7 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                                                          lddkv, scratch, du, dvb, a);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
+    if (phase == 1) return 0;
     dim3 g2(a.K, N);
     if (dtype == TGAN_F32)
         relattn_dec_dr<float><<<g2, DR_THREADS, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
@@ -445,4 +514,22 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int tgan_relattn_bwd_step(int phase, int dtype, const void* q, int64_t ldq, const void* k, const void* v,
+                                     int64_t ldkv, const void* r, int64_t ldr, const float* u, const float* vb,
+                                     const uint8_t* reset, const void* out, const void* dout, int64_t ldo,
+                                     const float* lse, float* scratch, void* dq, void* dk, void* dv, int64_t lddkv,
+                                     float* dr, int64_t lddr, float* du, float* dvb, int B, int N, int M, int msl,
+                                     int same_length, float scale, float drop_p, uint64_t seed, uint64_t site,
+                                     void* stream) {
+    TGAN_CHECK_ARG(phase == 1 || phase == 2, "tgan_relattn_bwd_step: phase must be 1 (query side) or 2 (memory side)");
+    TGAN_CHECK_ARG(B > 0 && N > 0 && M >= 0, "tgan_relattn_bwd_step: bad dims");
+    const uintptr_t al = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)r | (uintptr_t)out | (uintptr_t)dout |
+                         (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv | (uintptr_t)u | (uintptr_t)vb;
+    TGAN_CHECK_ARG((al & 31) == 0 && ldq % 8 == 0 && ldkv % 8 == 0 && ldr % 8 == 0 && ldo % 8 == 0 && lddkv % 8 == 0 &&
+                   lddr % 4 == 0, "tgan_relattn_bwd_step: operands must be 32-byte aligned, ld multiples of 8");
+    return tgan_relattn_bwd_decode1(dtype, q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, scratch, dq, dk,
+                                    dv, lddkv, dr, lddr, du, dvb, B, N, M, msl, same_length, scale, drop_p, seed, site,
+                                    (cudaStream_t)stream, phase);
 }

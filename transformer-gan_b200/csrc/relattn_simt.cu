@@ -619,7 +619,7 @@ int tgan_relattn_bwd_simt(int dtype, const void* q, int64_t ldq, const void* k, 
         // `delta` doubles as the dS scratch of the fused single-token backward: B * N * (M + 1) floats (tgan_b200.h)
         return tgan_relattn_bwd_decode1(dtype, q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq,
                                         dk, dv, lddkv, dr, lddr, du, dvb, B, N, M, msl, same_length, scale, drop_p, seed,
-                                        site, st);
+                                        site, st, 0);
     AttnArgs a = make_args(B, N, Q, M, msl, same_length, scale, drop_p, seed, site);
     if (dtype == TGAN_F32)
         return bwd_launch<float>(q, ldq, k, v, ldkv, r, ldr, u, vb, reset, out, dout, ldo, lse, delta, dq, dk, dv,

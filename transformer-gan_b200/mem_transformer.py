@@ -7,6 +7,7 @@ the reference -- ``MemTransformerLM(cfg, n_token, vec_len)`` with ``forward(data
 (:484-576) and its backward runs in the CUDA library through ``tgan_b200.engine.TxlEngine``.  There is no eager /
 CPU fallback: calling the model on a CPU tensor raises.
 """
+import contextlib
 import os
 import weakref
 
@@ -100,9 +101,8 @@ class _TxlFunction(torch.autograd.Function):
     """One autograd node for the whole generator stack (embedding .. NLL or Gumbel-ST output)."""
 
     @staticmethod
-    def forward(ctx, model, mode, inp, target, reset, mems, temperature, noise, names, lane, *params):
-        eng = model._get_engine(lane)
-        ctx.lane = lane
+    def forward(ctx, model, mode, inp, target, reset, mems, temperature, noise, names, *params):
+        eng = model._get_engine()
         need_grad = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
         ectx = eng.forward(inp.detach(), reset, mems, mem_len=model.mem_len, same_length=model.same_length,
                            training=model.training, target=target if mode == "mle" else None,
@@ -130,23 +130,18 @@ class _TxlFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         ectx, model, mode = ctx.ectx, ctx.model, ctx.mode
-        eng = model._get_engine(ctx.lane)
+        eng = model._get_engine()
         if ectx.layers is None or len(ectx.layers) == 0:
             raise RuntimeError("backward through a generator call that did not save activations")
         T, B, V = ectx.T, ectx.B, model.n_token
         gout = gout.contiguous().float()
         # Parameter gradients are ACCUMULATED straight into ``p.grad`` by one unpack kernel (what autograd's
         # AccumulateGrad nodes would do with 72 separate adds); the Function therefore returns None for them.
-        if ctx.lane:
-            # a concurrent sampling lane (TransformerGAN._lane_slices): its kernels run beside lane 0's, so it
-            # accumulates into its own staging tensors; fold_lane_grads() adds them to .grad after the join
-            targets = model._lane_grad_targets(ctx.lane, ctx.names, ctx.params)
-        else:
-            targets = {}
-            for n, prm in zip(ctx.names, ctx.params):
-                if prm.grad is None:
-                    prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
-                targets[n] = prm.grad
+        targets = {}
+        for n, prm in zip(ctx.names, ctx.params):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
+            targets[n] = prm.grad
         if mode == "mle":
             grads = eng.backward(ectx, dnll=gout, need_dinput=ctx.soft_in, grad_targets=targets,
                                  reducer=model.grad_reducer)
@@ -163,7 +158,7 @@ class _TxlFunction(torch.autograd.Function):
             dinp = torch.empty(ectx.Q * B, V, dtype=torch.float32, device=eng.device)
             L.convert(d, d.stride(0), dinp, V, ectx.Q * B, V, V)
             dinp = dinp.view(ectx.Q, B, V)
-        return (None, None, dinp, None, None, None, None, None, None, None) + (None,) * len(ctx.names)
+        return (None, None, dinp, None, None, None, None, None, None) + (None,) * len(ctx.names)
 
 
 class _GraphEntry:
@@ -268,8 +263,6 @@ class MemTransformerLM(nn.Module):
         self.compute_dtype = torch.float32 if os.environ.get("TGAN_B200_DTYPE", "bf16") == "fp32" else torch.bfloat16
         self.kernel_impl = L.IMPL_AUTO
         self._engine = None
-        self._lane_engines = {}   # lane (> 0) -> TxlEngine of a concurrent sampling lane
-        self._lane_grads = {}     # lane (> 0) -> {"t": {name: staging tensor}, "dirty": bool}
         self._new_mems = None
         # replay each steady-state MLE segment (forward, backward) as CUDA graphs instead of ~180 launches; see
         # _TxlGraphFunction.  Off by default: it pins the input / gradient buffers of the captured shapes.
@@ -296,55 +289,40 @@ class MemTransformerLM(nn.Module):
             return torch.empty(n_layers + 1, 0, dtype=param.dtype, device=param.device)
         return None
 
-    def _get_engine(self, lane: int = 0) -> TxlEngine:
-        """Lane 0 is THE engine; lanes > 0 are the extra engines of TransformerGAN's concurrent sampling lanes: same
-        parameters, private scratch / gradient accumulators / K/V caches, and their own noise stream (seed + lane)."""
+    def _get_engine(self) -> TxlEngine:
         dev = self.r_w_bias.device
         if dev.type != "cuda":
             raise RuntimeError("tgan_b200 MemTransformerLM runs on CUDA only (no CPU fallback): move the model to a GPU")
         drop, dropatt = self.drop.p, self.layers[0].dec_attn.dropatt.p
-        e = self._engine if lane == 0 else self._lane_engines.get(lane)
+        e = self._engine
         if e is None or e.device != dev or e.dtype != self.compute_dtype or e.impl != self.kernel_impl:
             dims = TxlDims(self.n_layer, self.n_head, self.d_model, self.layers[0].pos_ff.d_inner, self.n_token,
                            drop, dropatt, self.clamp_len)
-            e = TxlEngine(dims, dev, self.compute_dtype, seed=(torch.initial_seed() + 7919 * lane) & 0x7FFFFFFFFFFFFFFF,
+            e = TxlEngine(dims, dev, self.compute_dtype, seed=torch.initial_seed() & 0x7FFFFFFFFFFFFFFF,
                           impl=self.kernel_impl)
-            if lane == 0:
-                self._engine = e
-            else:
-                self._lane_engines[lane] = e
+            self._engine = e
         e.d.dropout, e.d.dropatt, e.d.clamp_len = drop, dropatt, self.clamp_len
         e.bind_params(_param_dict(self))
         return e
 
-    def _all_engines(self):
-        return ([self._engine] if self._engine is not None else []) + list(self._lane_engines.values())
-
-    def _lane_grad_targets(self, lane, names, params):
-        st = self._lane_grads.get(lane)
-        if st is None or any(st["t"][n].shape != p.shape or st["t"][n].device != p.device for n, p in zip(names, params)):
-            st = {"t": {n: torch.zeros_like(p, memory_format=torch.contiguous_format) for n, p in zip(names, params)},
-                  "dirty": False}
-            self._lane_grads[lane] = st
-        st["dirty"] = True
-        return st["t"]
-
-    def fold_lane_grads(self):
-        """.grad += the gradients the lanes > 0 accumulated since the last fold (call on the stream that joined them)."""
-        pd = _param_dict(self)
-        for st in self._lane_grads.values():
-            if not st["dirty"]:
-                continue
-            grads, staged = [], []
-            for n, t in st["t"].items():
+    @contextlib.contextmanager
+    def grad_window(self):
+        """``with model.grad_window(): loss.backward()`` -- every backward call through the generator inside the block
+        accumulates in the engine's padded gradient buffers; ``.grad`` is updated once when the block ends (see
+        TxlEngine.begin_grad_window).  TransformerGAN wraps the backward of a sampled chunk (64 single-token calls)."""
+        eng = self._get_engine()
+        eng.begin_grad_window()
+        try:
+            yield
+        finally:
+            targets = {}
+            pd = _param_dict(self)
+            for n, *_ in eng.layout.reference_map():
                 prm = pd[n]
                 if prm.grad is None:
                     prm.grad = torch.zeros_like(prm, memory_format=torch.contiguous_format)
-                grads.append(prm.grad)
-                staged.append(t)
-            torch._foreach_add_(grads, staged)
-            torch._foreach_zero_(staged)
-            st["dirty"] = False
+                targets[n] = prm.grad
+            eng.end_grad_window(targets)
 
     def _graph_entry(self, eng, data, target, reset_mems, ring):
         """The captured forward for this (ring phase, shape) key; captured on first use."""
@@ -395,8 +373,8 @@ class MemTransformerLM(nn.Module):
         for k in [k for k in self._graphs if k[0] == rid]:
             del self._graphs[k]
 
-    def _run(self, mode, data, target, reset_mems, mems, temperature=None, noise=None, lane=0):
-        eng = self._get_engine(lane)
+    def _run(self, mode, data, target, reset_mems, mems, temperature=None, noise=None):
+        eng = self._get_engine()
         if self.pad_type != "model":
             reset_mems = None  # the reset mask exists only for pad_type == 'model' (mem_transformer.py:495-528)
         names = [r for r, *_ in eng.layout.reference_map()]
@@ -412,7 +390,7 @@ class MemTransformerLM(nn.Module):
                 start, length = entry.new_mems
                 ring.note_write((ring.start + ring.length) % ring.capacity, data.shape[0])  # the replay wrote the rows
                 return out, RingMems(ring.slabs, start, length, self.d_model, kv=ring.kv, shared=ring.shared)
-        out = _TxlFunction.apply(self, mode, data, target, reset_mems, mems, temperature, noise, names, lane,
+        out = _TxlFunction.apply(self, mode, data, target, reset_mems, mems, temperature, noise, names,
                                  *[pd[n] for n in names])
         return out, self._new_mems
 
@@ -422,16 +400,16 @@ class MemTransformerLM(nn.Module):
             raise NotImplementedError("status_vec / append_note_status is not accelerated")
         return self._run("mle", data, target, reset_mems, mems)
 
-    def forward_generate(self, data, mems, status_vec=None, lane=0):
+    def forward_generate(self, data, mems, status_vec=None):
         """-> (logits [T, bsz, n_token] fp32, new_mems)   (mem_transformer.py:578-600)"""
         if status_vec is not None:
             raise NotImplementedError("status_vec / append_note_status is not accelerated")
-        return self._run("logits", data, None, None, mems, lane=lane)
+        return self._run("logits", data, None, None, mems)
 
-    def forward_generate_gumbel(self, data, temperature, mems, status_vec=None, noise=None, lane=0):
+    def forward_generate_gumbel(self, data, temperature, mems, status_vec=None, noise=None):
         """-> (straight-through one-hot [T, bsz, n_token], new_mems)   (mem_transformer.py:602-651).
         ``noise``: optional uniform [T, bsz, n_token] tensor replacing the reference's CPU ``torch.rand`` draw
         (parity tests); default is device-side Philox."""
         if status_vec is not None:
             raise NotImplementedError("status_vec / append_note_status is not accelerated")
-        return self._run("gumbel", data, None, None, mems, temperature=temperature, noise=noise, lane=lane)
+        return self._run("gumbel", data, None, None, mems, temperature=temperature, noise=noise)

@@ -290,6 +290,7 @@ class TxlEngine:
         # dgrad chain.  Captured in a CUDA graph the fork / join events become plain dependency edges.
         self.side_stream_max_rows = 8192
         self._side = None
+        self._window = None        # open gradient window: number of backward calls accumulated so far
 
     # -- parameters ---------------------------------------------------------------------------------------
     def bind_params(self, params: Dict[str, torch.Tensor]):
@@ -377,10 +378,31 @@ class TxlEngine:
             self._graph_pool = torch.cuda.graph_pool_handle()
         return self._graph_pool
 
-    def _side_stream(self):
+    # -- gradient window -----------------------------------------------------------------------------------
+    def begin_grad_window(self):
+        """Until end_grad_window(), backward() calls ACCUMULATE into the padded gradient buffers without zeroing them
+        first and without unpacking at the end: the 123 single-token backward calls of a sampling chain share one
+        60 MB zero-fill and one unpack into the reference-layout gradients instead of paying both per token
+        (every gradient kernel of the stack accumulates: TMA reduce-add / atomics)."""
+        if self._window is not None:
+            raise L.TganError("gradient window already open")
+        self.gv.zero_()
+        self.gmat.zero_()
+        self._window = 0
+
+    def end_grad_window(self, grad_targets: Dict[str, torch.Tensor], accumulate: bool = True) -> int:
+        """Unpack what the window accumulated into ``grad_targets`` (+= when ``accumulate``); returns the number of
+        backward calls it covered (0: nothing to unpack)."""
+        n, self._window = self._window, None
+        if n:
+            desc = self._unpack_desc_for(grad_targets)
+            L.unpack_grads(self.gmat, self.gvec, desc, desc.shape[0], self._max_elems, accumulate=accumulate)
+        return n or 0
+
+    def _side_stream(self, i: int = 0):
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        return self._side[i]
 
     def _site(self, call_id: int, local: int) -> int:
         return call_id * 256 + local
@@ -662,8 +684,11 @@ class TxlEngine:
         gm, gv = self.gmat, self.gvec
         # every weight-gradient GEMM accumulates (TMA reduce-add / split-K partial sums) into buffers zeroed ONCE here:
         # one 60 MB memset instead of a memset node in front of each of the ~37 split-K launches
-        gv.zero_()
-        gm.zero_()
+        if self._window is None:
+            gv.zero_()
+            gm.zero_()
+        else:
+            self._window += 1
 
         # small calls: weight-gradient GEMMs on the side stream (see side_stream_max_rows); their operands are kept
         # alive in `keep` until the join at the end -- the caching allocator would otherwise hand a freed block to the
@@ -672,13 +697,16 @@ class TxlEngine:
         main = torch.cuda.current_stream()
         keep = []
 
-        def wgrad(name, dY, X, rows, n_out, k_in, *, dy_off=0, x_off=0, ldy=None, ldx=None, row_off=0):
+        side2 = self._side_stream(1) if side is not None else None
+
+        def wgrad(name, dY, X, rows, n_out, k_in, *, dy_off=0, x_off=0, ldy=None, ldx=None, row_off=0, stream=None):
             """gmat[name][row_off : row_off+n_out, :k_in] (+)= dY^T X"""
             goff, _, gld = lay.gmat[name]
-            if side is not None:
-                side.wait_stream(main)  # everything enqueued so far (the producers of dY, the zeroing of gm)
+            st = stream if stream is not None else side
+            if st is not None:
+                st.wait_stream(main)  # everything enqueued so far (the producers of dY, the zeroing of gm)
                 keep.append((dY, X))
-            with torch.cuda.stream(side if side is not None else main):
+            with torch.cuda.stream(st if st is not None else main):
                 L.gemm(dY, X, gm, transA=True, transB=False, M=n_out, N=k_in, K=rows, lda=ldy, ldb=ldx, ldc=gld,
                        a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld, flags=L.EPI_ACCUM, impl=impl)
 
@@ -737,16 +765,29 @@ class TxlEngine:
             dq = self._buf(R, NH)
             dkv = self._buf(KR, 2 * NH)
             dr32 = dr_all32[:, l * NH:(l + 1) * NH]  # view: this layer's column block
-            delta = self._buf(B * d.n_head * (Q if Q > 1 else K), dtype=torch.float32)  # Q == 1: dS scratch [B*N, K]
-            L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
-                          sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
-                          ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,
-                          k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
+            split = side is not None and Q == 1  # single-token step: memory-side half on the second side stream
+            delta = self._buf(B * d.n_head * (Q if Q > 1 else (2 * K if split else K)),
+                              dtype=torch.float32)  # Q == 1: dS (and P~) scratch [N, K, B]
+            if split:
+                args = (sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt, sv.lse,
+                        delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, M, ctx.msl,
+                        ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l))
+                kw = dict(k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
+                L.relattn_bwd_step(1, *args, **kw)
+                side2.wait_stream(main)
+                with torch.cuda.stream(side2):
+                    L.relattn_bwd_step(2, *args, **kw)
+                keep.append((delta, dq, dkv, datt))
+            else:
+                L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
+                              sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
+                              ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,
+                              k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
             wgrad(p + "Wqkv", dq, slabs, R, NH, DP, ldy=NH, ldx=DP, x_off=cur_off[l])
             row = 0
             for pos, n in ctx.x_segs:
                 wgrad(p + "Wqkv", dkv, slabs, n * B, 2 * NH, DP, ldy=2 * NH, ldx=DP, dy_off=row * B * 2 * NH,
-                      x_off=x_base + pos * B * DP, row_off=NH)
+                      x_off=x_base + pos * B * DP, row_off=NH, stream=side2 if split else None)
                 row += n
             # dx_l = dz1 + dq Wq + dkv[current rows] Wkv
             wtoff, wtld = self._m(p + "Wqkv.T")
@@ -763,6 +804,7 @@ class TxlEngine:
                 reducer.reduce(gv, v0, v1 - v0)
         if side is not None:
             main.wait_stream(side)
+            main.wait_stream(side2)
             keep.clear()
         # ---- r_net weight gradients of all layers: dWr_all = dR_all^T pos_emb
         NL = d.n_layer * NH
@@ -794,7 +836,9 @@ class TxlEngine:
             reducer.reduce(gv, 0, lay.vec["l0.b1"][0])
             reducer.join()
         # ---- unpack to reference-layout gradients
-        if grad_targets is not None:
+        if self._window is not None:
+            grads = {}  # end_grad_window() unpacks once for all the calls of the window
+        elif grad_targets is not None:
             desc = self._unpack_desc_for(grad_targets)
             L.unpack_grads(gm, gv, desc, desc.shape[0], self._max_elems, accumulate=accumulate)
             grads = {}

@@ -48,6 +48,8 @@ _SIGS = {
     "tgan_relattn_fwd": [I, P, L, P, P, L, P, L, P, P, P, P, L, P, I, I, I, I, I, I, F, F, U, U, I, P],
     "tgan_relattn_bwd": [I, P, L, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P, P, L, P, L, P, P, I, I, I, I, I, I,
                          F, F, U, U, I, P],
+    "tgan_relattn_bwd_step": [I, I, P, L, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P, P, L, P, L, P, P, I, I, I, I, I,
+                              F, F, U, U, P],
     "tgan_ce_fwd": [P, L, P, P, P, I, I, P],
     "tgan_ce_bwd": [I, P, L, P, P, P, P, L, I, I, I, P],
     "tgan_gumbel_st_fwd": [P, L, P, L, F, P, P, L, P, L, P, I, I, U, U, P],
@@ -232,6 +234,19 @@ def ln_bwd(dy, z, gamma, mean, rstd, dz, dz_drop, dgamma, dbeta, rows, D, DP, dr
     _call("tgan_ln_bwd", dtype_code(dz.dtype), dy.data_ptr() + dy_off * dy.element_size(), DP, z.data_ptr(),
           z.stride(0), _ptr(gamma), _ptr(mean), _ptr(rstd), dz.data_ptr(), dz.stride(0),
           _ptr(dz_drop), DP, _ptr(dgamma), _ptr(dbeta), _ptr(dsum), rows, D, DP, drop_p, seed, site, _stream())
+
+
+def relattn_bwd_step(phase, q, k, v, ldkv, r, u, vb, reset, out, dout, lse, scratch, dq, dk, dv, lddkv, dr, du, dvb, B, N,
+                     M, msl, same_length, scale, drop_p, seed, site, k_off=0, v_off=0, dk_off=0, dv_off=0):
+    """single-token (Q = 1) attention backward in two launches: phase 1 = query side (dq, du / dvb, dk / dv of the
+    current row; on the dgrad chain), phase 2 = memory side (dk / dv of the rows j < M, dR; needed only by weight
+    gradients: a side stream).  scratch: fp32 [2 * B * N * (M + 1)]."""
+    es = q.element_size()
+    _call("tgan_relattn_bwd_step", phase, dtype_code(q.dtype), q.data_ptr(), q.stride(0), k.data_ptr() + k_off * es,
+          v.data_ptr() + v_off * es, ldkv, r.data_ptr(), r.stride(0), _ptr(u), _ptr(vb), _ptr(reset),
+          out.data_ptr(), dout.data_ptr(), out.stride(0), _ptr(lse), _ptr(scratch), dq.data_ptr(),
+          dk.data_ptr() + dk_off * es, dv.data_ptr() + dv_off * es, lddkv, dr.data_ptr(), dr.stride(0),
+          _ptr(du), _ptr(dvb), B, N, M, msl, int(same_length), scale, drop_p, seed, site, _stream())
 
 
 def dropout(src, dst, rows, cols, lds, ldd, p, seed, site, src_off=0, dst_off=0):

@@ -29,8 +29,6 @@ clipped-ratio generator target, :133-153, :184-201, :350-388) keep their host-si
 are therefore launched from the host rather than replayed as a graph; their arithmetic is torch on [B]-sized tensors
 plus the same generator / discriminator kernels.
 """
-import contextlib
-
 import torch
 import torch.nn as nn
 
@@ -80,11 +78,6 @@ class TransformerGAN(nn.Module):
         self.disc_tf32 = True  # TF32 tensor-core GEMMs for the discriminator when the generator computes in bf16
         self.use_own_bert = True   # frozen-encoder BERT discriminator on the repo's kernels (else: HuggingFace modules)
         self._bert_engine = None
-        # the sampling chain runs as this many concurrent column lanes (see _lane_slices); lanes narrower than
-        # sample_lane_min_batch sequences are not worth a stream
-        self.sample_lanes = 2
-        self.sample_lane_min_batch = 64
-        self._lane_stream_objs = []
 
     # ------------------------------------------------------------------------------------------------ discriminator
     def create_bert_model(self, model_name_or_path, loss_type, model_type=None, random_weights=False):
@@ -254,103 +247,40 @@ class TransformerGAN(nn.Module):
     def _one_hot(self, ids):
         return torch.zeros(*ids.shape, self.ntokens, dtype=torch.float32, device=ids.device).scatter_(-1, ids[..., None], 1.0)
 
-    def _lane_slices(self, B):
-        """Batch-column ranges of the sampling lanes.  The single-token steps of the chain are launch-latency-bound
-        kernels on a fraction of the SMs, and sequences are independent: with ``sample_lanes`` > 1 the batch is cut
-        into that many column ranges whose chains run on separate streams (separate engines: private scratch, K/V cache
-        and noise stream), so their kernels overlap -- in a captured graph as parallel branches."""
-        n = max(1, min(int(self.sample_lanes), B // max(1, int(self.sample_lane_min_batch))))
-        per = (B + n - 1) // n
-        return [(lo, min(B, lo + per)) for lo in range(0, B, per)]
-
-    def _lane_streams(self, n, device):
-        while len(self._lane_stream_objs) < n - 1:
-            self._lane_stream_objs.append(torch.cuda.Stream(device=device))
-        return [None] + self._lane_stream_objs[:n - 1]  # lane 0 runs on the caller's stream
-
     def _sample_chunks(self, data, with_grad):
         """Yields ``(chunk_start, chunk_end, fake_chunk [len, B, V])`` for each of the ``sample_chunks_mem`` pieces of
         the ``DISCRIMINATOR.tgt_len`` sequence (transformer_gan.py:273-349).  The first chunk starts with the
         ``context_len`` real tokens as one-hot rows; the gradient chain inside a chunk is the soft one-hot fed back as
-        the next input, and each chunk's first generated token restarts from a hard id."""
+        the next input, and each chunk's first generated token restarts from a hard id.
+        (Measured and dropped: cutting the batch into column lanes on separate streams.  The chain is a string of
+        DEPENDENT launch-latency-bound kernels; halving the rows of each does not shorten any of them, so two lanes
+        side by side take as long as one -- 245 vs 238 ms per generator update at 512 sequences.)"""
         dcfg, gen = self.cfg.DISCRIMINATOR, self.generator
-        B = data.shape[1]
-        lanes = self._lane_slices(B) if data.is_cuda else [(0, B)]
-        nl = len(lanes)
-        streams = self._lane_streams(nl, data.device) if nl > 1 else [None]
-        main = torch.cuda.current_stream() if data.is_cuda else None
-        cols = [data[:, lo:hi] for lo, hi in lanes]
-        mems = [None] * nl
-
-        def on_lane(k):
-            return torch.cuda.stream(streams[k]) if streams[k] is not None else contextlib.nullcontext()
-
-        def fork():
-            for st in streams[1:]:
-                st.wait_stream(main)
-
-        def join():
-            for st in streams[1:]:
-                main.wait_stream(st)
-
-        fork()
+        mems = None
         if dcfg.context_len > 1:
             with torch.no_grad():
-                for k in range(nl):
-                    with on_lane(k):
-                        _, mems[k] = gen.forward_generate(cols[k][:dcfg.context_len - 1], mems[k], lane=k)
+                _, mems = gen.forward_generate(data[:dcfg.context_len - 1], mems)
         chunk = dcfg.tgt_len // dcfg.sample_chunks_mem
-        seq = [[] for _ in range(nl)]
-        ids, step = [], 0
+        seq, ids, step = [], [], 0
         for cs in range(0, dcfg.tgt_len, chunk):
             ce = min(cs + chunk, dcfg.tgt_len)
             for pos in range(cs, ce):
                 if pos < dcfg.context_len:
-                    for k in range(nl):
-                        with on_lane(k):
-                            seq[k].append(self._one_hot(cols[k][pos]))
+                    seq.append(self._one_hot(data[pos]))
                     continue
-                noise = None
-                if self.gumbel_noise_source is not None:
-                    noise = self.gumbel_noise_source(step, (1, B, self.ntokens))
-                    if nl > 1:
-                        join()   # whatever produced the injected noise ran on the caller's stream
-                        fork()
-                step_ids = []
-                for k, (lo, hi) in enumerate(lanes):  # lanes alternate step by step: their launches (and, in the
-                    with on_lane(k):                  # backward, their autograd nodes) interleave
-                        prev = seq[k][-1]
-                        hard = prev.argmax(dim=-1)[None, :].detach()
-                        inp = hard if (dcfg.truncate_backprop or pos == cs or not with_grad) else prev[None]
-                        st, mems[k] = gen.forward_generate_gumbel(inp, self.temperature, mems[k],
-                                                                  noise=None if noise is None else noise[:, lo:hi],
-                                                                  lane=k)
-                        seq[k].append(st[0])
-                        step_ids.append(st[0].detach().argmax(dim=-1))
-                ids.append(step_ids)
+                prev = seq[-1]
+                hard = prev.argmax(dim=-1)[None, :].detach()
+                inp = hard if (dcfg.truncate_backprop or pos == cs or not with_grad) else prev[None]
+                noise = None if self.gumbel_noise_source is None else self.gumbel_noise_source(step, (1,) + tuple(prev.shape))
+                st, mems = gen.forward_generate_gumbel(inp, self.temperature, mems, noise=noise)
+                seq.append(st[0])
+                ids.append(st[0].detach().argmax(dim=-1))
                 step += 1
-            parts = []
-            for k in range(nl):
-                with on_lane(k):
-                    if len(seq[k]) == chunk + 1:  # later chunks carry the previous chunk's last token only as the seed
-                        seq[k] = seq[k][1:]
-                    part = torch.stack(seq[k], 0)
-                    if streams[k] is not None:
-                        part.record_stream(main)
-                    parts.append(part)
-                    seq[k] = [seq[k][-1].detach()]
-            join()
-            yield cs, ce, (parts[0] if nl == 1 else torch.cat(parts, 1))
-            fork()
-        join()
-        if ids:
-            for row in ids:
-                for k, t in enumerate(row):
-                    if streams[k] is not None:
-                        t.record_stream(main)
-            self.last_sampled_ids = torch.stack([r[0] if nl == 1 else torch.cat(r, 0) for r in ids], 0)
-        else:
-            self.last_sampled_ids = None
+            if len(seq) == chunk + 1:  # later chunks carry the previous chunk's last token only as the seed
+                seq = seq[1:]
+            yield cs, ce, torch.stack(seq, 0)
+            seq = [seq[-1].detach()]
+        self.last_sampled_ids = torch.stack(ids, 0) if ids else None
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, data, target, reset_mems, train_loss, mems=None, status_vec=None, update_D0=False):
@@ -417,14 +347,10 @@ class TransformerGAN(nn.Module):
             # descriptor table staged outside the capture; the entry owns it for the graph's lifetime (the captured
             # unpack kernel reads it at every replay -- the engine's cache may evict its own reference)
             entry.desc = eng._unpack_desc_for({n: pd[n].grad for n in names})
-            # ... and so are the tables of the concurrent lanes' engines (created by the eager warm-up call)
-            entry.lane_descs = [e._unpack_desc_for(gen._lane_grads[k]["t"]) for k, e in gen._lane_engines.items()
-                                if k in gen._lane_grads]
             entry.data, entry.tau = data.clone(), torch.ones(1, dtype=torch.float32, device=data.device)
             entry.grad_ptrs = tuple(t.data_ptr() for t in grads)
             ctr = L.step_counter(data.device)
-            for e in gen._all_engines():
-                e.invalidate()  # the parameter re-pack (of every lane's engine) must be part of the graph
+            eng.invalidate()  # the parameter re-pack must be part of the graph
             saved_tau, self.temperature = self.temperature, entry.tau
             import gc
             gc.collect()  # no autograd graph of the eager warm-up call (built on another stream) may survive into the capture
@@ -437,8 +363,7 @@ class TransformerGAN(nn.Module):
                     entry.out = self._gan_phase(entry.data, train_loss)
             finally:
                 self.temperature = saved_tau
-                for e in gen._all_engines():
-                    e.invalidate()
+                eng.invalidate()
             entry.graph, entry.n = g, L.launch_count() - n0
             self._gan_graphs[key] = entry
         entry = self._gan_graphs[key]
@@ -449,8 +374,7 @@ class TransformerGAN(nn.Module):
         entry.tau.fill_(float(self.temperature))
         entry.graph.replay()
         L.note_graph_replay(entry.n)
-        for e in gen._all_engines():
-            e.pack_epoch += 1
+        eng.pack_epoch += 1
         return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in entry.out.items()}
 
     def _gan_phase(self, data, train_loss):
@@ -534,7 +458,8 @@ class TransformerGAN(nn.Module):
                     gp_total = gp_total + keep(gp)
                 if dcfg.backprop_outside:  # the reference's name for "backward happens here, inside forward" (:487-502)
                     if train_gen or ("gen" in train_loss and not train_dis):
-                        (g_loss.float().mean() * dcfg.gen_loss_factor / share).backward()
+                        with gen.grad_window():  # the chunk's single-token backward calls share one zero-fill / unpack
+                            (g_loss.float().mean() * dcfg.gen_loss_factor / share).backward()
                     if train_dis:
                         (d_loss.float().mean() * dcfg.dis_loss_factor / share).backward()
                         if gp is not None:
@@ -542,7 +467,6 @@ class TransformerGAN(nn.Module):
         finally:
             gen.detach_mems_grad = True
             gen.reset_length(*cached)
-        gen.fold_lane_grads()
         if train_cls:
             return out
         if train_dis:
