@@ -140,9 +140,11 @@ int tgan_relattn_bwd(int dtype, const void* q, int64_t ldq, const void* k, const
 
 /* The single-token case (Q == 1: every step of the GAN sampling chain, transformer_gan.py:299-334) in two launches,
  * so that the caller can keep the half that only weight gradients need off the chain's critical path:
- *   phase 1 (query side):  dq, du / dvb (+=), dk / dv of the CURRENT row (j == M), and the scratch rows
- *                          dS[n, j, b], P~[n, j, b] (scratch: fp32 [2 * N * (M+1) * B]);
- *   phase 2 (memory side): dk / dv of the rows j < M (outer products of the scratch with q + u / dout) and dr.
+ *   phase 1 (query side):  dq, dk / dv of the CURRENT row (j == M), and the scratch: dS[b, n, j], P~[b, n, j] and
+ *                          the per-sequence r_w_bias / r_r_bias gradient rows
+ *                          (scratch: fp32 [2 * B * N * (M+1) + 2 * B * N * 64]);
+ *   phase 2 (memory side): dk / dv of the rows j < M (outer products of the scratch with q + u / dout), dr, and
+ *                          du / dvb (+=: batch sums of the scratch rows).
  * The memory rows are detached (mem_transformer.py:461-475): their dk / dv feed only dW_kv.  Phase 2 must be ordered
  * after phase 1 (same stream or an event).  Same arguments as tgan_relattn_bwd otherwise.                        */
 int tgan_relattn_bwd_step(int phase, int dtype, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,

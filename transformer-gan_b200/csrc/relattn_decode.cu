@@ -189,9 +189,10 @@ relattn_dec_fwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
     }
 }
 
-// Fused backward for Q = 1.  dsbuf: fp32 [N, K, B] scratch (dS already multiplied by scale; batch index contiguous so
-// that the batch reduction of relattn_dec_dr reads it coalesced).
-template <typename T>
+// Fused backward for Q = 1.  dsbuf: fp32 [B, N, K] scratch (dS already multiplied by scale; one contiguous row per
+// warp, written 16 bytes per key quartet -- the [N, K, B] layout of an earlier version meant one isolated 4-byte
+// write per key).  Split mode appends P~ [B, N, K] and the per-sequence dq parts [2][B, N * 64].
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(128, 5)
 relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
                 const T* __restrict__ r, int64_t ldr, const float* __restrict__ u, const float* __restrict__ vb,
@@ -231,18 +232,18 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
         T* dkbase = dk + (int64_t)b * lddkv + col;
         T* dvbase = dv + (int64_t)b * lddkv + col;
         const int64_t kstride = (int64_t)a.B * ldkv, dstride = (int64_t)a.B * lddkv;
-        float* dsrow = dsbuf + (int64_t)n * a.K * a.B + b;  // entry j at dsrow[j * B]
+        float* dsrow = dsbuf + (int64_t)bn * a.K;            // entry j at dsrow[j]: a warp writes its own contiguous row
         const int64_t pw_off = (int64_t)a.N * a.K * a.B;    // split mode: the dropped weights P~ follow the dS block
         // keys a reset row does not attend to: zero gradients
         for (int j = kg; j < jlo; j += 4) {
-            if (!a.split) {
+            if constexpr (!SPLIT) {
                 float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 store8(dkbase + j * dstride, z);
                 store8(dvbase + j * dstride, z);
             }
             if (dc == 0) {
-                dsrow[(int64_t)j * a.B] = 0.f;
-                if (a.split) dsrow[(int64_t)j * a.B + pw_off] = 0.f;
+                dsrow[j] = 0.f;
+                if constexpr (SPLIT) dsrow[j + pw_off] = 0.f;
             }
         }
         extern __shared__ __align__(16) uint8_t fifo_raw[];
@@ -250,14 +251,14 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
         uint8_t* fifo = fifo_raw + threadIdx.x * CH;
         const uint32_t fifo_s = (uint32_t)__cvta_generic_to_shared(fifo);
         const uint32_t slot = blockDim.x * CH;
-        const int64_t kstep = 4 * kstride, rstep = 4 * ldr, dstep = 4 * dstride, sstep = 4 * (int64_t)a.B;
+        const int64_t kstep = 4 * kstride, rstep = 4 * ldr, dstep = 4 * dstride, sstep = 4;
         int j = jlo + kg;
         const T* kp = kbase + j * kstride;
         const T* rp = r + (int64_t)j * ldr + col;
         const T* vp = vbase + j * kstride;
         T* dkp = dkbase + j * dstride;
         T* dvp = dvbase + j * dstride;
-        float* dsp = dsrow + (int64_t)j * a.B;
+        float* dsp = dsrow + j;
         int jp = j;
         uint32_t wr = fifo_s;
         const uint32_t fifo_end = fifo_s + PF * 3 * slot;
@@ -300,23 +301,24 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
                 const bool keep = !a.thresh || attn_drop_keep(rowkey, j, a.thresh);
                 const float pw = keep ? pr * a.drop_scale : 0.f;
                 const float ds = pr * ((keep ? dp * a.drop_scale : 0.f) - delta) * a.scale;
-                float dk8[8], dv8[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    dk8[t] = ds * qu[t];
-                    dv8[t] = pw * g8[t];
                     dqk[t] = fmaf(ds, k8[t], dqk[t]);
                     dqr[t] = fmaf(ds, r8[t], dqr[t]);
                 }
                 // split mode: only the current row (the one whose dk / dv the dgrad chain needs) is written here;
                 // the memory rows are outer products of the saved (dS, P~) with (q + u, dO): relattn_dec_keys
-                if (!a.split || j == jhi) {
+                if (!SPLIT || j == jhi) {
+                    float dk8[8], dv8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) { dk8[t] = ds * qu[t]; dv8[t] = pw * g8[t]; }
                     store8(dkp, dk8);
                     store8(dvp, dv8);
                 }
-                if (dc == 0) {
-                    *dsp = ds;
-                    if (a.split) dsp[pw_off] = pw;
+                if constexpr (SPLIT) {  // two lanes of the key group write the two scratch values side by side
+                    if (dc < 2) dsp[dc ? pw_off : 0] = dc ? pw : ds;
+                } else {
+                    if (dc == 0) *dsp = ds;
                 }
             }
             dkp += dstep; dvp += dstep; dsp += sstep;
@@ -342,45 +344,74 @@ relattn_dec_bwd(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
     // du = column sums of the content part of dq, dvb of the position part (r_w_bias / r_r_bias are shared by all rows):
     // 128 float atomics per warp onto N * 128 addresses.  (A first version merged the warps of a CTA in shared memory
     // first; its head-matching loops with integer modulo cost more instructions than the whole key loop of short rows.)
+    // Split mode: the 128 x B*N atomics land 512-deep on N * 128 addresses -- on the critical path of the chain.  The
+    // per-sequence rows go to the scratch instead ([2][B, N * 64] after the dS / P~ blocks) and relattn_dec_bias sums
+    // them over the batch on the side stream.
     if (active && kg == 0) {
+        if constexpr (SPLIT) {
+            float* rows = dsbuf + 2 * (int64_t)a.N * a.K * a.B + (int64_t)b * a.N * HS + col;
+            store8(rows, dqk);
+            store8(rows + (int64_t)a.B * a.N * HS, dqr);
+        } else {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            atomicAdd(&du[col + t], dqk[t]);
-            atomicAdd(&dvb[col + t], dqr[t]);
+            for (int t = 0; t < 8; ++t) {
+                atomicAdd(&du[col + t], dqk[t]);
+                atomicAdd(&dvb[col + t], dqr[t]);
+            }
         }
     }
 }
 
-// dR[j, n, :] = sum_b dS[n, j, b] * (q[b, n, :] + r_r_bias[n, :])      (dS carries the 1/sqrt(d_head) factor)
-// One CTA per (key j, head n), 256 threads = 4 batch phases x 64 dims: thread (bq, d) sums b = bq, bq + 4, ...; the dS
-// value of a (b) step is one broadcast load per warp, the q row one coalesced 128-byte (bf16) line.  The four partial
-// sums meet in shared memory.  (Round 2's first version walked the batch with one thread per (j, 4 dims): 512
-// dependent-latency steps on uncoalesced 4-byte reads, 199 us per launch = a third of the generator update.)
-constexpr int DR_THREADS = 256;
+// du[c] += sum_b rows[0][b, c],  dvb[c] += sum_b rows[1][b, c]   (split mode, memory-side phase)
+__global__ void __launch_bounds__(256)
+relattn_dec_bias(const float* __restrict__ rows, float* __restrict__ du, float* __restrict__ dvb, int B, int NH) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const float* src = rows + (int64_t)blockIdx.y * B * NH;
+    float s = 0.f;
+    if (c < NH)
+        for (int b = threadIdx.y; b < B; b += 8) s += src[(int64_t)b * NH + c];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < NH) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(blockIdx.y ? &dvb[c] : &du[c], t);
+    }
+}
+
+// dR[j, n, :] += sum_b dS[b, n, j] * (q[b, n, :] + r_r_bias[n, :])      (dS carries the 1/sqrt(d_head) factor)
+// One CTA per (16-key tile, head n, batch slice): thread = (key jj, 4 dims); per sequence the CTA reads 16 consecutive
+// dS values (one 64-byte piece of the warp-contiguous [B, N, K] scratch rows) and the head's 128-byte q row.  The
+// batch is cut into DR_SLICES slices for parallelism (the whole reduction is 44 MFMA: latency, not throughput); the
+// slices meet in the zeroed dr through atomics (DR_SLICES-way contention).
+constexpr int DR_THREADS = 256, DR_KEYS = 16, DR_SLICES = 8;
 template <typename T>
 __global__ void __launch_bounds__(DR_THREADS)
 relattn_dec_dr(const T* __restrict__ q, int64_t ldq, const float* __restrict__ vb, const float* __restrict__ dsbuf,
                float* __restrict__ dr, int64_t lddr, DecArgs a) {
-    __shared__ float s_acc[4][HS], s_sum[4];
-    const int j = blockIdx.x, n = blockIdx.y;
-    const int d = threadIdx.x & 63, bq = threadIdx.x >> 6;
-    const float* ds = dsbuf + ((int64_t)n * a.K + j) * a.B;
-    const T* qp = q + n * HS + d;
-    float acc = 0.f, sum = 0.f;
+    const int n = blockIdx.y;
+    const int jj = threadIdx.x >> 4, dq4 = (threadIdx.x & 15) * 4;
+    const int j = blockIdx.x * DR_KEYS + jj;
+    const int per = (a.B + DR_SLICES - 1) / DR_SLICES;
+    const int b0 = blockIdx.z * per, b1 = min(a.B, b0 + per);
+    if (j >= a.K) return;
+    const float* ds = dsbuf + (int64_t)n * a.K + j;  // dS[b, n, j] at ds[b * N * K]
+    const int64_t bstride = (int64_t)a.N * a.K;
+    const T* qp = q + n * HS + dq4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, sum = 0.f;
 #pragma unroll 8
-    for (int b = bq; b < a.B; b += 4) {
-        const float w = ds[b];
-        acc = fmaf(w, to_f(qp[(int64_t)b * ldq]), acc);
+    for (int b = b0; b < b1; ++b) {
+        const float w = ds[b * bstride];
+        const T* qr = qp + (int64_t)b * ldq;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = fmaf(w, to_f(qr[t]), acc[t]);
         sum += w;
     }
-    s_acc[bq][d] = acc;
-    if (d == 0) s_sum[bq] = sum;
-    __syncthreads();
-    if (bq == 0) {
-        const float tot = s_acc[0][d] + s_acc[1][d] + s_acc[2][d] + s_acc[3][d];
-        const float st = s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3];
-        dr[(int64_t)j * lddr + n * HS + d] = fmaf(st, vb[n * HS + d], tot);
-    }
+    float* dst = dr + (int64_t)j * lddr + n * HS + dq4;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) atomicAdd(dst + t, fmaf(sum, vb[n * HS + dq4 + t], acc[t]));
 }
 
 // Memory-row half of the split backward: dk[j, b, n, :] = dS[n, j, b] (q + r_w_bias)[b, n, :],
@@ -397,7 +428,7 @@ relattn_dec_keys(const T* __restrict__ q, int64_t ldq, const float* __restrict__
         const int b = blockIdx.y * 32 + e / NC, c = e % NC;
         if (b >= a.B) break;
         const int n = c >> 3, col = 8 * c;
-        const float* sp = dsbuf + ((int64_t)n * a.K + j) * a.B + b;
+        const float* sp = dsbuf + ((int64_t)b * a.N + n) * a.K + j;
         const float ds = sp[0], pw = sp[pw_off];
         float x[8], uu[8], g8[8], dk8[8], dv8[8];
         load8(q + (int64_t)b * ldq + col, x);
@@ -476,11 +507,16 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
             TGAN_COUNT_LAUNCH();
             TGAN_LAUNCH_OK();
         }
-        dim3 g2(a.K, N);
+        TGAN_CUDA_OK(cudaMemset2DAsync(dr, lddr * sizeof(float), 0, (size_t)N * HS * sizeof(float), a.K, st));
+        dim3 g2(ceil_div(a.K, DR_KEYS), N, DR_SLICES);
         if (dtype == TGAN_F32)
             relattn_dec_dr<float><<<g2, DR_THREADS, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
         else
             relattn_dec_dr<bf16><<<g2, DR_THREADS, 0, st>>>((const bf16*)q, ldq, vb, scratch, dr, lddr, a);
+        TGAN_COUNT_LAUNCH();
+        TGAN_LAUNCH_OK();
+        relattn_dec_bias<<<dim3(ceil_div(N * HS, 32), 2), dim3(32, 8), 0, st>>>(scratch + 2 * (int64_t)N * a.K * B, du, dvb, B,
+                                                                             N * HS);
         TGAN_COUNT_LAUNCH();
         TGAN_LAUNCH_OK();
         return 0;
@@ -490,23 +526,25 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
     const size_t sm_f32 = (size_t)PF * 3 * DW * 32 * 32, sm_bf16 = (size_t)PF * 3 * DW * 32 * 16;
     static bool attr = false;
     if (!attr) {  // fp32: 48 KB of FIFO + the static du / dvb staging exceeds the default 48 KB window
-        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_dec_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF * 3 * 128 * 32));
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_dec_bwd<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF * 3 * 128 * 32));
+        TGAN_CUDA_OK(cudaFuncSetAttribute(relattn_dec_bwd<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF * 3 * 128 * 32));
         attr = true;
     }
-    if (dtype == TGAN_F32)
-        relattn_dec_bwd<float><<<grid, DW * 32, sm_f32, st>>>((const float*)q, ldq, (const float*)k, (const float*)v, ldkv,
-                                                          (const float*)r, ldr, u, vb, reset, (const float*)out,
-                                                          (const float*)dout, ldo, lse, (float*)dq, (float*)dk,
-                                                          (float*)dv, lddkv, scratch, du, dvb, a);
-    else
-        relattn_dec_bwd<bf16><<<grid, DW * 32, sm_bf16, st>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv,
-                                                         (const bf16*)r, ldr, u, vb, reset, (const bf16*)out,
-                                                         (const bf16*)dout, ldo, lse, (bf16*)dq, (bf16*)dk, (bf16*)dv,
-                                                         lddkv, scratch, du, dvb, a);
+#define TGAN_DEC_BWD(T, S, SM)                                                                                         \
+    relattn_dec_bwd<T, S><<<grid, DW * 32, SM, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)r, ldr, u, \
+                                                     vb, reset, (const T*)out, (const T*)dout, ldo, lse, (T*)dq, (T*)dk,  \
+                                                     (T*)dv, lddkv, scratch, du, dvb, a)
+    if (dtype == TGAN_F32) {
+        if (phase) TGAN_DEC_BWD(float, true, sm_f32); else TGAN_DEC_BWD(float, false, sm_f32);
+    } else {
+        if (phase) TGAN_DEC_BWD(bf16, true, sm_bf16); else TGAN_DEC_BWD(bf16, false, sm_bf16);
+    }
+#undef TGAN_DEC_BWD
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     if (phase == 1) return 0;
-    dim3 g2(a.K, N);
+    TGAN_CUDA_OK(cudaMemset2DAsync(dr, lddr * sizeof(float), 0, (size_t)N * HS * sizeof(float), a.K, st));
+    dim3 g2(ceil_div(a.K, DR_KEYS), N, DR_SLICES);
     if (dtype == TGAN_F32)
         relattn_dec_dr<float><<<g2, DR_THREADS, 0, st>>>((const float*)q, ldq, vb, scratch, dr, lddr, a);
     else

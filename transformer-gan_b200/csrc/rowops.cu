@@ -674,7 +674,7 @@ extern "C" int tgan_ln_bwd(int dtype, const void* dy, int64_t lddy, const float*
                    "tgan_ln_bwd: DP <= 1024, multiples of 8, 16-byte aligned z / gamma");
     uint32_t th = (drop_p > 0.f && dz_drop) ? dropout_thresh(drop_p) : 0u;
     float ds = (drop_p > 0.f && dz_drop) ? 1.f / (1.f - drop_p) : 1.f;
-    int blocks = min(ceil_div(rows, WPB), 148 * 4);
+    int blocks = min(ceil_div(rows, WPB), 148 * 4);  // (4 rows per warp for small calls was measured: 14 -> 19 us at 512 rows)
     int rpb = ceil_div(rows, blocks);
     blocks = ceil_div(rows, rpb);
     size_t smem = 3 * DP * sizeof(float);

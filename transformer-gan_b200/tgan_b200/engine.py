@@ -386,7 +386,7 @@ class TxlEngine:
         (every gradient kernel of the stack accumulates: TMA reduce-add / atomics)."""
         if self._window is not None:
             raise L.TganError("gradient window already open")
-        self.gv.zero_()
+        self.gvec.zero_()
         self.gmat.zero_()
         self._window = 0
 
@@ -766,8 +766,9 @@ class TxlEngine:
             dkv = self._buf(KR, 2 * NH)
             dr32 = dr_all32[:, l * NH:(l + 1) * NH]  # view: this layer's column block
             split = side is not None and Q == 1  # single-token step: memory-side half on the second side stream
-            delta = self._buf(B * d.n_head * (Q if Q > 1 else (2 * K if split else K)),
-                              dtype=torch.float32)  # Q == 1: dS (and P~) scratch [N, K, B]
+            # Q == 1: dS scratch [B, N, K]; split: + P~ [B, N, K] + the per-sequence r_w_bias / r_r_bias parts [2][B, NH]
+            delta = self._buf(B * d.n_head * (Q if Q > 1 else (2 * K if split else K)) + (2 * B * NH if split else 0),
+                              dtype=torch.float32)
             if split:
                 args = (sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt, sv.lse,
                         delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, M, ctx.msl,
@@ -804,7 +805,8 @@ class TxlEngine:
                 reducer.reduce(gv, v0, v1 - v0)
         if side is not None:
             main.wait_stream(side)
-            main.wait_stream(side2)
+            if Q == 1:  # (a stream that never forked from a capturing stream must not be joined into the capture)
+                main.wait_stream(side2)
             keep.clear()
         # ---- r_net weight gradients of all layers: dWr_all = dR_all^T pos_emb
         NL = d.n_layer * NH

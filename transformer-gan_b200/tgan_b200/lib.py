@@ -240,7 +240,7 @@ def relattn_bwd_step(phase, q, k, v, ldkv, r, u, vb, reset, out, dout, lse, scra
                      M, msl, same_length, scale, drop_p, seed, site, k_off=0, v_off=0, dk_off=0, dv_off=0):
     """single-token (Q = 1) attention backward in two launches: phase 1 = query side (dq, du / dvb, dk / dv of the
     current row; on the dgrad chain), phase 2 = memory side (dk / dv of the rows j < M, dR; needed only by weight
-    gradients: a side stream).  scratch: fp32 [2 * B * N * (M + 1)]."""
+    gradients: a side stream).  scratch: fp32 [2 * B * N * (M + 1) + 2 * B * N * 64]."""
     es = q.element_size()
     _call("tgan_relattn_bwd_step", phase, dtype_code(q.dtype), q.data_ptr(), q.stride(0), k.data_ptr() + k_off * es,
           v.data_ptr() + v_off * es, ldkv, r.data_ptr(), r.stride(0), _ptr(u), _ptr(vb), _ptr(reset),
