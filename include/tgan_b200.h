@@ -251,6 +251,23 @@ int tgan_nccl_init(const void* id128, int nranks, int rank, void** comm_out);
 int tgan_allreduce_bucket(void* comm, void* buf, int64_t count, int dtype, void* stream);
 int tgan_nccl_destroy(void* comm);
 
+/* ---- device-side batch assembly: data_utils.py:226-304 (get_iterator), :307-368, :370-434 ---------------------
+ * The corpus of a split lives in HBM: corpus int32 [sum of lengths] (every sequence with its start token,
+ * data_utils.py:121-141), seq_off int64 [n_seq], seq_len int32 [n_seq], perm int32 [n_seq] (the epoch's permutation).
+ * tgan_batch_next: one training batch.  tracker int32 [2*B + 1] = column sequence index [B], column position [B],
+ * next_idx (initially i, 0, B as in :236-237) is advanced in place; data / target int64 [bptt, B] are filled (pad_id
+ * beyond each column's n_new), reset uint8 [B] and *n_tokens (device int32, = batch_token_num) are written.
+ * plan_src / plan_n (int64 / int32 [B], may be NULL) receive the plan for inspection.  random_crop and
+ * append_note_status are off (as in every shipped config).  n_tokens == 0 means the permutation is used up: the host
+ * reshuffles (:285-293).
+ * tgan_batch_gather: fills data (and target unless NULL) from a given plan: column i gets plan_n[i] tokens starting at
+ * corpus[plan_src[i]] -- eval_iterator's closed-form plan, get_dis_iterator's host-drawn random offsets.        */
+int tgan_batch_next(const int32_t* corpus, const int64_t* seq_off, const int32_t* seq_len, const int32_t* perm, int n_seq,
+                    int32_t* tracker, int64_t* plan_src, int32_t* plan_n, int64_t* data, int64_t* target, uint8_t* reset,
+                    int32_t* n_tokens, int bptt, int B, int64_t pad_id, void* stream);
+int tgan_batch_gather(const int32_t* corpus, const int64_t* plan_src, const int32_t* plan_n, int64_t* data,
+                      int64_t* target, int bptt, int B, int64_t pad_id, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

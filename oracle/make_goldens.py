@@ -213,6 +213,48 @@ def run_gan_ppo_case(name, shape: O.TxlShape, seed, B, dis_tgt_len=16, context_l
     print("wrote", name, {k: float(v) for k, v in out.items() if k.endswith("_loss")})
 
 
+def run_batches_case(name, seed=21, n_seq=37, B=5, bptt=8, n_train=60, n_dis=12):
+    """Batches of the UNMODIFIED reference iterators (data_utils.py:206-434) on a seeded ragged corpus: the training
+    iterator through two reshuffles, the one-pass (do_shuffle False) variant, eval_iterator with and without rank
+    sharding, and get_dis_iterator under a seeded global numpy RNG."""
+    sys.path.insert(0, "/root/reference/model")
+    import data_utils as DU
+    import data_oracle
+    seqs = data_oracle.ragged_corpus(seed, n_seq)
+    ds = DU.MusicDataset.__new__(DU.MusicDataset)  # bypass the directory loader: the iterators only read these fields
+    ds._vocab = DU.BaseVocab(["<S>", "<PAD>"] + [f"t{i}" for i in range(308)])
+    tens = [torch.from_numpy(a) for a in seqs]
+    ds._train_data = ds._valid_data = ds._test_data = tens
+    ds._train_seq_length = ds._valid_seq_length = ds._test_seq_length = np.array([len(a) for a in seqs], dtype=np.int32)
+    ns = ref_harness._Node
+    ds.cfg = ns(TRAIN=ns(append_note_status=False, random_crop=False, mem_length=16))
+    out = {"seed": seed, "n_seq": n_seq, "B": B, "bptt": bptt, "pad_id": ds.vocab.pad_id}
+
+    def dump(tag, it, n, has_target=True):
+        k = 0
+        for item in it:
+            if k >= n:
+                break
+            out[f"{tag}.data{k}"] = item[0].numpy().copy()
+            if has_target:
+                out[f"{tag}.target{k}"] = item[1].numpy().copy()
+                out[f"{tag}.reset{k}"] = np.asarray(item[2].numpy() if hasattr(item[2], "numpy") else item[2]).copy()
+                out[f"{tag}.ntok{k}"] = np.array(int(item[3]))
+            else:
+                out[f"{tag}.ntok{k}"] = np.array(int(item[1]))
+            k += 1
+        out[f"{tag}.n"] = k
+
+    dump("train", ds.get_iterator(B, bptt, "cpu", "train", True, seed=7)(), n_train)
+    dump("once", ds.get_iterator(B, bptt, "cpu", "train", False)(), 10 ** 6)
+    dump("eval", ds.eval_iterator(B, bptt, "cpu", "valid")(), 10 ** 6)
+    dump("eval_r1", ds.eval_iterator(B, bptt, "cpu", "valid", local_rank=1, world_size=2)(), 10 ** 6)
+    np.random.seed(99)  # get_dis_iterator draws its offsets from the GLOBAL numpy RNG (:349)
+    dump("dis", ds.get_dis_iterator(B, bptt, "cpu", "train", True, seed=5)(), n_dis, has_target=False)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, {k: out[k] for k in out if k.endswith(".n")})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -235,6 +277,7 @@ def main():
         "gan_bert_tiny": lambda n: run_gan_case(n, gan, seed=15, B=3, dis_type="bert", loss_type="wgan-gp"),
         "gan_cnn_tiny": lambda n: run_gan_case(n, gan, seed=16, B=2, dis_type="cnn", loss_type="rsgan"),
         "gan_ppo_tiny": lambda n: run_gan_ppo_case(n, gan, seed=17, B=3),
+        "batches_tiny": lambda n: run_batches_case(n),
     }
     for name, fn in cases.items():
         if not only or name in only:

@@ -50,6 +50,8 @@ _SIGS = {
                          F, F, U, U, I, P],
     "tgan_relattn_bwd_step": [I, I, P, L, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P, P, L, P, L, P, P, I, I, I, I, I,
                               F, F, U, U, P],
+    "tgan_batch_next": [P, P, P, P, I, P, P, P, P, P, P, P, I, I, L, P],
+    "tgan_batch_gather": [P, P, P, P, P, I, I, L, P],
     "tgan_ce_fwd": [P, L, P, P, P, I, I, P],
     "tgan_ce_bwd": [I, P, L, P, P, P, P, L, I, I, I, P],
     "tgan_gumbel_st_fwd": [P, L, P, L, F, P, P, L, P, L, P, I, I, U, U, P],
@@ -247,6 +249,18 @@ def relattn_bwd_step(phase, q, k, v, ldkv, r, u, vb, reset, out, dout, lse, scra
           out.data_ptr(), dout.data_ptr(), out.stride(0), _ptr(lse), _ptr(scratch), dq.data_ptr(),
           dk.data_ptr() + dk_off * es, dv.data_ptr() + dv_off * es, lddkv, dr.data_ptr(), dr.stride(0),
           _ptr(du), _ptr(dvb), B, N, M, msl, int(same_length), scale, drop_p, seed, site, _stream())
+
+
+def batch_next(corpus, seq_off, seq_len, perm, n_seq, tracker, data, target, reset, n_tokens, bptt, B, pad_id,
+               plan_src=None, plan_n=None):
+    _call("tgan_batch_next", corpus.data_ptr(), seq_off.data_ptr(), seq_len.data_ptr(), perm.data_ptr(), n_seq,
+          tracker.data_ptr(), _ptr(plan_src), _ptr(plan_n), data.data_ptr(), target.data_ptr(), reset.data_ptr(),
+          n_tokens.data_ptr(), bptt, B, pad_id, _stream())
+
+
+def batch_gather(corpus, plan_src, plan_n, data, target, bptt, B, pad_id):
+    _call("tgan_batch_gather", corpus.data_ptr(), plan_src.data_ptr(), plan_n.data_ptr(), data.data_ptr(), _ptr(target),
+          bptt, B, pad_id, _stream())
 
 
 def dropout(src, dst, rows, cols, lds, ldd, p, seed, site, src_off=0, dst_off=0):
