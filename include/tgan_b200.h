@@ -251,6 +251,17 @@ int tgan_nccl_init(const void* id128, int nranks, int rank, void** comm_out);
 int tgan_allreduce_bucket(void* comm, void* buf, int64_t count, int dtype, void* stream);
 int tgan_nccl_destroy(void* comm);
 
+/* ---- LAMB: lamb.py:57-118 ("paper v3": no bias correction) with clip_grad_norm_ (train.py:914-921) folded in ----
+ * Flat fp32 buffers param / grad / m / v / upd (scratch) of the optimizer group; chunks int64 [n_chunks][3] =
+ * (tensor id, first element, count <= 16384) cuts them into per-tensor pieces; norms fp32 [2 * n_tensors] scratch
+ * (per-tensor sum p^2, sum adam_step^2; afterwards the reference's state['weight_norm'] / ['adam_norm'] squared).
+ * p -= lr * trust * (m / (sqrt(v) + eps) + wd * p), trust = clamp(|p|, 0, 10) / (|adam_step| + eps), 1 when either
+ * norm is 0 or adam != 0.  Gradients are scaled by grad_scale and by min(1, clip / (sqrt(*gnorm_sq) * grad_scale + 1e-6))
+ * when gnorm_sq != NULL and clip > 0.                                                                           */
+int tgan_lamb_step(float* param, const float* grad, float* m, float* v, float* upd, const int64_t* chunks, int n_chunks,
+                   float* norms, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   const float* gnorm_sq, float clip, float grad_scale, int adam, void* stream);
+
 /* ---- device-side batch assembly: data_utils.py:226-304 (get_iterator), :307-368, :370-434 ---------------------
  * The corpus of a split lives in HBM: corpus int32 [sum of lengths] (every sequence with its start token,
  * data_utils.py:121-141), seq_off int64 [n_seq], seq_len int32 [n_seq], perm int32 [n_seq] (the epoch's permutation).

@@ -255,6 +255,38 @@ def run_batches_case(name, seed=21, n_seq=37, B=5, bptt=8, n_train=60, n_dis=12)
     print("wrote", name, {k: out[k] for k in out if k.endswith(".n")})
 
 
+def lamb_case_tensors(seed):
+    """Seeded parameter / gradient tensors of the LAMB fixture: a matrix, an all-zero vector (trust ratio 1), a long
+    vector whose norm exceeds the clamp at 10, and a tensor that spans several 16384-element chunks."""
+    g = torch.Generator().manual_seed(seed)
+    params = [torch.randn(7, 5, generator=g), torch.zeros(4), 20.0 * torch.randn(3000, generator=g),
+              0.02 * torch.randn(150, 300, generator=g)]
+    grads = [[torch.randn(p.shape, generator=g) * (0.5 + k) for p in params] for k in range(3)]
+    return params, grads
+
+
+def run_lamb_case(name, seed=23):
+    """Three steps of the UNMODIFIED reference ``lamb.Lamb`` (lamb.py:57-118), weight decay 0.01."""
+    sys.path.insert(0, "/root/reference/model")
+    import warnings
+    import lamb
+    params, grads = lamb_case_tensors(seed)
+    ps = [torch.nn.Parameter(p.clone()) for p in params]
+    opt = lamb.Lamb(ps, lr=0.01, weight_decay=0.01)
+    out = {"seed": seed, "lr": 0.01, "weight_decay": 0.01, "steps": len(grads)}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, gs in enumerate(grads):
+            for p, g in zip(ps, gs):
+                p.grad = g.clone()
+            opt.step()
+            out[f"trust{k}"] = np.array([float(opt.state[p]["trust_ratio"]) for p in ps])
+            for i, p in enumerate(ps):
+                out[f"p{k}.{i}"] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, out["trust2"])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -278,6 +310,7 @@ def main():
         "gan_cnn_tiny": lambda n: run_gan_case(n, gan, seed=16, B=2, dis_type="cnn", loss_type="rsgan"),
         "gan_ppo_tiny": lambda n: run_gan_ppo_case(n, gan, seed=17, B=3),
         "batches_tiny": lambda n: run_batches_case(n),
+        "lamb_tiny": lambda n: run_lamb_case(n),
     }
     for name, fn in cases.items():
         if not only or name in only:

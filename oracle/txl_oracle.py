@@ -533,3 +533,25 @@ def categorical_from_uniform(probs: torch.Tensor, u: float):
     steps = torch.cat([torch.zeros(1, dtype=torch.float64), c])
     margin = float((steps - target).abs().min())
     return idx, margin
+
+
+# ----------------------------------------------------------------------------------------------
+# f2  LAMB                                                                        lamb.py:57-118
+# ----------------------------------------------------------------------------------------------
+def lamb_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
+              exp_avg_sq: List[torch.Tensor], lr: float, betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0,
+              adam: bool = False) -> List[float]:
+    """One ``Lamb.step`` in place (lamb.py:64-116; "paper v3", no bias correction); returns the trust ratios."""
+    ratios = []
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        m.mul_(betas[0]).add_(g, alpha=1 - betas[0])                                    # :87
+        v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])                             # :89
+        weight_norm = p.norm(p=2).clamp(0, 10)                                          # :97
+        adam_step = m / v.sqrt().add(eps)                                               # :99
+        if weight_decay != 0:
+            adam_step = adam_step + weight_decay * p                                    # :100-101
+        adam_norm = adam_step.norm(p=2)                                                 # :103
+        trust = 1.0 if (weight_norm == 0 or adam_norm == 0) else float(weight_norm / (adam_norm + eps))  # :105-108
+        ratios.append(trust)
+        p.add_(adam_step, alpha=-lr * (1.0 if adam else trust))                         # :113-116
+    return ratios

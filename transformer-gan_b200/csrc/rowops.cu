@@ -576,6 +576,56 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// LAMB (lamb.py:57-118; "paper v3": no bias correction) over a flat parameter buffer cut into per-tensor chunks.
+// chunk table: int64 [n_chunks][3] = (tensor id, first element, element count <= LAMB_CHUNK).
+// stage 1: moments, adam_step = m / (sqrt(v) + eps) + wd * p (kept in `upd`), per-tensor sums of p^2 and adam_step^2;
+// stage 2: p -= lr * trust * adam_step with trust = clamp(|p|, 0, 10) / (|adam_step| + eps), 1 when either norm is 0.
+constexpr int LAMB_CHUNK = 16384;
+__global__ void __launch_bounds__(256)
+lamb_stage1_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   float* __restrict__ upd, const int64_t* __restrict__ chunks, float* __restrict__ norms, float b1,
+                   float b2, float eps, float wd, const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+    __shared__ float red[2][8];
+    const int64_t tid = chunks[3 * blockIdx.x], e0 = chunks[3 * blockIdx.x + 1], cnt = chunks[3 * blockIdx.x + 2];
+    float cs = grad_scale;
+    if (gnorm_sq && clip > 0.f) {
+        const float coef = clip / (sqrtf(*gnorm_sq) * grad_scale + 1e-6f);  // torch.nn.utils.clip_grad_norm_
+        if (coef < 1.f) cs *= coef;
+    }
+    float sp = 0.f, su = 0.f;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int64_t e = e0 + i;
+        const float gr = g[e] * cs, pv = p[e];
+        const float mm = b1 * m[e] + (1.f - b1) * gr;
+        const float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+        m[e] = mm; v[e] = vv;
+        const float a = mm / (sqrtf(vv) + eps) + wd * pv;
+        upd[e] = a;
+        sp = fmaf(pv, pv, sp);
+        su = fmaf(a, a, su);
+    }
+    sp = warp_sum(sp); su = warp_sum(su);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = sp; red[1][warp] = su; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        atomicAdd(&norms[2 * tid + threadIdx.x], t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lamb_stage2_kernel(float* __restrict__ p, const float* __restrict__ upd, const int64_t* __restrict__ chunks,
+                   const float* __restrict__ norms, float lr, float eps, int adam) {
+    const int64_t tid = chunks[3 * blockIdx.x], e0 = chunks[3 * blockIdx.x + 1], cnt = chunks[3 * blockIdx.x + 2];
+    const float wn = fminf(sqrtf(norms[2 * tid]), 10.f), un = sqrtf(norms[2 * tid + 1]);
+    const float trust = (adam || wn == 0.f || un == 0.f) ? 1.f : wn / (un + eps);
+    const float step = lr * trust;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) p[e0 + i] -= step * upd[e0 + i];
+}
+
 inline int grid_for(int64_t n, int threads) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = 148LL * 16;
@@ -810,6 +860,26 @@ extern "C" int tgan_adam_step(float* param, const float* grad, float* m, float* 
     float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     adam_kernel<<<grid_for(n, 256), 256, 0, ST>>>(param, grad, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
                                                    gnorm_sq, clip, grad_scale);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LAMB: lamb.py:57-118 (+ clip_grad_norm_, train.py:914-921) on flat buffers
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int tgan_lamb_step(float* param, const float* grad, float* m, float* v, float* upd, const int64_t* chunks,
+                              int n_chunks, float* norms, int n_tensors, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, const float* gnorm_sq, float clip, float grad_scale, int adam,
+                              void* stream) {
+    if (n_chunks <= 0) return 0;
+    TGAN_CHECK_ARG(param && grad && m && v && upd && chunks && norms && n_tensors > 0, "tgan_lamb_step: null argument");
+    TGAN_CUDA_OK(cudaMemsetAsync(norms, 0, sizeof(float) * 2 * (size_t)n_tensors, ST));
+    lamb_stage1_kernel<<<n_chunks, 256, 0, ST>>>(param, grad, m, v, upd, chunks, norms, beta1, beta2, eps, weight_decay,
+                                                  gnorm_sq, clip, grad_scale);
+    TGAN_COUNT_LAUNCH();
+    TGAN_LAUNCH_OK();
+    lamb_stage2_kernel<<<n_chunks, 256, 0, ST>>>(param, upd, chunks, norms, lr, eps, adam);
     TGAN_COUNT_LAUNCH();
     TGAN_LAUNCH_OK();
     return 0;

@@ -149,3 +149,49 @@ class FusedClipAdam:
         # engine to re-pack its kernel-private parameter copies at the next forward
         from .engine import notify_params_updated
         notify_params_updated()
+
+
+class FusedLamb:
+    """The reference's LAMB (``lamb.Lamb``, lamb.py:57-118: moments without bias correction, per-tensor trust ratio
+    ``clamp(|w|, 0, 10) / (|adam_step| + eps)``) preceded by ``clip_grad_norm_`` (train.py:914-921), on the flat buffers of
+    a ``FlatParams`` group through the CUDA library: tgan_sumsq + tgan_lamb_step (two passes over the group: moments /
+    per-tensor norms, then the update).  Same call surface as ``FusedClipAdam``.  CUDA only."""
+
+    CHUNK = 16384
+
+    def __init__(self, fp: FlatParams, lr: float, betas=(0.9, 0.999), eps: float = 1e-6, weight_decay: float = 0.0,
+                 clip: float = 0.0, world: int = 1, reduce: bool = True, adam: bool = False):
+        from . import lib as L
+        self.L = L
+        self.fp, self.lr, self.betas, self.eps, self.wd, self.clip, self.world = fp, lr, betas, eps, weight_decay, clip, world
+        self.reduce, self.adam = reduce, adam
+        dev = fp.flat.device
+        self.m, self.v, self.upd = torch.zeros_like(fp.flat), torch.zeros_like(fp.flat), torch.empty_like(fp.flat)
+        rows = []
+        for tid, (off, k) in enumerate(fp.slices):
+            for c0 in range(0, k, self.CHUNK):
+                rows.append([tid, off + c0, min(self.CHUNK, k - c0)])
+        self.chunks = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self.norms = torch.zeros(2 * len(fp.slices), dtype=torch.float32, device=dev)
+        self.gnorm_sq = torch.zeros(1, device=dev)
+        self.steps = 0
+
+    def step(self, lr: Optional[float] = None):
+        fp, L = self.fp, self.L
+        self.steps += 1
+        if self.reduce:
+            allreduce_gradients(fp.grad, self.world)
+        self.gnorm_sq.zero_()
+        L.sumsq(fp.grad, fp.grad.numel(), self.gnorm_sq)
+        L.lamb_step(fp.flat, fp.grad, self.m, self.v, self.upd, self.chunks, self.chunks.shape[0], self.norms,
+                    len(fp.slices), self.lr if lr is None else lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                    self.gnorm_sq, self.clip, 1.0 / self.world, adam=self.adam)
+        fp.zero_grad()
+        from .engine import notify_params_updated
+        notify_params_updated()
+
+    def trust_ratios(self) -> torch.Tensor:
+        """per-tensor trust ratio of the last step (the reference keeps it in ``state['trust_ratio']``)."""
+        n = self.norms.view(-1, 2).sqrt()
+        wn, un = n[:, 0].clamp(0, 10), n[:, 1]
+        return torch.where((wn == 0) | (un == 0), torch.ones_like(wn), wn / (un + self.eps))

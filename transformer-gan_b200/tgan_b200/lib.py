@@ -50,6 +50,7 @@ _SIGS = {
                          F, F, U, U, I, P],
     "tgan_relattn_bwd_step": [I, I, P, L, P, P, L, P, L, P, P, P, P, P, L, P, P, P, P, P, L, P, L, P, P, I, I, I, I, I,
                               F, F, U, U, P],
+    "tgan_lamb_step": [P, P, P, P, P, P, I, P, I, F, F, F, F, F, P, F, F, I, P],
     "tgan_batch_next": [P, P, P, P, I, P, P, P, P, P, P, P, I, I, L, P],
     "tgan_batch_gather": [P, P, P, P, P, I, I, L, P],
     "tgan_ce_fwd": [P, L, P, P, P, I, I, P],
@@ -249,6 +250,13 @@ def relattn_bwd_step(phase, q, k, v, ldkv, r, u, vb, reset, out, dout, lse, scra
           out.data_ptr(), dout.data_ptr(), out.stride(0), _ptr(lse), _ptr(scratch), dq.data_ptr(),
           dk.data_ptr() + dk_off * es, dv.data_ptr() + dv_off * es, lddkv, dr.data_ptr(), dr.stride(0),
           _ptr(du), _ptr(dvb), B, N, M, msl, int(same_length), scale, drop_p, seed, site, _stream())
+
+
+def lamb_step(param, grad, m, v, upd, chunks, n_chunks, norms, n_tensors, lr, beta1, beta2, eps, weight_decay, gnorm_sq,
+              clip, grad_scale, adam=False):
+    _call("tgan_lamb_step", param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), upd.data_ptr(),
+          chunks.data_ptr(), n_chunks, norms.data_ptr(), n_tensors, lr, beta1, beta2, eps, weight_decay, _ptr(gnorm_sq),
+          clip, grad_scale, int(adam), _stream())
 
 
 def batch_next(corpus, seq_off, seq_len, perm, n_seq, tracker, data, target, reset, n_tokens, bptt, B, pad_id,
