@@ -29,12 +29,12 @@ batch_next_kernel(const int32_t* __restrict__ corpus, const int64_t* __restrict_
                   int32_t* __restrict__ tracker, int64_t* __restrict__ plan_src, int32_t* __restrict__ plan_n,
                   int64_t* __restrict__ data, int64_t* __restrict__ target, uint8_t* __restrict__ reset,
                   int32_t* __restrict__ n_tokens, int bptt, int B, int64_t pad_id) {
-    extern __shared__ int32_t sh[];  // idx[B], pos[B], cur_len[B], n[B]; then int64 src[B]
+    extern __shared__ __align__(16) int32_t sh[];  // idx[B], pos[B], cur_len[B], n[B]; then int64 src[B]
     int32_t* s_idx = sh;
     int32_t* s_pos = sh + B;
     int32_t* s_len = sh + 2 * B;
     int32_t* s_n = sh + 3 * B;
-    int64_t* s_src = reinterpret_cast<int64_t*>(sh + 4 * B + (B & 1));
+    int64_t* s_src = reinterpret_cast<int64_t*>(sh + 4 * B);  // 16 * B bytes in: 8-byte aligned
     for (int i = threadIdx.x; i < B; i += BT) {
         const int idx = tracker[i];
         s_idx[i] = idx;
@@ -108,7 +108,7 @@ extern "C" int tgan_batch_next(const int32_t* corpus, const int64_t* seq_off, co
     TGAN_CHECK_ARG(corpus && seq_off && seq_len && perm && tracker && data && target && reset && n_tokens,
                    "tgan_batch_next: null argument");
     TGAN_CHECK_ARG(n_seq > 0 && bptt > 0 && B > 0 && B <= 8192, "tgan_batch_next: bad dims (batch <= 8192)");
-    const size_t smem = (size_t)(4 * B + (B & 1)) * sizeof(int32_t) + (size_t)B * sizeof(int64_t);
+    const size_t smem = (size_t)4 * B * sizeof(int32_t) + (size_t)B * sizeof(int64_t);
     static bool attr = false;
     if (!attr) {
         TGAN_CUDA_OK(cudaFuncSetAttribute(batch_next_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24 + 8));
