@@ -53,3 +53,52 @@ def test_device_rng_draws_follow_the_distribution():
     freq = torch.bincount(ids.cpu(), minlength=V).double() / B
     assert (freq - want).abs().max() < 0.015
     assert freq[want == 0].sum() == 0
+
+
+@pytest.mark.parametrize("technique,topk,p,k_empty", [("topk", 32, 0.0, 0), ("topk", 6, 0.0, 2), ("nucleus", None, 0.9, 0)])
+def test_batched_generation_loop_matches_generate_py(technique, topk, p, k_empty):
+    """MemTransformerLM.generate_batched (device-side loop: single-token forward with the K/V cache + tgan_sample_tokens,
+    ids fed back on the device) against generate.py:207-304 restated with the oracle, sequence by sequence, under the
+    same injected uniforms: ids bit-exact (fp32 mode) along every sequence up to the first draw whose uniform falls
+    within rounding distance of a CDF step."""
+    from test_model_gpu import build
+    shape = O.TxlShape(n_layer=2, n_head=4, d_model=40, d_inner=72, n_token=310, mem_len=12, same_length=True)
+    seed, B, T0, G, temperature = 31, 3, 3, 20, 0.95
+    model = build(shape, seed, 1, torch.float32).eval()
+    g = torch.Generator().manual_seed(8)
+    start = torch.randint(2, 310, (T0, B), generator=g)
+    U = torch.rand(G, B, generator=g)
+    empty_tok = 37
+    if k_empty:  # make the suppressed token likely, so that runs of it (and hence the suppression) actually occur
+        with torch.no_grad():
+            model.crit.out_layers[0].bias[empty_tok] += 6.0
+    ids, _ = model.generate_batched(start.cuda(), G, technique=technique, topk=topk, top_p=p, temperature=temperature,
+                                    exclude_bos=True, empty_token=empty_tok, num_empty_tokens_to_ignore=k_empty,
+                                    uniforms=U.cuda())
+    torch.cuda.synchronize()
+    ids = ids.cpu()
+    params = {k: v.double() for k, v in O.init_params(shape, seed).items()}
+    if k_empty:
+        params["crit.out_layers.0.bias"] = params["crit.out_layers.0.bias"].clone()
+        params["crit.out_layers.0.bias"][empty_tok] += 6.0
+    checked = suppressed = 0
+    for b in range(B):  # generate.py handles one sequence at a time
+        seq = [int(t) for t in start[:, b]]
+        _, mems = O.generate_logits(start[:-1, b:b + 1], None, params, shape)
+        for t in range(G):
+            lg, mems = O.generate_logits(torch.tensor([[seq[-1]]]), mems, params, shape)
+            sup = k_empty > 0 and all(s == empty_tok for s in seq[-k_empty:])
+            suppressed += int(sup)
+            probs = O.generation_probs(lg[-1, 0], temperature=temperature, technique=technique, topk=topk, p=p,
+                                       exclude_bos=True, suppress_empty=sup, empty_bar_token=empty_tok)
+            tok, margin = O.categorical_from_uniform(probs, float(U[t, b]))
+            got = int(ids[t, b])
+            if margin < 2e-4:  # u within the fp32 model error of a CDF step: either neighbour is a legitimate draw
+                assert probs[got] > 0, (b, t, got)
+            else:
+                assert got == tok, (b, t, got, tok, margin)
+                checked += 1
+            assert got != 0 and not (sup and got == empty_tok)
+            seq.append(got)  # follow the device's sequence: later steps stay comparable
+    assert checked > 0.85 * B * G
+    assert not k_empty or suppressed > 0

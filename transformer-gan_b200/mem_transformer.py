@@ -413,3 +413,49 @@ class MemTransformerLM(nn.Module):
         if status_vec is not None:
             raise NotImplementedError("status_vec / append_note_status is not accelerated")
         return self._run("gumbel", data, None, None, mems, temperature=temperature, noise=noise)
+
+    # ---- batched generation (generate.py:207-304 for a whole batch, sampling on the device) ----------------
+    @torch.no_grad()
+    def generate_batched(self, start_ids, gen_len, *, technique="topk", topk=32, top_p=0.0, temperature=0.95,
+                         exclude_bos=True, empty_token=-1, num_empty_tokens_to_ignore=0, mems=None, uniforms=None):
+        """The generation loop of generate.py:207-304 for ``B`` sequences at once with NO per-token host
+        synchronisation: per step one single-token forward (projected-K/V cache, ``memory_length`` = ``self.mem_len``)
+        and one ``tgan_sample_tokens`` launch (exclude-BOS, empty-bar suppression once the last
+        ``num_empty_tokens_to_ignore`` tokens were all ``empty_token``, temperature, top-k / nucleus / random, one
+        categorical draw per sequence); the sampled ids feed the next step on the device.
+
+        start_ids: int64 [T0, B] -- the conditioning tokens (unconditional generation: one row of BOS ids, :180-186).
+        uniforms:  optional [gen_len, B] uniforms in [0, 1) replacing the device RNG (parity tests).
+        Returns (ids int64 [gen_len, B], mems)."""
+        eng = self._get_engine()
+        dev = eng.device
+        start_ids = start_ids.to(dev)
+        T0, B = start_ids.shape
+        mode = {"random": 0, "topk": 1, "nucleus": 2}[technique]
+        if T0 > 1:  # context pass over all but the last conditioning token (:190-199)
+            _, mems = self._run("logits", start_ids[:-1], None, None, mems)
+        cur = start_ids[-1:].contiguous()
+        out = torch.empty(gen_len, B, dtype=torch.int64, device=dev)
+        k = int(num_empty_tokens_to_ignore)
+        run = suppress = None
+        if k > 0:
+            # length of the run of `empty_token` at the end of each sequence (conditioning tokens included, :235-238)
+            run = torch.zeros(B, dtype=torch.int32, device=dev)
+            for t in range(T0):
+                run = torch.where(start_ids[t] == empty_token, run + 1, torch.zeros_like(run))
+        V = self.n_token
+        for t in range(gen_len):
+            ectx = eng.forward(cur, None, mems, mem_len=self.mem_len, same_length=self.same_length, training=False,
+                               save_for_backward=False)
+            mems = ectx.new_mems
+            if k > 0:
+                suppress = (run >= k).to(torch.uint8)
+            eng.calls += 1
+            L.sample_tokens(ectx.logits, out[t], V, u=None if uniforms is None else uniforms[t].contiguous(),
+                            suppress_empty=suppress, exclude_bos=exclude_bos, empty_token=empty_token, mode=mode,
+                            topk=topk or 0, top_p=top_p, temperature=temperature, seed=eng.seed,
+                            site=eng._site(eng.calls, 5))
+            cur = out[t:t + 1]
+            if k > 0:
+                run = torch.where(out[t] == empty_token, run + 1, torch.zeros_like(run))
+        return out, mems

@@ -14,6 +14,7 @@ and the closed-form backward of all of them.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -399,6 +400,12 @@ class TxlEngine:
             L.unpack_grads(self.gmat, self.gvec, desc, desc.shape[0], self._max_elems, accumulate=accumulate)
         return n or 0
 
+    def _use_side_streams(self, rows: int) -> bool:
+        """Small calls inside a CUDA-graph capture only: launched from the host these calls are enqueue-bound (the GPU
+        idles between kernels anyway) and every stream switch costs host time -- a generation step went from 1.6 to
+        3.2 ms of host work with the forks enabled."""
+        return rows <= self.side_stream_max_rows and torch.cuda.is_current_stream_capturing()
+
     def _side_stream(self, i: int = 0):
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
@@ -569,11 +576,11 @@ class TxlEngine:
             x_base = l * slab_elems
             if use_cache:
                 kv, kv_off = ring.kv["buf"], (l * C + ctx.x_segs[0][0]) * B * 2 * NH
-                side = self._side_stream() if R <= self.side_stream_max_rows else None
+                side = self._side_stream() if self._use_side_streams(R) else None
                 main = torch.cuda.current_stream()
                 if side is not None:  # the K/V projection of the new rows runs beside the Q projection
                     side.wait_stream(main)
-                with torch.cuda.stream(side if side is not None else main):
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                     L.gemm(slabs, self.pmat, kv, M=(w + Q - kv_from) * B, N=2 * NH, K=DP, lda=DP, ldb=wld, ldc=2 * NH,
                            a_off=x_base + kv_from * B * DP, b_off=woff + NH * wld, c_off=(l * C + kv_from) * B * 2 * NH,
                            impl=self.impl)
@@ -693,7 +700,7 @@ class TxlEngine:
         # small calls: weight-gradient GEMMs on the side stream (see side_stream_max_rows); their operands are kept
         # alive in `keep` until the join at the end -- the caching allocator would otherwise hand a freed block to the
         # next allocation on the main stream while the side stream still reads it
-        side = self._side_stream() if (R <= self.side_stream_max_rows and reducer is None) else None
+        side = self._side_stream() if (reducer is None and self._use_side_streams(R)) else None
         main = torch.cuda.current_stream()
         keep = []
 
@@ -706,7 +713,7 @@ class TxlEngine:
             if st is not None:
                 st.wait_stream(main)  # everything enqueued so far (the producers of dY, the zeroing of gm)
                 keep.append((dY, X))
-            with torch.cuda.stream(st if st is not None else main):
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
                 L.gemm(dY, X, gm, transA=True, transB=False, M=n_out, N=k_in, K=rows, lda=ldy, ldb=ldx, ldc=gld,
                        a_off=dy_off, b_off=x_off, c_off=goff + row_off * gld, flags=L.EPI_ACCUM, impl=impl)
 
