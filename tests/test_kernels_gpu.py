@@ -304,3 +304,25 @@ def test_colsum_convert_dropout_pack_adam():
         L.sumsq(g0 * step, 5000, nsq)
         L.adam_step(p, g0 * step, m, v, 5000, 1e-2, 0.9, 0.999, 1e-8, 0.0, step, nsq, 3.0, 1.0)
     assert (p - pr.detach()).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("M,K,N,bias", [(640, 310, 64, False), (512, 1200, 1200, True), (384, 1200, 100, True)])
+def test_nn_linear_forward_backward_match_torch(M, K, N, bias):
+    """tgan_b200.nn.linear (RelGAN_D's dense layers on tgan_gemm: forward, dgrad, wgrad, bias gradient) against
+    F.linear in fp64 on bf16-rounded operands; shapes = the discriminator's three layers (vocabulary 310 -> padded)."""
+    from tgan_b200.nn import linear
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).bfloat16().float().cuda().requires_grad_(True)
+    w = (0.05 * torch.randn(N, K, generator=g)).bfloat16().float().cuda().requires_grad_(True)
+    b = (0.1 * torch.randn(N, generator=g)).cuda().requires_grad_(True) if bias else None
+    y = linear(x, w, b)
+    dy = torch.randn(M, N, generator=g).bfloat16().float().cuda()
+    y.backward(dy)
+    xd, wd = x.detach().double(), w.detach().double()
+    yr = xd @ wd.t() + (b.detach().double() if bias else 0)
+    assert (y.double() - yr).abs().max() < 2e-3 * yr.abs().max()
+    dxr, dwr = dy.double() @ wd, dy.double().t() @ xd
+    assert (x.grad.double() - dxr).abs().max() < 2e-3 * dxr.abs().max()
+    assert (w.grad.double() - dwr).abs().max() < 2e-3 * dwr.abs().max()
+    if bias:
+        assert (b.grad.double() - dy.double().sum(0)).abs().max() < 1e-3 * dy.abs().sum(0).max()

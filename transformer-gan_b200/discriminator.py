@@ -3,8 +3,10 @@
 Reference: ``CNNDiscriminator`` (model/discriminator.py:27-82) and ``RelGAN_D`` (model/transformer_gan.py:44-119), the
 discriminator of ``experiment_cnn.yml``.  Its input is the generator's straight-through one-hot sequence
 ``[batch, seq, vocab]`` written by the fused Gumbel sampler; the body (a bias-free embedding projection, four
-time-convolutions over ``num_rep`` independent representations, max-over-time, highway, two linears) is small
-library work (cuDNN / cuBLAS through torch) -- the hand-written kernels of this package are the generator side.
+time-convolutions over ``num_rep`` independent representations, max-over-time, highway, two linears): in bf16 mode
+its three dense layers (98 % of the FLOPs: embedding projection, the 1200 x 1200 highway layer, feature2out) run on the
+library's tcgen05 GEMM through ``tgan_b200.nn.linear``; the 2..5-tap time convolutions (contraction length <= 5: not
+tensor-core work), ReLU / max-over-time and the 100 -> 1 output layer are torch.
 """
 import math
 
@@ -77,9 +79,20 @@ class RelGAN_D(CNNDiscriminator):
         self.dropout = nn.Dropout(dropout)
         self.init_params()
 
+    # set by TransformerGAN in bf16 mode when no gradient penalty (= no double backward) is configured: the three
+    # dense layers run on the library's tcgen05 GEMM (tgan_b200.nn.linear) instead of cuBLAS
+    own_gemm = False
+
+    def _lin(self, layer, x):
+        if self.own_gemm and x.is_cuda:
+            from tgan_b200.nn import linear
+            return linear(x, layer.weight, layer.bias)
+        return layer(x)
+
     def forward(self, inp):
-        emb = self.embeddings(inp).unsqueeze(1)                       # [B, 1, T, embed_dim]
+        B, T, V = inp.shape
+        emb = self._lin(self.embeddings, inp.reshape(B * T, V)).view(B, 1, T, self.embed_dim)  # [B, 1, T, embed_dim]
         pooled = [F.relu(conv(emb)).amax(dim=2) for conv in self.convs]  # each [B, filters, num_rep]
         feat = torch.cat(pooled, 1).permute(0, 2, 1).reshape(-1, self.feature_dim)  # [(B * num_rep), feature_dim]
-        feat = self._highway(self.highway(feat), feat)
-        return self.out2logits(self.feature2out(self.dropout(feat))).squeeze(1)
+        feat = self._highway(self._lin(self.highway, feat), feat)
+        return self.out2logits(self._lin(self.feature2out, self.dropout(feat))).squeeze(1)

@@ -18,7 +18,8 @@ What runs where
     graph: d/dtheta ||grad_x D|| only involves the encoder through one Jacobian-vector product.  Only the 592 k-parameter
     head stays in torch.  Any other trainable set falls back to HuggingFace ``BertForSequenceClassification``
     (third-party in the reference as well, transformer_gan.py:23-30 / requirements.sh:12) with eager attention so that
-    autograd's double backward works.  The CNN ``RelGAN_D`` (discriminator.py) is library conv / GEMM work.
+    autograd's double backward works.  The CNN ``RelGAN_D`` (discriminator.py) runs its dense layers on ``tgan_gemm`` in bf16
+    mode (time convolutions / pooling: torch).
 Differences from the reference, all numerically neutral:
   * in ``"dis_loss"`` mode the sampling loop runs under ``no_grad`` (the reference builds the 123-step graph and then
     detaches it, :346-347);
@@ -78,6 +79,7 @@ class TransformerGAN(nn.Module):
         self.disc_tf32 = True  # TF32 tensor-core GEMMs for the discriminator when the generator computes in bf16
         self.use_own_bert = True   # frozen-encoder BERT discriminator on the repo's kernels (else: HuggingFace modules)
         self._bert_engine = None
+        self.use_own_cnn_gemm = True  # RelGAN_D's dense layers on tgan_gemm in bf16 mode (see discriminator.py)
 
     # ------------------------------------------------------------------------------------------------ discriminator
     def create_bert_model(self, model_name_or_path, loss_type, model_type=None, random_weights=False):
@@ -296,6 +298,10 @@ class TransformerGAN(nn.Module):
         self._update_D0 = bool(update_D0)
         # In bf16 mode the discriminator's GEMMs (HuggingFace BERT / RelGAN_D: library code, fp32 tensors) run on the
         # tensor cores as TF32 -- more mantissa than the generator's own bf16 operands; fp32 mode keeps them exact.
+        if isinstance(self.discriminator, RelGAN_D):
+            # bf16 mode without a gradient penalty (its double backward needs torch's differentiable backward)
+            self.discriminator.own_gemm = bool(self.use_own_cnn_gemm and gen_is_bf16(self.generator) and
+                                               "gp" not in self.cfg.DISCRIMINATOR.CNN.loss_type)
         tf32 = self.disc_tf32 and gen_is_bf16(self.generator)
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev_tf32
