@@ -10,6 +10,8 @@
 // embeddings) theta sits behind the encoder, so that derivative is J_enc applied to a direction = one JVP pass; no
 // double-backward graph is ever built.  The dense layers run on tgan_gemm (tcgen05); everything here is HBM- or
 // latency-bound glue plus the 64 x 64 attention tiles (3 % of the encoder's FLOPs).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -214,19 +216,27 @@ bert_attn_fwd_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ ctx
     store_acc(sS, acc, a.scale);
     __syncthreads();
     const uint32_t key = step_fold(a.key);
-    if (threadIdx.x < AT) {  // one thread per query row: softmax + dropout in place
-        const int i = threadIdx.x;
+    {   // 4 threads per query row (adjacent lanes), 16 columns each: softmax + dropout in place.  (One thread per row
+        // left 192 of the 256 threads idle through the longest dependent chain of the kernel.)
+        const int i = threadIdx.x >> 2, part = threadIdx.x & 3, j0 = part * 16, j1 = min(j0 + 16, a.T);
         float* row = sS + i * ALD;
-        if (i < a.T) {
-            float m = -INFINITY;
-            for (int j = 0; j < a.T; ++j) m = fmaxf(m, row[j]);
-            float l = 0.f;
-            for (int j = 0; j < a.T; ++j) { const float e = __expf(row[j] - m); row[j] = e; l += e; }
+        const bool live = i < a.T;
+        float m = -INFINITY;
+        if (live)
+            for (int j = j0; j < j1; ++j) m = fmaxf(m, row[j]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float l = 0.f;
+        if (live)
+            for (int j = j0; j < j1; ++j) { const float e = __expf(row[j] - m); row[j] = e; l += e; }
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        if (live) {
             const float inv = 1.f / l;
-            for (int j = 0; j < a.T; ++j) row[j] = bert_keep(a, key, bh, i, j) ? row[j] * inv * a.drop_scale : 0.f;
-            lse[(int64_t)bh * a.T + i] = m + __logf(l);
+            for (int j = j0; j < j1; ++j) row[j] = bert_keep(a, key, bh, i, j) ? row[j] * inv * a.drop_scale : 0.f;
+            if (part == 0) lse[(int64_t)bh * a.T + i] = m + __logf(l);
         }
-        for (int j = (i < a.T ? a.T : 0); j < AT; ++j) row[j] = 0.f;
+        for (int j = max(j0, live ? a.T : 0); j < j0 + 16; ++j) row[j] = 0.f;
     }
     __syncthreads();
     zero_acc(acc);
@@ -270,25 +280,28 @@ bert_attn_bwd_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict
     probs_from_lse(sS, s_lse, a.T);
     __syncthreads();
     const uint32_t key = step_fold(a.key);
-    if (threadIdx.x < AT) {  // per row: delta = sum_j P~ dP~ ; then sD := dS, sS := P~
-        const int i = threadIdx.x;
+    {   // 4 threads per row: delta = sum_j P~ dP~ ; then sD := dS, sS := P~
+        const int i = threadIdx.x >> 2, part = threadIdx.x & 3, j0 = part * 16, j1 = min(j0 + 16, a.T);
         float* p = sS + i * ALD;
         float* d = sD + i * ALD;
+        const bool live = i < a.T;
         float delta = 0.f;
-        if (i < a.T) {
-            for (int j = 0; j < a.T; ++j) {
+        if (live)
+            for (int j = j0; j < j1; ++j) {
                 const bool keep = bert_keep(a, key, bh, i, j);
                 const float dpk = keep ? d[j] * a.drop_scale : 0.f;   // gradient w.r.t. the un-dropped probability
                 delta += p[j] * dpk;
                 d[j] = dpk;
             }
-            for (int j = 0; j < a.T; ++j) {
+        delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+        if (live)
+            for (int j = j0; j < j1; ++j) {
                 const float pj = p[j];
                 const bool keep = bert_keep(a, key, bh, i, j);
                 d[j] = pj * (d[j] - delta);
                 p[j] = keep ? pj * a.drop_scale : 0.f;
             }
-        }
     }
     __syncthreads();
     T* obase = dqkv + (int64_t)b * a.T * lddq + h * a.dh;
@@ -335,21 +348,24 @@ bert_attn_jvp_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict
     probs_from_lse(sS, s_lse, a.T);
     __syncthreads();
     const uint32_t key = step_fold(a.key);
-    if (threadIdx.x < AT) {  // per row: sSd := drop(Pd), sS := drop(P)
-        const int i = threadIdx.x;
+    {   // 4 threads per row: sSd := drop(Pd), sS := drop(P)
+        const int i = threadIdx.x >> 2, part = threadIdx.x & 3, j0 = part * 16, j1 = min(j0 + 16, a.T);
         float* p = sS + i * ALD;
         float* d = sSd + i * ALD;
-        if (i < a.T) {
-            float dot = 0.f;
-            for (int j = 0; j < a.T; ++j) dot += p[j] * d[j];
-            for (int j = 0; j < a.T; ++j) {
+        const bool live = i < a.T;
+        float dot = 0.f;
+        if (live)
+            for (int j = j0; j < j1; ++j) dot += p[j] * d[j];
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        if (live)
+            for (int j = j0; j < j1; ++j) {
                 const float m = bert_keep(a, key, bh, i, j) ? a.drop_scale : 0.f;
                 const float pj = p[j];
                 d[j] = pj * (d[j] - dot) * m;
                 p[j] = pj * m;
             }
-        }
-        for (int j = (i < a.T ? a.T : 0); j < AT; ++j) d[j] = 0.f;
+        for (int j = max(j0, live ? a.T : 0); j < j0 + 16; ++j) d[j] = 0.f;
     }
     __syncthreads();
     zero_acc(acc);
@@ -428,6 +444,13 @@ extern "C" int tgan_ln_jvp(int dtype, const float* zd, int64_t ldzd, const float
     return 0;
 }
 
+// bf16 tiles with d_head a multiple of 16 and 16-byte aligned rows run on the tensor cores (bert_attn_mma.cu)
+static bool mma_ok(int dtype, int dh, int64_t ld0, int64_t ld1, int64_t ld2, const void* p0, const void* p1, const void* p2) {
+    static const bool off = getenv("TGAN_BERT_ATTN_SIMT") != nullptr;
+    return !off && dtype == TGAN_BF16 && dh % 16 == 0 && ld0 % 8 == 0 && ld1 % 8 == 0 && ld2 % 8 == 0 &&
+           ((((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) == 0);
+}
+
 static int check_attn(int T, int dh, int64_t ldq, const char* who) {
     if (!(T >= 1 && T <= AT && dh >= 8 && dh <= AT && dh % 8 == 0 && ldq % 8 == 0)) {
         tgan_set_error("%s: needs 1 <= T <= 64 tokens, d_head a multiple of 8 <= 64, ld multiples of 8", who);
@@ -439,6 +462,8 @@ static int check_attn(int T, int dh, int64_t ldq, const char* who) {
 extern "C" int tgan_bert_attn_fwd(int dtype, const void* qkv, int64_t ldq, void* ctx, int64_t ldc, float* lse, int B,
                                   int heads, int T, int dh, float drop_p, uint64_t seed, uint64_t site, void* stream) {
     if (check_attn(T, dh, ldq, "tgan_bert_attn_fwd")) return 1;
+    if (mma_ok(dtype, dh, ldq, ldc, 8, qkv, ctx, nullptr))
+        return tgan_bert_attn_fwd_mma(qkv, ldq, ctx, ldc, lse, B, heads, T, dh, drop_p, seed, site, ST);
     BertAttnArgs a = make_bargs(B, heads, T, dh, drop_p, seed, site);
     const int smem = 4 * AT * ALD * sizeof(float);
     if (dtype == TGAN_F32) TGAN_CUDA_OK((cudaError_t)set_smem(bert_attn_fwd_kernel<float>, smem));
@@ -453,6 +478,8 @@ extern "C" int tgan_bert_attn_bwd(int dtype, const void* qkv, int64_t ldq, const
                                   void* dqkv, int64_t lddq, int B, int heads, int T, int dh, float drop_p, uint64_t seed,
                                   uint64_t site, void* stream) {
     if (check_attn(T, dh, ldq, "tgan_bert_attn_bwd")) return 1;
+    if (mma_ok(dtype, dh, ldq, ldc, lddq, qkv, dctx, dqkv))
+        return tgan_bert_attn_bwd_mma(qkv, ldq, dctx, ldc, lse, dqkv, lddq, B, heads, T, dh, drop_p, seed, site, ST);
     BertAttnArgs a = make_bargs(B, heads, T, dh, drop_p, seed, site);
     const int smem = 6 * AT * ALD * sizeof(float);
     if (dtype == TGAN_F32) TGAN_CUDA_OK((cudaError_t)set_smem(bert_attn_bwd_kernel<float>, smem));
@@ -468,6 +495,8 @@ extern "C" int tgan_bert_attn_jvp(int dtype, const void* qkv, int64_t ldq, const
                                   void* ctxd, int64_t ldc, int B, int heads, int T, int dh, float drop_p, uint64_t seed,
                                   uint64_t site, void* stream) {
     if (check_attn(T, dh, ldq, "tgan_bert_attn_jvp")) return 1;
+    if (mma_ok(dtype, dh, ldq, ldqd, ldc, qkv, qkvd, ctxd))
+        return tgan_bert_attn_jvp_mma(qkv, ldq, qkvd, ldqd, lse, ctxd, ldc, B, heads, T, dh, drop_p, seed, site, ST);
     BertAttnArgs a = make_bargs(B, heads, T, dh, drop_p, seed, site);
     const int smem = 8 * AT * ALD * sizeof(float);
     if (dtype == TGAN_F32) TGAN_CUDA_OK((cudaError_t)set_smem(bert_attn_jvp_kernel<float>, smem));

@@ -239,6 +239,15 @@ int tgan_relattn_bwd_decode1(int dtype, const void* q, int64_t ldq, const void* 
                              void* dk, void* dv, int64_t lddkv, float* dr, int64_t lddr, float* du, float* dvb, int B,
                              int N, int M, int msl, int same_length, float scale, float drop_p, uint64_t seed,
                              uint64_t site, cudaStream_t st, int phase);
+// BERT attention tiles on mma.sync (bert_attn_mma.cu): bf16, T <= 64, d_head a multiple of 16 <= 64
+int tgan_bert_attn_fwd_mma(const void* qkv, int64_t ldq, void* ctx, int64_t ldc, float* lse, int B, int heads, int T, int dh,
+                           float drop_p, uint64_t seed, uint64_t site, cudaStream_t st);
+int tgan_bert_attn_bwd_mma(const void* qkv, int64_t ldq, const void* dctx, int64_t ldc, const float* lse, void* dqkv,
+                           int64_t lddq, int B, int heads, int T, int dh, float drop_p, uint64_t seed, uint64_t site,
+                           cudaStream_t st);
+int tgan_bert_attn_jvp_mma(const void* qkv, int64_t ldq, const void* qkvd, int64_t ldqd, const float* lse, void* ctxd,
+                           int64_t ldc, int B, int heads, int T, int dh, float drop_p, uint64_t seed, uint64_t site,
+                           cudaStream_t st);
 // tcgen05 attention (bf16 only); return -1 when the shape is not eligible
 int tgan_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const void* r,
                         int64_t ldr, const float* u, const float* vb, const uint8_t* reset, void* out, int64_t ldo,
