@@ -292,6 +292,7 @@ class TxlEngine:
         self.side_stream_max_rows = 8192
         self._side = None
         self._window = None        # open gradient window: number of backward calls accumulated so far
+        self._late = None          # (side event, side2 event, buffers) of the previous single-token backward in the window
 
     # -- parameters ---------------------------------------------------------------------------------------
     def bind_params(self, params: Dict[str, torch.Tensor]):
@@ -395,6 +396,12 @@ class TxlEngine:
         """Unpack what the window accumulated into ``grad_targets`` (+= when ``accumulate``); returns the number of
         backward calls it covered (0: nothing to unpack)."""
         n, self._window = self._window, None
+        if self._late is not None:  # join the side streams of the window's last backward call
+            main = torch.cuda.current_stream()
+            main.wait_event(self._late[0])
+            main.wait_event(self._late[1])
+            self._late[2].clear()
+            self._late = None
         if n:
             desc = self._unpack_desc_for(grad_targets)
             L.unpack_grads(self.gmat, self.gvec, desc, desc.shape[0], self._max_elems, accumulate=accumulate)
@@ -810,20 +817,36 @@ class TxlEngine:
                 v0, v1 = lay.vec[p + "b1"][0], lay.vec[p + "ln2_b"][0] + lay.vec[p + "ln2_b"][1]
                 reducer.reduce(gm, m0, m1 - m0)
                 reducer.reduce(gv, v0, v1 - v0)
-        if side is not None:
+        # Late join (inside a gradient window, single-token calls): nothing the main stream does from here to the end of
+        # the window needs the side streams' results -- the r_net weight gradient below moves to the memory-side stream,
+        # where dR is produced -- so the join with THIS call's side work is deferred by one call (its buffers are kept
+        # alive until then): the last layer's memory-side tail (~90 us) overlaps the head of the next token's backward
+        # instead of idling the main stream.  end_grad_window() joins the last one.
+        late = side is not None and self._window is not None and Q == 1
+        if side is not None and not late:
             main.wait_stream(side)
             if Q == 1:  # (a stream that never forked from a capturing stream must not be joined into the capture)
                 main.wait_stream(side2)
             keep.clear()
         # ---- r_net weight gradients of all layers: dWr_all = dR_all^T pos_emb
         NL = d.n_layer * NH
-        if dt == torch.float32:
-            dr_all = dr_all32
-        else:
-            dr_all = self._buf(K, NL)
-            L.convert(dr_all32, NL, dr_all, NL, K, NL, NL)
-        L.gemm(dr_all, ctx.pe, gm, transA=True, transB=False, M=NL, N=DP, K=K, lda=NL, ldb=DP, ldc=DP,
-               c_off=lay.gmat["l0.Wr"][0], flags=L.EPI_ACCUM, impl=impl)
+        if late:
+            side2.wait_stream(main)
+        with (torch.cuda.stream(side2) if late else contextlib.nullcontext()):
+            if dt == torch.float32:
+                dr_all = dr_all32
+            else:
+                dr_all = self._buf(K, NL)
+                L.convert(dr_all32, NL, dr_all, NL, K, NL, NL)
+            L.gemm(dr_all, ctx.pe, gm, transA=True, transB=False, M=NL, N=DP, K=K, lda=NL, ldb=DP, ldc=DP,
+                   c_off=lay.gmat["l0.Wr"][0], flags=L.EPI_ACCUM, impl=impl)
+        if late:
+            keep.append((dr_all, dr_all32, ctx.pe, ctx.layers, ctx.soft))
+            prev, self._late = self._late, (side.record_event(), side2.record_event(), keep)
+            if prev is not None:
+                main.wait_event(prev[0])
+                main.wait_event(prev[1])
+                prev[2].clear()
         # ---- embedding
         out: Dict[str, torch.Tensor] = {}
         goff, _, gld = lay.gmat["E"]
