@@ -578,7 +578,9 @@ class TxlEngine:
             p = f"l{l}."
             sv = _Ctx()
             woff, wld = self._m(p + "Wqkv")
-            q = self._buf(R, NH)
+            # single-token calls: q (and, in the backward, dq) are the first third of [R, 3 * NH] rows -- the backward then
+            # has dq | dk | dv of the current position side by side and needs ONE dgrad / wgrad GEMM for them
+            q = self._buf(R, 3 * NH)[:, :NH] if Q == 1 else self._buf(R, NH)
             r = r_all[:, l * NH:(l + 1) * NH]  # view: row pitch n_layer * NH
             x_base = l * slab_elems
             if use_cache:
@@ -776,7 +778,9 @@ class TxlEngine:
             datt = self._buf(R, NH)
             L.gemm(g1, self.pmat, datt, M=R, N=NH, K=DP, ldb=wotld, b_off=wotoff, impl=impl)
             # attention core backward
-            dq = self._buf(R, NH)
+            qp = sv.q.stride(0)  # the kernels address dq with q's row pitch (3 * NH for single-token calls)
+            dq3 = self._buf(R, qp)
+            dq = dq3[:, :NH]
             dkv = self._buf(KR, 2 * NH)
             dr32 = dr_all32[:, l * NH:(l + 1) * NH]  # view: this layer's column block
             split = side is not None and Q == 1  # single-token step: memory-side half on the second side stream
@@ -784,34 +788,53 @@ class TxlEngine:
             delta = self._buf(B * d.n_head * (Q if Q > 1 else (2 * K if split else K)) + (2 * B * NH if split else 0),
                               dtype=torch.float32)
             if split:
-                args = (sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt, sv.lse,
-                        delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, M, ctx.msl,
-                        ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l))
-                kw = dict(k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
-                L.relattn_bwd_step(1, *args, **kw)
+                head = (sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt, sv.lse,
+                        delta, dq)
+                tail = (dr32, self._gv("u"), self._gv("vb"), B, d.n_head, M, ctx.msl, ctx.same_length, scale, p_att, seed,
+                        self._site(cid, 8 + 4 * l))
+                # query side: dk / dv of the current position (key row M) land in dq3[:, NH:3NH] -- the kernel addresses
+                # key row j at dk + (j * B + b) * lddkv, so the base is shifted back by M rows of the 3 * NH pitch
+                back = M * B * 3 * NH
+                L.relattn_bwd_step(1, *head, dq3, dq3, 3 * NH, *tail, k_off=sv.kv_off, v_off=sv.kv_off + NH,
+                                   dk_off=NH - back, dv_off=2 * NH - back)
                 side2.wait_stream(main)
-                with torch.cuda.stream(side2):
-                    L.relattn_bwd_step(2, *args, **kw)
-                keep.append((delta, dq, dkv, datt))
+                with torch.cuda.stream(side2):  # memory side: rows j < M of dkv, dR, bias sums
+                    L.relattn_bwd_step(2, *head, dkv, dkv, 2 * NH, *tail, k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
+                keep.append((delta, dq3, dkv, datt))
             else:
                 L.relattn_bwd(sv.q, sv.kv, sv.kv, 2 * NH, sv.r, self._v("u"), self._v("vb"), ctx.reset, sv.att, datt,
                               sv.lse, delta, dq, dkv, dkv, 2 * NH, dr32, self._gv("u"), self._gv("vb"), B, d.n_head, Q, M,
                               ctx.msl, ctx.same_length, scale, p_att, seed, self._site(cid, 8 + 4 * l), impl=impl,
                               k_off=sv.kv_off, v_off=sv.kv_off + NH, dv_off=NH)
-            wgrad(p + "Wqkv", dq, slabs, R, NH, DP, ldy=NH, ldx=DP, x_off=cur_off[l])
-            row = 0
-            for pos, n in ctx.x_segs:
-                wgrad(p + "Wqkv", dkv, slabs, n * B, 2 * NH, DP, ldy=2 * NH, ldx=DP, dy_off=row * B * 2 * NH,
-                      x_off=x_base + pos * B * DP, row_off=NH, stream=side2 if split else None)
-                row += n
-            # dx_l = dz1 + dq Wq + dkv[current rows] Wkv
             wtoff, wtld = self._m(p + "Wqkv.T")
-            t = self._buf(R, DP)
-            L.gemm(dq, self.pmat, t, M=R, N=DP, K=NH, ldb=wtld, b_off=wtoff, aux=dz1, ldaux=DP, flags=L.EPI_ADD_AUX,
-                   impl=impl)
-            dx = self._buf(R, DP)
-            L.gemm(dkv, self.pmat, dx, M=R, N=DP, K=2 * NH, lda=2 * NH, ldb=wtld, a_off=M * B * 2 * NH,
-                   b_off=wtoff + NH, aux=t, ldaux=DP, flags=L.EPI_ADD_AUX, impl=impl)
+            if split:
+                # [dq | dk | dv] of the current position: one weight-gradient GEMM for all of Wqkv ...
+                wgrad(p + "Wqkv", dq3, slabs, R, 3 * NH, DP, ldy=3 * NH, ldx=DP, x_off=cur_off[l])
+                row, left = 0, M  # ... the memory rows (behind the memory-side kernels on their stream) ...
+                for pos, n in ctx.x_segs:
+                    n = min(n, left)
+                    if n > 0:
+                        wgrad(p + "Wqkv", dkv, slabs, n * B, 2 * NH, DP, ldy=2 * NH, ldx=DP, dy_off=row * B * 2 * NH,
+                              x_off=x_base + pos * B * DP, row_off=NH, stream=side2)
+                    row, left = row + n, left - n
+                # ... and one dgrad GEMM: dx_l = dz1 + [dq | dk | dv] Wqkv
+                dx = self._buf(R, DP)
+                L.gemm(dq3, self.pmat, dx, M=R, N=DP, K=3 * NH, ldb=wtld, b_off=wtoff, aux=dz1, ldaux=DP,
+                       flags=L.EPI_ADD_AUX, impl=impl)
+            else:
+                wgrad(p + "Wqkv", dq3, slabs, R, NH, DP, ldy=qp, ldx=DP, x_off=cur_off[l])
+                row = 0
+                for pos, n in ctx.x_segs:
+                    wgrad(p + "Wqkv", dkv, slabs, n * B, 2 * NH, DP, ldy=2 * NH, ldx=DP, dy_off=row * B * 2 * NH,
+                          x_off=x_base + pos * B * DP, row_off=NH)
+                    row += n
+                # dx_l = dz1 + dq Wq + dkv[current rows] Wkv
+                t = self._buf(R, DP)
+                L.gemm(dq, self.pmat, t, M=R, N=DP, K=NH, ldb=wtld, b_off=wtoff, aux=dz1, ldaux=DP, flags=L.EPI_ADD_AUX,
+                       impl=impl)
+                dx = self._buf(R, DP)
+                L.gemm(dkv, self.pmat, dx, M=R, N=DP, K=2 * NH, lda=2 * NH, ldb=wtld, a_off=M * B * 2 * NH,
+                       b_off=wtoff + NH, aux=t, ldaux=DP, flags=L.EPI_ADD_AUX, impl=impl)
             if reducer is not None:  # this layer's weight / bias / LayerNorm gradients are final: exchange them now
                 m0, m1 = lay.gmat[p + "Wqkv"][0], lay.gmat[p + "W2"][0] + lay.gmat[p + "W2"][1] * lay.gmat[p + "W2"][2]
                 v0, v1 = lay.vec[p + "b1"][0], lay.vec[p + "ln2_b"][0] + lay.vec[p + "ln2_b"][1]
