@@ -98,8 +98,14 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(int M, int N, int K, cons
                 v = dropout_keep_k(step_fold(ep.drop_key), (uint64_t)gm * ldc + gn, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
             }
             TC* cp = C + (int64_t)gm * ldc + gn;
-            if (flags & TGAN_EPI_ACCUM) v += to_f(*cp);
-            *cp = from_f<TC>(v);
+            if constexpr (sizeof(TC) == 4) {
+                // fp32 accumulation is a reduction: weight-gradient GEMMs of concurrent streams may target the same rows
+                if (flags & TGAN_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(cp), v);
+                else *cp = from_f<TC>(v);
+            } else {
+                if (flags & TGAN_EPI_ACCUM) v += to_f(*cp);
+                *cp = from_f<TC>(v);
+            }
         }
     }
 }

@@ -878,6 +878,11 @@ int tgan_gemm_tc(int dtype_c, int transA, int transB, int M, int N, int K, const
         if (rc) return rc;
         ep.flags |= EPI_TMA;
     }
+    // fp32 accumulation without the TMA reduce path (unaligned C): atomics, so that it stays a reduction -- accumulating
+    // GEMMs of concurrent streams may target the same rows (engine.py: weight gradients on side streams)
+    if (!(ep.flags & EPI_TMA) && (ep.flags & TGAN_EPI_ACCUM) && dtype_c == TGAN_F32 &&
+        (ep.flags & ~(TGAN_EPI_ACCUM | TGAN_EPI_AUX_F32 | EPI_VEC | EPI_BIAS_VEC)) == 0)
+        ep.flags = (ep.flags & ~TGAN_EPI_ACCUM) | EPI_ATOMIC;
     // compile-time epilogue variant: whole 8-column groups, aligned bias, bf16 aux
     int epi_ct = -1;
     if ((ep.flags & EPI_TMA) && N % 8 == 0 && !ep.aux_is_f32 && (!(ep.flags & TGAN_EPI_BIAS) || (ep.flags & EPI_BIAS_VEC)) &&
