@@ -20,7 +20,7 @@ void tgan_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 extern "C" const char* tgan_last_error(void) { return g_err; }
-extern "C" int tgan_version(void) { return 100; }
+extern "C" int tgan_version(void) { return 200; }  // 2xx: round-2 surface (split single-token backward, BERT ops, sampling, batching, LAMB, NCCL buckets)
 extern "C" unsigned long long tgan_launch_count(void) { return g_tgan_launches; }
 extern "C" int tgan_set_step_counter(const void* dev_u32) {
     int rc = tgan_set_step_ctr_local(dev_u32);
