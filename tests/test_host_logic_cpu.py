@@ -78,3 +78,30 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_lamb_chunk_table_covers_every_tensor_exactly_once():
+    """FusedLamb cuts the flat parameter buffer into per-tensor chunks of <= 16384 elements (host logic, no kernel)."""
+    import torch
+    from tgan_b200 import dp
+    ps = [torch.nn.Parameter(torch.zeros(7, 5)), torch.nn.Parameter(torch.zeros(40000)), torch.nn.Parameter(torch.zeros(3))]
+    fp = dp.FlatParams(ps)
+    opt = dp.FusedLamb(fp, 0.01)
+    rows = opt.chunks.tolist()
+    covered = torch.zeros(fp.numel(), dtype=torch.int32)
+    for tid, off, cnt in rows:
+        assert 0 < cnt <= dp.FusedLamb.CHUNK
+        lo, n = fp.slices[tid]
+        assert lo <= off and off + cnt <= lo + n
+        covered[off:off + cnt] += 1
+    assert bool((covered == 1).all())
+    assert opt.norms.numel() == 2 * len(ps)
+
+
+def test_device_dataset_refuses_cpu_and_unsupported_modes():
+    import pytest
+    from tgan_b200 import data, lib
+    with pytest.raises(lib.TganError):
+        data.DeviceSplit([[0, 5, 6]], "cpu")
+    with pytest.raises(NotImplementedError):
+        data.DeviceMusicDataset({}, 1, "cpu", random_crop=True)
