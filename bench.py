@@ -11,8 +11,10 @@ BASELINE.json's metric is "train tokens/sec (GAN step)".  A "step" is one iterat
 123 Gumbel-softmax sampling steps, BERT 5x768 discriminator on real / fake, WGAN-GP) and one generator update
 ("gen_loss": the same sampling chain with gradient, discriminator forward / backward to the samples).  Tokens counted
 = the MLE target tokens, exactly what train.py logs (train.py:906, 1158-1163).  K should be a multiple of 5 (whole
-cycles); the timed region starts on a cycle boundary.  `extras.mle_only` keeps round 1's headline (the MLE step of
-experiment_baseline.yml alone).
+cycles); the timed region starts on a cycle boundary.  `extras` (N = 1, own process): `mle_only` keeps round 1's headline
+(the MLE step of experiment_baseline.yml alone), `gan_phases` the ms per adversarial update, `generate` BASELINE config 5
+(batched generation against a full 4146-position memory with on-device sampling), `eager_gpu_bar` the reference's
+algorithm run eagerly on the same GPU.
 
 One process per GPU.  N > 1 is data parallel over sequences: every rank runs the configuration's batch (512 sequences
 per GPU: WEAK scaling, global batch 512 x N; `--scaling strong` keeps the global batch at 512 and divides it as

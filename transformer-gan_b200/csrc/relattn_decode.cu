@@ -13,6 +13,10 @@
 //   * forward: one pass over K, R, V.  Backward (fused, replaces the three generic passes rows / keys / rel that each
 //     recomputed the scores): one pass over K, R, V producing dq, dk, dv and dS; dR (a reduction over the BATCH) is a
 //     second tiny kernel over the dS scratch instead of B*N*K*64 global atomics.
+//   * split backward (tgan_relattn_bwd_step, used by the captured sampling chain): the pass over K, R, V produces only
+//     what the dgrad chain needs (dq, dk / dv of the current position) plus warp-contiguous scratch rows (dS, P~, the
+//     per-sequence bias-gradient parts); dk / dv of the detached memory rows (pure outer products of the scratch), dR
+//     and the bias sums are separate kernels that the host puts on a side stream.
 // Dropout masks come from the same stateless hash as every other attention kernel (common.cuh: attn_drop_keep).
 #include "common.cuh"
 
