@@ -195,3 +195,94 @@ class FusedLamb:
         n = self.norms.view(-1, 2).sqrt()
         wn, un = n[:, 0].clamp(0, 10), n[:, 1]
         return torch.where((wn == 0) | (un == 0), torch.ones_like(wn), wn / (un + self.eps))
+
+
+class Lamb(torch.optim.Optimizer):
+    """Drop-in for the reference's ``lamb.Lamb`` (lamb.py:21-118: same constructor, ``param_groups``, ``state`` entries
+    ``step`` / ``exp_avg`` / ``exp_avg_sq`` / ``weight_norm`` / ``adam_norm`` / ``trust_ratio``) whose ``step()`` is the
+    fused kernel pair (``tgan_lamb_step``) instead of ~10 small torch kernels per tensor.
+
+    A trainer keeps its own objects -- ``optimizer = Lamb(model.generator.parameters(), lr=..)``, ``clip_grad_norm_``,
+    LR schedulers writing ``param_groups[i]['lr']``, ``zero_grad()``, ``state_dict()`` -- (train.py:396-398, 914-921).  On
+    the first step the parameters of a group that carry a gradient are moved into one flat buffer (they become views of
+    it, as with ``FlatParams``); the moments live in flat buffers too and ``state[p]['exp_avg']`` etc. are views of them.
+    Gradients are gathered with one multi-tensor copy per step (``zero_grad()`` drops the ``.grad`` tensors, so they
+    cannot be aliased permanently).  Parameters without a gradient are skipped exactly as the reference skips them.
+    To run the unmodified train.py on it: ``sys.modules['lamb'] = tgan_b200.dp`` before train.py imports ``lamb``.
+    CUDA only."""
+
+    CHUNK = FusedLamb.CHUNK
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0, adam=False):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameters: {}".format(betas))
+        self.adam = adam
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._flat = {}  # group index -> dict(key, params, flat, grad, m, v, upd, chunks, norms, slices)
+
+    def _build(self, gi, ps):
+        from . import lib as L
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise L.TganError("tgan_b200.dp.Lamb runs on CUDA only (no host fallback)")
+        n = sum(p.numel() for p in ps)
+        f = dict(key=tuple(id(p) for p in ps), params=ps, flat=torch.empty(n, dtype=torch.float32, device=dev),
+                 grad=torch.empty(n, dtype=torch.float32, device=dev), m=torch.zeros(n, dtype=torch.float32, device=dev),
+                 v=torch.zeros(n, dtype=torch.float32, device=dev), upd=torch.empty(n, dtype=torch.float32, device=dev))
+        off, rows, f["slices"] = 0, [], []
+        for tid, p in enumerate(ps):
+            k = p.numel()
+            f["flat"][off:off + k].copy_(p.data.reshape(-1))
+            p.data = f["flat"][off:off + k].view_as(p)
+            st = self.state[p]
+            for name, buf in (("exp_avg", f["m"]), ("exp_avg_sq", f["v"])):
+                view = buf[off:off + k].view_as(p)
+                if name in st:  # moments from an earlier layout / a loaded state_dict are carried over
+                    view.copy_(st[name])
+                st[name] = view
+            st.setdefault("step", 0)
+            f["slices"].append((off, k))
+            for c0 in range(0, k, self.CHUNK):
+                rows.append([tid, off + c0, min(self.CHUNK, k - c0)])
+            off += k
+        f["chunks"] = torch.tensor(rows, dtype=torch.int64, device=dev)
+        f["norms"] = torch.zeros(2 * len(ps), dtype=torch.float32, device=dev)
+        f["grad_views"] = [f["grad"][o:o + k].view_as(p) for p, (o, k) in zip(ps, f["slices"])]
+        self._flat[gi] = f
+        return f
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import lib as L
+        from .engine import notify_params_updated
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            f = self._flat.get(gi)
+            if f is None or f["key"] != tuple(id(p) for p in ps) or \
+                    any(self.state[p].get("exp_avg") is None or
+                        self.state[p]["exp_avg"].data_ptr() != f["m"].data_ptr() + 4 * o
+                        for p, (o, _) in zip(ps, f["slices"])):
+                f = self._build(gi, ps)  # first step, a changed set of trained tensors, or a loaded state_dict
+            torch._foreach_copy_(f["grad_views"], [p.grad for p in ps])
+            L.lamb_step(f["flat"], f["grad"], f["m"], f["v"], f["upd"], f["chunks"], f["chunks"].shape[0], f["norms"],
+                        len(ps), group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"],
+                        None, 0.0, 1.0, adam=self.adam)
+            nr = f["norms"].view(-1, 2).sqrt()
+            wn, an = nr[:, 0].clamp(0, 10), nr[:, 1]
+            tr = torch.where((wn == 0) | (an == 0), torch.ones_like(wn), wn / (an + group["eps"]))
+            for i, p in enumerate(ps):  # device scalars (views): no host synchronisation
+                st = self.state[p]
+                st["step"] += 1
+                st["weight_norm"], st["adam_norm"], st["trust_ratio"] = wn[i], an[i], tr[i]
+        notify_params_updated()
+        return loss
